@@ -1,0 +1,83 @@
+/*
+ * uhdr_b200.h -- extensions of libuhdr_b200 beyond the reference C API: stage-level entry points
+ * (the reference exposes these only as C++ members of ultrahdr::JpegR / UltraHdr), batch encode
+ * and the LUT install hook used for the multi-GPU NCCL broadcast.  Plain C ABI: pointers, sizes,
+ * PODs; no torch / CUDA types.  Return value: a uhdr_codec_err_t (0 = UHDR_CODEC_OK); on failure
+ * uhdr_b200_last_error() returns a thread-local message.
+ *
+ * All image descriptors carry HOST pointers unless the function name ends in `_dev`.
+ * Every entry point needs a CUDA device: there is no CPU fallback.
+ */
+#ifndef UHDR_B200_H
+#define UHDR_B200_H
+
+#include <stdint.h>
+#include "ultrahdr_api.h"
+
+typedef struct uhdr_b200_gm_config {
+  /* ultrahdr::JpegR constructor arguments, ref lib/include/ultrahdr/jpegr.h:54-62 and
+   * lib/include/ultrahdr/ultrahdrcommon.h:450-457 */
+  int scale_factor;            /* mapDimensionScaleFactor */
+  int quality;                 /* mapCompressQuality */
+  int multichannel;            /* useMultiChannelGainMap */
+  float gamma;
+  int preset;                  /* uhdr_enc_preset_t */
+  float min_content_boost;     /* FLT_MIN = unset */
+  float max_content_boost;     /* FLT_MAX = unset */
+  float target_disp_peak_nits; /* -1 = unset */
+  /* UltraHdr::generateGainMap flags, ref lib/include/ultrahdr/ultrahdrcommon.h:496-499 */
+  int sdr_is_601;
+  int use_luminance;
+} uhdr_b200_gm_config_t;
+
+UHDR_EXTERN const char* uhdr_b200_last_error(void);
+UHDR_EXTERN int uhdr_b200_device_count(void);
+UHDR_EXTERN unsigned long long uhdr_b200_kernel_launches(void);
+
+/* UltraHdr::generateGainMap, ref lib/src/jpegr.cpp:530.  gainmap_out->planes[0] must point to
+ * (w/scale)*(h/scale)*(multichannel?3:1) bytes; written tightly packed, descriptor filled in. */
+UHDR_EXTERN int uhdr_b200_generate_gainmap(const uhdr_raw_image_t* sdr, const uhdr_raw_image_t* hdr,
+                                           const uhdr_b200_gm_config_t* cfg,
+                                           uhdr_gainmap_metadata_t* metadata_out,
+                                           uhdr_raw_image_t* gainmap_out);
+/* UltraHdr::applyGainMap, ref lib/src/jpegr.cpp:1533 */
+UHDR_EXTERN int uhdr_b200_apply_gainmap(const uhdr_raw_image_t* sdr, const uhdr_raw_image_t* gainmap,
+                                        const uhdr_gainmap_metadata_t* metadata, int output_ct,
+                                        int output_fmt, float max_display_boost,
+                                        uhdr_raw_image_t* dest);
+/* UltraHdr::toneMap, ref lib/src/jpegr.cpp:1985 */
+UHDR_EXTERN int uhdr_b200_tonemap(const uhdr_raw_image_t* hdr, uhdr_raw_image_t* sdr);
+/* UltraHdr::convertYuv (in place), ref lib/src/jpegr.cpp:436 */
+UHDR_EXTERN int uhdr_b200_convert_yuv(uhdr_raw_image_t* image, int src_cg, int dst_cg);
+
+/* JpegEncoderHelper::compressImage, ref lib/src/jpegencoderhelper.cpp:101.  `is_gainmap_comment`
+ * is implied by the format exactly as in the reference (RGB888 / Y400 carry the COM marker).
+ * out must hold `cap` bytes. */
+UHDR_EXTERN int uhdr_b200_jpeg_encode(const uhdr_raw_image_t* img, int quality, const void* icc,
+                                      size_t icc_size, void* out, size_t cap, size_t* out_size);
+/* forward block stage only: quantised coefficients per component, raster block order, natural
+ * order inside a block (parity hook for FDCT + quantise). coefs[c] sized wblocks*hblocks*64. */
+UHDR_EXTERN int uhdr_b200_jpeg_forward(const uhdr_raw_image_t* img, int quality, int16_t* coefs[3]);
+/* JpegDecoderHelper::decompressImage, ref lib/src/jpegdecoderhelper.cpp:169.
+ * mode: 0 = DECODE_TO_YCBCR_CS raw planes, 1 = DECODE_TO_RGB_CS (RGBA8888), 2 = DECODE_STREAM.
+ * out->planes[0] must point to a buffer of `cap` bytes; planes are laid out back to back like
+ * JpegDecoderHelper::getDecompressedImage (:536-552). */
+UHDR_EXTERN int uhdr_b200_jpeg_decode(const void* data, size_t size, int mode, uhdr_raw_image_t* out,
+                                      size_t cap);
+
+/* LUT blob (OETF / inverse-OETF tables): build on the host with the reference's libm
+ * expressions, or install a blob that was broadcast from rank 0 (NCCL) into device memory. */
+UHDR_EXTERN size_t uhdr_b200_lut_blob_floats(void);
+UHDR_EXTERN int uhdr_b200_build_lut_blob(float* host_out);
+UHDR_EXTERN int uhdr_b200_install_lut_blob_dev(const void* device_ptr); /* copies D2D on the current device */
+UHDR_EXTERN int uhdr_b200_get_lut_blob(float* host_out);               /* read back what the device holds */
+
+/* Batch API-1 / API-0 encode of independent frames on the current device: `n` frames share one
+ * geometry/config; frames are pipelined over `streams` CUDA streams with pinned staging.
+ * hdr[i] / sdr[i] host descriptors (sdr == NULL selects API-0); out[i].data must hold
+ * out[i].capacity bytes and receives data_sz. */
+UHDR_EXTERN int uhdr_b200_encode_batch(int n, const uhdr_raw_image_t* hdr, const uhdr_raw_image_t* sdr,
+                                       const uhdr_b200_gm_config_t* cfg, int base_quality,
+                                       uhdr_compressed_image_t* out, int streams);
+
+#endif

@@ -1,0 +1,139 @@
+// extern "C" stage entry points with HOST buffers (include/uhdr_b200.h): upload, run the device
+// stage, download, synchronise.  These are what the parity tests call through ctypes.
+#include <cstring>
+#include <mutex>
+
+#include "engine.h"
+
+using namespace uhdr_b200;
+
+namespace {
+// one workspace per calling thread, created on first use and kept (arenas are rewound per call)
+Workspace* tls_workspace() {
+  static thread_local Workspace* ws = nullptr;
+  if (!ws) {
+    ws = new Workspace();
+    if (ws->init() != E_OK) {
+      delete ws;
+      ws = nullptr;
+    }
+  }
+  if (ws) ws->rewind();
+  return ws;
+}
+}  // namespace
+
+extern "C" {
+
+UHDR_API const char* uhdr_b200_last_error(void) { return last_error(); }
+
+UHDR_API int uhdr_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+UHDR_API unsigned long long uhdr_b200_kernel_launches(void) { return launch_count(); }
+
+UHDR_API size_t uhdr_b200_lut_blob_floats(void) { return kLutTotalFloats; }
+UHDR_API int uhdr_b200_build_lut_blob(float* host_out) {
+  build_lut_blob(host_out);
+  return E_OK;
+}
+UHDR_API int uhdr_b200_install_lut_blob_dev(const void* device_ptr) {
+  return install_luts_from_device(device_ptr);
+}
+UHDR_API int uhdr_b200_get_lut_blob(float* host_out) { return read_back_luts(host_out); }
+
+UHDR_API int uhdr_b200_generate_gainmap(const uhdr_raw_image_t* sdr, const uhdr_raw_image_t* hdr,
+                                        const uhdr_b200_gm_config_t* cfg,
+                                        uhdr_gainmap_metadata_t* md_out,
+                                        uhdr_raw_image_t* gainmap_out) {
+  if (!sdr || !hdr || !cfg || !md_out || !gainmap_out || !gainmap_out->planes[0])
+    return fail(E_INVALID_PARAM, "received nullptr argument");
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  DevImage dsdr, dhdr;
+  int rc = upload_image(*ws, *sdr, &dsdr);
+  if (rc) return rc;
+  rc = upload_image(*ws, *hdr, &dhdr);
+  if (rc) return rc;
+  GainmapJob job;
+  rc = generate_gainmap_dev(*ws, dsdr, dhdr, *cfg, 64, &job);
+  if (rc) return rc;
+  gainmap_out->fmt = (uhdr_img_fmt_t)job.map.v.fmt;
+  gainmap_out->cg = (uhdr_color_gamut_t)job.map.cg;
+  gainmap_out->ct = (uhdr_color_transfer_t)job.map.ct;
+  gainmap_out->range = (uhdr_color_range_t)job.map.range;
+  gainmap_out->w = job.map.v.w;
+  gainmap_out->h = job.map.v.h;
+  gainmap_out->stride[0] = job.map.v.w;
+  rc = download_image(*ws, job.map, gainmap_out);
+  if (rc) return rc;
+  rc = ws->sync();
+  if (rc) return rc;
+  finish_gainmap_metadata(job, md_out);
+  return E_OK;
+}
+
+UHDR_API int uhdr_b200_apply_gainmap(const uhdr_raw_image_t* sdr, const uhdr_raw_image_t* gainmap,
+                                     const uhdr_gainmap_metadata_t* md, int output_ct, int output_fmt,
+                                     float max_display_boost, uhdr_raw_image_t* dest) {
+  (void)output_fmt;
+  if (!sdr || !gainmap || !md) return fail(E_INVALID_PARAM, "received nullptr argument");
+  if (dest == nullptr || dest->planes[UHDR_PLANE_PACKED] == nullptr)
+    return fail(E_INVALID_PARAM, "apply gainmap method received nullptr for destination image or plane pointer");
+  if (dest->stride[UHDR_PLANE_PACKED] < dest->w)
+    return fail(E_INVALID_PARAM, "destination stride (%u) cannot be less than image width (%u)",
+                dest->stride[UHDR_PLANE_PACKED], dest->w);
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  DevImage dsdr, dmap, ddst;
+  int rc = upload_image(*ws, *sdr, &dsdr);
+  if (rc) return rc;
+  rc = upload_image(*ws, *gainmap, &dmap);
+  if (rc) return rc;
+  rc = alloc_dev_image(*ws, dest->fmt, sdr->w, sdr->h, 64, &ddst);
+  if (rc) return rc;
+  rc = apply_gainmap_dev(*ws, dsdr, dmap, *md, output_ct, max_display_boost, &ddst);
+  if (rc) return rc;
+  dest->cg = (uhdr_color_gamut_t)ddst.cg;
+  rc = download_image(*ws, ddst, dest);
+  if (rc) return rc;
+  return ws->sync();
+}
+
+UHDR_API int uhdr_b200_tonemap(const uhdr_raw_image_t* hdr, uhdr_raw_image_t* sdr) {
+  if (!hdr || !sdr) return fail(E_INVALID_PARAM, "received nullptr argument");
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  DevImage dhdr, dsdr;
+  int rc = upload_image(*ws, *hdr, &dhdr);
+  if (rc) return rc;
+  rc = alloc_dev_image(*ws, sdr->fmt, hdr->w, hdr->h, 64, &dsdr);
+  if (rc) return rc;
+  rc = tonemap_dev(*ws, dhdr, &dsdr);
+  if (rc) return rc;
+  sdr->cg = (uhdr_color_gamut_t)dsdr.cg;
+  sdr->ct = (uhdr_color_transfer_t)dsdr.ct;
+  sdr->range = (uhdr_color_range_t)dsdr.range;
+  rc = download_image(*ws, dsdr, sdr);
+  if (rc) return rc;
+  return ws->sync();
+}
+
+UHDR_API int uhdr_b200_convert_yuv(uhdr_raw_image_t* image, int src_cg, int dst_cg) {
+  if (!image) return fail(E_INVALID_PARAM, "received nullptr argument");
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  DevImage d;
+  int rc = upload_image(*ws, *image, &d);
+  if (rc) return rc;
+  rc = convert_yuv_dev(*ws, &d, src_cg, dst_cg);
+  if (rc) return rc;
+  rc = download_image(*ws, d, image);
+  if (rc) return rc;
+  return ws->sync();
+}
+
+}  // extern "C"

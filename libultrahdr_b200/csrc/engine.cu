@@ -1,0 +1,386 @@
+#include "engine.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace uhdr_b200 {
+
+int fmt_planes(int fmt) {
+  switch (fmt) {
+    case F_P010: return 2;
+    case F_YUV420: case F_YUV444: case F_YUV422: case F_YUV444_10: return 3;
+    case F_Y400: case F_RGBA8888: case F_RGBAF16: case F_RGBA1010102: case F_RGB888: return 1;
+  }
+  return 0;
+}
+
+void fmt_plane_geom(int fmt, int w, int h, int i, int* pw, int* ph, int* esz) {
+  *pw = w; *ph = h; *esz = 1;
+  switch (fmt) {
+    case F_P010:
+      *esz = 2;
+      if (i == 1) { *pw = ((w + 1) / 2) * 2; *ph = (h + 1) / 2; }
+      break;
+    case F_YUV420:
+      if (i > 0) { *pw = (w + 1) / 2; *ph = (h + 1) / 2; }
+      break;
+    case F_YUV422:
+      if (i > 0) *pw = (w + 1) / 2;
+      break;
+    case F_YUV444_10: *esz = 2; break;
+    case F_RGBA8888: case F_RGBA1010102: *esz = 4; break;
+    case F_RGBAF16: *esz = 8; break;
+    case F_RGB888: *esz = 3; break;
+    default: break;
+  }
+}
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+int alloc_dev_image(Workspace& ws, int fmt, int w, int h, int stride_align, DevImage* out) {
+  memset(out, 0, sizeof *out);
+  out->v.fmt = fmt;
+  out->v.w = w;
+  out->v.h = h;
+  out->cg = out->ct = out->range = -1;
+  const int np = fmt_planes(fmt);
+  if (np == 0) return fail(E_UNSUPPORTED, "unsupported image format %d", fmt);
+  const int ystride = align_up(w, stride_align);
+  for (int i = 0; i < np; i++) {
+    int pw, ph, esz;
+    fmt_plane_geom(fmt, w, h, i, &pw, &ph, &esz);
+    int stride = i == 0 ? ystride : (fmt == F_P010 ? ystride : align_up(pw, stride_align > 1 ? stride_align / 2 : 1));
+    if (fmt == F_YUV444 || fmt == F_YUV444_10) stride = ystride;
+    // 8 spare rows: the JPEG block stage reads whole 8-row blocks
+    void* p = ws.dalloc((size_t)stride * (ph + 8) * esz);
+    if (!p) return E_MEM;
+    out->v.p[i] = p;
+    out->v.stride[i] = stride;
+  }
+  return E_OK;
+}
+
+int upload_image(Workspace& ws, const uhdr_raw_image_t& src, DevImage* out) {
+  if (src.w == 0 || src.h == 0) return fail(E_INVALID_PARAM, "image has zero dimension");
+  int rc = alloc_dev_image(ws, src.fmt, src.w, src.h, 64, out);
+  if (rc) return rc;
+  out->cg = src.cg;
+  out->ct = src.ct;
+  out->range = src.range;
+  out->v.full_range = src.range == UHDR_CR_FULL_RANGE;
+  const int np = fmt_planes(src.fmt);
+  for (int i = 0; i < np; i++) {
+    if (!src.planes[i]) return fail(E_INVALID_PARAM, "plane %d of the image is a null pointer", i);
+    int pw, ph, esz;
+    fmt_plane_geom(src.fmt, src.w, src.h, i, &pw, &ph, &esz);
+    if ((int)src.stride[i] < pw) pw = src.stride[i];
+    CUDA_TRY(cudaMemcpy2DAsync((void*)out->v.p[i], (size_t)out->v.stride[i] * esz, src.planes[i],
+                               (size_t)src.stride[i] * esz, (size_t)pw * esz, ph,
+                               cudaMemcpyHostToDevice, ws.stream()));
+  }
+  return E_OK;
+}
+
+int download_image(Workspace& ws, const DevImage& src, uhdr_raw_image_t* dst) {
+  const int np = fmt_planes(src.v.fmt);
+  for (int i = 0; i < np; i++) {
+    int pw, ph, esz;
+    fmt_plane_geom(src.v.fmt, src.v.w, src.v.h, i, &pw, &ph, &esz);
+    if ((int)dst->stride[i] < pw) pw = dst->stride[i];
+    CUDA_TRY(cudaMemcpy2DAsync(dst->planes[i], (size_t)dst->stride[i] * esz, src.v.p[i],
+                               (size_t)src.v.stride[i] * esz, (size_t)pw * esz, ph,
+                               cudaMemcpyDeviceToHost, ws.stream()));
+  }
+  return E_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr,
+                         const uhdr_b200_gm_config_t& cfg, int map_align, GainmapJob* job) {
+  // format checks, jpegr.cpp:537-562
+  if (sdr.v.fmt != F_YUV444 && sdr.v.fmt != F_YUV422 && sdr.v.fmt != F_YUV420 && sdr.v.fmt != F_RGBA8888)
+    return fail(E_UNSUPPORTED, "generate gainmap method expects sdr intent color format to be one of "
+                "{YCbCr444, YCbCr422, YCbCr420, RGBA8888}. Received %d", sdr.v.fmt);
+  if (hdr.v.fmt != F_P010 && hdr.v.fmt != F_YUV444_10 && hdr.v.fmt != F_RGBA1010102 && hdr.v.fmt != F_RGBAF16)
+    return fail(E_UNSUPPORTED, "generate gainmap method expects hdr intent color format to be one of "
+                "{P010, 30bppYCbCr444, RGBA1010102, RGBAHalfFloat}. Received %d", hdr.v.fmt);
+  if (hdr.ct < 0 || hdr.ct > 3)
+    return fail(E_UNSUPPORTED, "No implementation available for converting transfer characteristics %d to linear", hdr.ct);
+  if (sdr.v.w != hdr.v.w || sdr.v.h != hdr.v.h)
+    return fail(E_INVALID_PARAM, "sdr intent resolution %dx%d and hdr intent resolution %dx%d do not match",
+                sdr.v.w, sdr.v.h, hdr.v.w, hdr.v.h);
+  GainmapGenParams p;
+  memset(&p, 0, sizeof p);
+  p.hdr = hdr.v;
+  p.sdr = sdr.v;
+  p.hdr_ct = hdr.ct;
+  if (!luminance_coeffs(hdr.cg, p.lum))
+    return fail(E_UNSUPPORTED, "No implementation available for calculating luminance for color gamut %d", hdr.cg);
+  const float hdr_white_nits = reference_display_peak_nits(hdr.ct);
+  // gamut side selection, jpegr.cpp:605-638 (UHDR_WRITE_XMP is off: kWriteXmpMetadata == false)
+  bool use_sdr_cg = true;
+  bool ident = true;
+  if (sdr.cg != hdr.cg) {
+    use_sdr_cg = !(hdr.cg == UHDR_CG_BT_2100 || (hdr.cg == UHDR_CG_DISPLAY_P3 && sdr.cg != UHDR_CG_BT_2100));
+    const bool ok = use_sdr_cg ? gamut_matrix(sdr.cg, hdr.cg, p.gamut, &ident)
+                               : gamut_matrix(hdr.cg, sdr.cg, p.gamut, &ident);
+    if (!ok) return fail(E_UNSUPPORTED, "No implementation available for gamut conversion from %d to %d", hdr.cg, sdr.cg);
+  }
+  p.gamut_on_hdr = use_sdr_cg ? 1 : 0;
+  p.gamut_identity = ident ? 1 : 0;
+  if (!yuv2rgb_coeffs(sdr.cg, p.sdr_y2r))  // :640-648
+    return fail(E_UNSUPPORTED, "No implementation available for converting yuv to rgb for color gamut %d", sdr.cg);
+  if (cfg.sdr_is_601) yuv2rgb_coeffs(UHDR_CG_DISPLAY_P3, p.sdr_y2r);  // :688-690
+  if (!yuv2rgb_coeffs(hdr.cg, p.hdr_y2r))
+    return fail(E_UNSUPPORTED, "No implementation available for converting yuv to rgb for color gamut %d", hdr.cg);
+  if (!luminance_coeffs(sdr.cg, p.lum))  // luminanceFn = getLuminanceFn(sdr_intent->cg), :660
+    return fail(E_UNSUPPORTED, "No implementation available for computing luminance for color gamut %d", sdr.cg);
+  p.use_luminance = cfg.use_luminance;
+  // map geometry :692-706
+  int scale = cfg.scale_factor;
+  if (scale <= 0) return fail(E_INVALID_PARAM, "invalid gainmap scale factor %d", scale);
+  int mw = sdr.v.w / scale, mh = sdr.v.h / scale;
+  if (mw == 0 || mh == 0) {
+    int sf = sdr.v.w < sdr.v.h ? sdr.v.w : sdr.v.h;
+    scale = sf >= 8 ? sf / 8 : 1;
+    mw = sdr.v.w / scale;
+    mh = sdr.v.h / scale;
+  }
+  p.scale = scale;
+  p.map_w = mw;
+  p.map_h = mh;
+  p.nch = cfg.multichannel ? 3 : 1;
+  p.sdr_nits = 203.0f;
+  p.hdr_nits = hdr.ct == UHDR_CT_LINEAR ? 203.0f : hdr_white_nits;
+  p.luts = ws.luts();
+  int rc = alloc_dev_image(ws, cfg.multichannel ? F_RGB888 : F_Y400, mw, mh, map_align, &job->map);
+  if (rc) return rc;
+  job->map.cg = hdr.cg;  // :714-716: initialised with the hdr intent's colour aspects
+  job->map.ct = hdr.ct;
+  job->map.range = hdr.range;
+  p.dst = (uint8_t*)job->map.v.p[0];
+  p.dst_stride = job->map.v.stride[0];
+  job->nch = p.nch;
+  job->hdr_white_nits = hdr_white_nits;
+  job->gamma = cfg.gamma;
+  job->target_nits = cfg.target_disp_peak_nits;
+  job->use_base_cg = use_sdr_cg ? 1 : 0;
+  job->onepass = cfg.preset == UHDR_USAGE_REALTIME;
+  if (job->onepass) {
+    p.min_boost = 1.0f;
+    p.max_boost = hdr_white_nits / 203.0f;
+    p.log2_min = std::log2(p.min_boost);  // float overloads: jpegr.cpp has `using namespace std`
+    p.log2_max = std::log2(p.max_boost);
+    p.gamma = cfg.gamma;
+    CUDA_TRY(launch_gainmap_onepass(p, ws.stream()));
+    return E_OK;
+  }
+  p.gains = (float*)ws.dalloc(sizeof(float) * (size_t)mw * mh * p.nch);
+  p.minmax = (unsigned*)ws.dalloc(64);
+  float* d_minmax_f = (float*)ws.dalloc(64);
+  job->h_minmax = (float*)ws.halloc(64);
+  if (!p.gains || !p.minmax || !d_minmax_f || !job->h_minmax) return E_MEM;
+  CUDA_TRY(launch_gainmap_init_minmax(p.minmax, ws.stream()));
+  CUDA_TRY(launch_gainmap_pass1(p, ws.stream()));
+  GainmapFinalizeParams f;
+  f.minmax = p.minmax;
+  f.minmax_f = d_minmax_f;
+  f.nch = p.nch;
+  f.has_user_max = cfg.max_content_boost != FLT_MAX;
+  f.has_user_min = cfg.min_content_boost != FLT_MIN;
+  f.log2_user_max = f.has_user_max ? std::log2(cfg.max_content_boost) : 0.0f;
+  f.log2_user_min = f.has_user_min ? std::log2(cfg.min_content_boost) : 0.0f;
+  CUDA_TRY(launch_gainmap_finalize(f, ws.stream()));
+  AffineParams a;
+  a.gains = p.gains;
+  a.minmax_f = d_minmax_f;
+  a.dst = p.dst;
+  a.map_w = mw;
+  a.map_h = mh;
+  a.nch = p.nch;
+  a.dst_stride = p.dst_stride;
+  a.gamma = cfg.gamma;
+  CUDA_TRY(launch_gainmap_affine(a, ws.stream()));
+  CUDA_TRY(cudaMemcpyAsync(job->h_minmax, d_minmax_f, 6 * sizeof(float), cudaMemcpyDeviceToHost, ws.stream()));
+  return E_OK;
+}
+
+void finish_gainmap_metadata(const GainmapJob& job, uhdr_gainmap_metadata_t* md) {
+  const float kSdrWhiteNits = 203.0f;
+  if (job.onepass) {  // jpegr.cpp:724-734
+    for (int i = 0; i < 3; i++) {
+      md->max_content_boost[i] = job.hdr_white_nits / kSdrWhiteNits;
+      md->min_content_boost[i] = 1.0f;
+      md->gamma[i] = job.gamma;
+      md->offset_sdr[i] = 0.0f;
+      md->offset_hdr[i] = 0.0f;
+    }
+    md->hdr_capacity_min = 1.0f;
+    md->hdr_capacity_max = job.target_nits != -1.0f ? job.target_nits / kSdrWhiteNits : md->max_content_boost[0];
+  } else {            // :1031-1048, float exp2 (using namespace std)
+    for (int i = 0; i < 3; i++) {
+      const int c = job.nch == 3 ? i : 0;
+      md->max_content_boost[i] = std::exp2(job.h_minmax[3 + c]);
+      md->min_content_boost[i] = std::exp2(job.h_minmax[c]);
+      md->gamma[i] = job.gamma;
+      md->offset_sdr[i] = 1e-7f;
+      md->offset_hdr[i] = 1e-7f;
+    }
+    md->hdr_capacity_min = 1.0f;
+    md->hdr_capacity_max = job.target_nits != -1.0f ? job.target_nits / kSdrWhiteNits : job.hdr_white_nits / kSdrWhiteNits;
+  }
+  md->use_base_cg = job.use_base_cg;
+}
+
+// ------------------------------------------------------------------------------------------------
+int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
+                      const uhdr_gainmap_metadata_t& md, int out_ct, float max_display_boost,
+                      DevImage* dst) {
+  // validation, jpegr.cpp:1538-1614
+  if (!dst || !dst->v.p[0])
+    return fail(E_INVALID_PARAM, "apply gainmap method received nullptr for destination image or plane pointer");
+  if (dst->v.stride[0] < dst->v.w)
+    return fail(E_INVALID_PARAM, "destination stride (%u) cannot be less than image width (%u)", dst->v.stride[0], dst->v.w);
+  if (out_ct != UHDR_CT_LINEAR && out_ct != UHDR_CT_HLG && out_ct != UHDR_CT_PQ)
+    return fail(E_INVALID_PARAM, "apply gainmap method expects output color transfer to be one of "
+                "{UHDR_CT_LINEAR, UHDR_CT_HLG, UHDR_CT_PQ}. Received %d", out_ct);
+  if ((out_ct == UHDR_CT_LINEAR && dst->v.fmt != F_RGBAF16) || (out_ct != UHDR_CT_LINEAR && dst->v.fmt != F_RGBA1010102))
+    return fail(E_INVALID_PARAM, "unsupported destination pixel format %d for output color transfer %d", dst->v.fmt, out_ct);
+  if (sdr.v.fmt != F_YUV444 && sdr.v.fmt != F_YUV422 && sdr.v.fmt != F_YUV420 && sdr.v.fmt != F_RGB888 && sdr.v.fmt != F_RGBA8888)
+    return fail(E_UNSUPPORTED, "apply gainmap method expects base image color format to be one of "
+                "{YCbCr444, YCbCr422, YCbCr420, RGB888, RGBA8888}. Received %d", sdr.v.fmt);
+  if (map.v.fmt != F_Y400 && map.v.fmt != F_RGB888 && map.v.fmt != F_RGBA8888)
+    return fail(E_UNSUPPORTED, "apply gainmap method expects gainmap image color format to be one of "
+                "{YCbCr400, RGB888, RGBA8888}. Received %d", map.v.fmt);
+  ApplyParams p;
+  memset(&p, 0, sizeof p);
+  const int sdr_cg = sdr.cg == UHDR_CG_UNSPECIFIED ? (int)UHDR_CG_BT_709 : sdr.cg;
+  const int hdr_cg = map.cg == UHDR_CG_UNSPECIFIED ? sdr_cg : map.cg;
+  dst->cg = hdr_cg;
+  bool ident = true;
+  if (!gamut_matrix(hdr_cg, sdr_cg, p.gamut, &ident))
+    return fail(E_ERROR, "No implementation available for converting from gamut %d to %d", sdr_cg, hdr_cg);
+  p.gamut_on_sdr = md.use_base_cg ? 0 : 1;
+  p.gamut_identity = ident ? 1 : 0;
+  {  // aspect-ratio check :1652-1671
+    const float pa = (float)sdr.v.w / sdr.v.h, ga = (float)map.v.w / map.v.h;
+    if (std::fabs(pa - ga) / pa > 0.01f)
+      return fail(E_UNSUPPORTED, "gainmap aspect ratio differs from the primary image by more than 1%%; "
+                  "the bicubic gainmap resize (editorhelper.cpp:100-146) is outside the B200 hot path");
+  }
+  const float scale = (float)sdr.v.w / map.v.w;
+  int srnd = (int)std::roundf(scale);
+  if (srnd < 1) srnd = 1;
+  const bool integer = scale == std::floor(scale);
+  p.scale_int = integer ? (int)(size_t)scale : 0;
+  p.scale_f = scale;
+  float display_boost = max_display_boost < md.hdr_capacity_max ? max_display_boost : md.hdr_capacity_max;
+  float weight;
+  if (display_boost != md.hdr_capacity_max) {  // :1680-1689, float log2 (using namespace std)
+    weight = (std::log2(display_boost) - std::log2(md.hdr_capacity_min)) /
+             (std::log2(md.hdr_capacity_max) - std::log2(md.hdr_capacity_min));
+    weight = weight < 0.0f ? 0.0f : (weight > 1.0f ? 1.0f : weight);
+  } else {
+    weight = 1.0f;
+  }
+  // per-call tables: IDW (only needed for integer scale > 1) and the gain LUT
+  GainmapMetadata m;
+  static_assert(sizeof(GainmapMetadata) == sizeof(uhdr_gainmap_metadata_t), "layout");
+  memcpy(&m, &md, sizeof m);
+  const size_t idw_floats = integer && p.scale_int > 1 ? (size_t)16 * p.scale_int * p.scale_int : 0;
+  float* h_tab = (float*)ws.halloc(sizeof(float) * (3 * 1024 + idw_floats));
+  float* d_tab = (float*)ws.dalloc(sizeof(float) * (3 * 1024 + idw_floats));
+  if (!h_tab || !d_tab) return E_MEM;
+  build_gain_lut(m, weight, h_tab);
+  if (idw_floats) {
+    std::vector<float> idw;
+    build_idw_tables(p.scale_int, idw);
+    memcpy(h_tab + 3 * 1024, idw.data(), sizeof(float) * idw_floats);
+  }
+  CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, sizeof(float) * (3 * 1024 + idw_floats), cudaMemcpyHostToDevice, ws.stream()));
+  p.gain_lut = d_tab;
+  p.idw = d_tab + 3 * 1024;
+  const bool single = metadata_single_channel(m);
+  for (int c = 0; c < 3; c++) {
+    p.gamma_inv[c] = 1.0f / md.gamma[single ? 0 : c];
+    p.off_sdr[c] = md.offset_sdr[c];
+    p.off_hdr[c] = md.offset_hdr[c];
+  }
+  yuv2rgb_coeffs(UHDR_CG_DISPLAY_P3, p.y2r);
+  p.sdr = sdr.v;
+  p.map = (const uint8_t*)map.v.p[0];
+  p.map_w = map.v.w;
+  p.map_h = map.v.h;
+  p.map_stride = map.v.stride[0];
+  p.map_bpp = map.v.fmt == F_RGBA8888 ? 4 : (map.v.fmt == F_RGB888 ? 3 : 1);
+  p.map_nch = map.v.fmt == F_Y400 ? 1 : 3;
+  p.out_ct = out_ct;
+  p.out_nits = out_ct == UHDR_CT_HLG ? 1000.0f : 10000.0f;
+  p.luts = ws.luts();
+  p.dst = (void*)dst->v.p[0];
+  p.dst_stride = dst->v.stride[0];
+  CUDA_TRY(launch_apply_gainmap(p, ws.stream()));
+  return E_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int tonemap_dev(Workspace& ws, const DevImage& hdr, DevImage* sdr) {
+  // jpegr.cpp:1986-2037
+  if (hdr.v.fmt != F_P010 && hdr.v.fmt != F_YUV444_10 && hdr.v.fmt != F_RGBA1010102 && hdr.v.fmt != F_RGBAF16)
+    return fail(E_UNSUPPORTED, "tonemap method expects hdr intent color format to be one of "
+                "{P010, 30bppYCbCr444, RGBA1010102, RGBAHalfFloat}. Received %d", hdr.v.fmt);
+  if (hdr.v.fmt == F_P010 && sdr->v.fmt != F_YUV420)
+    return fail(E_UNSUPPORTED, "tonemap method expects sdr intent color format to be YCbCr420 if hdr intent is P010. Received %d", sdr->v.fmt);
+  if (hdr.v.fmt == F_YUV444_10 && sdr->v.fmt != F_YUV444)
+    return fail(E_UNSUPPORTED, "tonemap method expects sdr intent color format to be YCbCr444 if hdr intent is 30bppYCbCr444. Received %d", sdr->v.fmt);
+  if ((hdr.v.fmt == F_RGBA1010102 || hdr.v.fmt == F_RGBAF16) && sdr->v.fmt != F_RGBA8888)
+    return fail(E_UNSUPPORTED, "tonemap method expects sdr intent color format to be RGBA8888 if hdr intent is RGBA1010102 or RGBAHalfFloat. Received %d", sdr->v.fmt);
+  TonemapParams p;
+  memset(&p, 0, sizeof p);
+  if (!yuv2rgb_coeffs(hdr.cg, p.y2r))
+    return fail(E_UNSUPPORTED, "No implementation available for converting yuv to rgb for color gamut %d", hdr.cg);
+  const float nits = reference_display_peak_nits(hdr.ct);
+  if (nits == -1.0f)
+    return fail(E_UNSUPPORTED, "received invalid peak brightness %f nits for hdr reference display with color transfer %d", nits, hdr.ct);
+  sdr->cg = UHDR_CG_DISPLAY_P3;  // :2117-2119
+  sdr->ct = UHDR_CT_SRGB;
+  sdr->range = UHDR_CR_FULL_RANGE;
+  bool ident = true;
+  gamut_matrix(UHDR_CG_DISPLAY_P3, hdr.cg, p.gamut, &ident);
+  p.gamut_identity = ident;
+  p.hdr = hdr.v;
+  p.hdr_ct = hdr.ct;
+  p.headroom = nits / 203.0f;
+  p.normalized = hdr.ct != UHDR_CT_LINEAR;
+  p.luts = ws.luts();
+  for (int i = 0; i < 3; i++) {
+    p.dst[i] = (uint8_t*)sdr->v.p[i];
+    p.dst_stride[i] = sdr->v.stride[i];
+  }
+  p.dst_fmt = sdr->v.fmt;
+  CUDA_TRY(launch_tonemap(p, ws.stream()));
+  return E_OK;
+}
+
+int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg) {
+  // jpegr.cpp:436-518
+  if (src_cg < 0 || src_cg > 2) return fail(E_INVALID_PARAM, "Unrecognized src color gamut %d", src_cg);
+  if (dst_cg < 0 || dst_cg > 2) return fail(E_INVALID_PARAM, "Unrecognized dest color gamut %d", dst_cg);
+  if (src_cg == dst_cg) return E_OK;
+  if (img->v.fmt != F_YUV420 && img->v.fmt != F_YUV444)
+    return fail(E_UNSUPPORTED, "No implementation available for performing gamut conversion for color format %d", img->v.fmt);
+  YuvConvParams p;
+  yuv_matrix(src_cg, dst_cg, p.m);
+  for (int i = 0; i < 3; i++) {
+    p.p[i] = (uint8_t*)img->v.p[i];
+    p.stride[i] = img->v.stride[i];
+  }
+  p.w = img->v.w;
+  p.h = img->v.h;
+  p.fmt = img->v.fmt;
+  CUDA_TRY(launch_yuv_convert(p, ws.stream()));
+  return E_OK;
+}
+
+}  // namespace uhdr_b200

@@ -1,0 +1,139 @@
+// Device-side parameter blocks and launcher prototypes of the gain-map hot path (sm_100a).
+// All launchers take DEVICE pointers and a stream; they never synchronise.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uhdr_b200 {
+
+// uhdr_img_fmt_t values (ultrahdr_api.h)
+enum : int { F_P010 = 0, F_YUV420 = 1, F_Y400 = 2, F_RGBA8888 = 3, F_RGBAF16 = 4,
+             F_RGBA1010102 = 5, F_YUV444 = 6, F_YUV422 = 7, F_RGB888 = 11, F_YUV444_10 = 12 };
+enum : int { CT_LINEAR = 0, CT_HLG = 1, CT_PQ = 2, CT_SRGB = 3 };
+
+struct ImgView {           // device view of a uhdr_raw_image_t
+  const void* p[3];
+  int stride[3];           // in pixels (elements), like the reference
+  int fmt, w, h, full_range;
+};
+
+struct GainmapGenParams {  // generateGainMap, lib/src/jpegr.cpp:530-1058
+  ImgView hdr, sdr;
+  int hdr_ct;
+  int map_w, map_h, scale, nch;     // nch = 3 multichannel, 1 single
+  float hdr_y2r[4], sdr_y2r[4];     // {cr, cb, gcb, gcr}
+  float gamut[9];
+  int gamut_on_hdr, gamut_identity; // use_sdr_cg rule, :607-638
+  float lum[3];
+  int use_luminance;
+  float sdr_nits, hdr_nits;         // 203 and hdrSampleToNitsFactor
+  const float* luts;                // LUT blob (tables.h)
+  // two-pass (BEST_QUALITY)
+  float* gains;                     // map_w*map_h*nch floats, tight
+  unsigned* minmax;                 // 6 order-preserving keys: min[3], max[3]
+  // one-pass (REALTIME) :724-737, encodeGain gainmapmath.cpp:758-771
+  float min_boost, max_boost, log2_min, log2_max, gamma;
+  uint8_t* dst;                     // RGB888 / Y400
+  int dst_stride;                   // pixels
+};
+
+struct GainmapFinalizeParams {      // clamp / hints, jpegr.cpp:969-986
+  unsigned* minmax;                 // in : keys
+  float* minmax_f;                  // out: min[3], max[3] as floats after clamping
+  int nch;
+  float log2_user_max, log2_user_min;
+  int has_user_max, has_user_min;
+};
+
+struct AffineParams {               // jpegr.cpp:988-1013, affineMapGain gainmapmath.cpp:784-789
+  const float* gains;
+  const float* minmax_f;
+  uint8_t* dst;
+  int map_w, map_h, nch, dst_stride;
+  float gamma;
+};
+
+struct ApplyParams {                // applyGainMap, jpegr.cpp:1533-1831
+  ImgView sdr;
+  const uint8_t* map;
+  int map_w, map_h, map_stride, map_bpp, map_nch;  // bpp 1/3/4 bytes per map pixel, nch 1/3
+  int scale_int;                    // integer scale (0 -> use scale_f path)
+  float scale_f;
+  const float* idw;                 // 4 variants x s*s*4 (device)
+  const float* gain_lut;            // 3 x 1024 (device)
+  float gamma_inv[3], off_sdr[3], off_hdr[3];
+  float y2r[4];                     // BT.601 always (:1723)
+  float gamut[9];
+  int gamut_on_sdr, gamut_identity; // !use_base_cg -> sdr side
+  int out_ct;                       // LINEAR / HLG / PQ
+  float out_nits;                   // kHlgMaxNits / kPqMaxNits
+  const float* luts;
+  void* dst;
+  int dst_stride;
+};
+
+struct TonemapParams {              // toneMap, jpegr.cpp:1985-2222
+  ImgView hdr;
+  int hdr_ct;
+  float y2r[4];
+  float gamut[9];                   // hdr cg -> P3
+  int gamut_identity;
+  float headroom;
+  int normalized;
+  const float* luts;
+  uint8_t* dst[3];
+  int dst_stride[3];
+  int dst_fmt;                      // YUV420 / YUV444 / RGBA8888
+};
+
+struct YuvConvParams {              // transformYuv420/444, gainmapmath.cpp:686-748
+  uint8_t* p[3];
+  int stride[3];
+  int w, h, fmt;
+  float m[9];
+};
+
+struct DctPlaneParams {             // forward: samples -> coefficients
+  const uint8_t* src;               // plane (or packed RGB when rgb_comp >= 0)
+  int src_stride;                   // elements per row (pixels for RGB)
+  int w, h;                         // real plane size
+  int wblocks, hblocks;
+  int pad_mode;                     // 0: rows >= h read as `fill`; 1: replicate edges
+  int fill;
+  int rgb_comp;                     // -1 plane; 0/1/2 = Y/Cb/Cr computed from RGB888
+  uint16_t q[64];                   // natural order
+  int16_t* coefs;                   // [hblocks*wblocks][64]
+};
+
+struct IdctPlaneParams {
+  const int16_t* coefs;
+  uint16_t q[64];
+  int wblocks, hblocks;
+  uint8_t* dst;
+  int dst_stride;                   // >= wblocks*8 unless clipped by dst_w/dst_h
+  int dst_w, dst_h;                 // samples beyond are not written
+};
+
+struct YccToRgbaParams {
+  const uint8_t* y; const uint8_t* cb; const uint8_t* cr;
+  int src_stride, w, h;
+  uint8_t* dst;                     // RGBA8888
+  int dst_stride;                   // pixels
+};
+
+cudaError_t launch_gainmap_pass1(const GainmapGenParams& p, cudaStream_t s);
+cudaError_t launch_gainmap_onepass(const GainmapGenParams& p, cudaStream_t s);
+cudaError_t launch_gainmap_init_minmax(unsigned* minmax, cudaStream_t s);
+cudaError_t launch_gainmap_finalize(const GainmapFinalizeParams& p, cudaStream_t s);
+cudaError_t launch_gainmap_affine(const AffineParams& p, cudaStream_t s);
+cudaError_t launch_apply_gainmap(const ApplyParams& p, cudaStream_t s);
+cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s);
+cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s);
+cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s);
+cudaError_t launch_idct_dequant(const IdctPlaneParams& p, cudaStream_t s);
+cudaError_t launch_ycc_to_rgba(const YccToRgbaParams& p, cudaStream_t s);
+
+// number of kernel launches issued by this library since load (bench.py's gpu_launches)
+unsigned long long launch_count();
+
+}  // namespace uhdr_b200

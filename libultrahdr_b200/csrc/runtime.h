@@ -1,0 +1,69 @@
+// Device runtime: per-device LUT residency, a grow-only arena per worker (device + pinned host)
+// and a stream.  180 GB of HBM per GPU means we never free inside a codec call: arenas are
+// rewound, not released.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <string>
+#include <vector>
+
+namespace uhdr_b200 {
+
+// uhdr_codec_err_t values
+enum : int { E_OK = 0, E_ERROR = 1, E_UNKNOWN = 2, E_INVALID_PARAM = 3, E_MEM = 4,
+             E_INVALID_OP = 5, E_UNSUPPORTED = 6 };
+
+void set_last_error(const std::string& s);
+const char* last_error();
+int fail(int code, const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::uhdr_b200::fail(_e == cudaErrorMemoryAllocation ? E_MEM : E_ERROR,          \
+                               "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e),      \
+                               __FILE__, __LINE__, #expr);                                 \
+  } while (0)
+
+// Device-resident LUT blob for the current device (built on first use, or installed from a
+// broadcast).  Returns nullptr + sets last error when no CUDA device is usable.
+const float* device_luts();
+int install_luts_from_device(const void* dptr);
+int read_back_luts(float* host_out);
+
+class Arena {
+ public:
+  explicit Arena(bool pinned_host) : pinned_(pinned_host) {}
+  ~Arena();
+  void* alloc(size_t bytes, size_t align = 256);  // nullptr on failure (last error set)
+  void rewind();
+  size_t reserved() const;
+
+ private:
+  struct Block { char* base; size_t size, used; };
+  std::vector<Block> blocks_;
+  bool pinned_;
+};
+
+class Workspace {
+ public:
+  Workspace();
+  ~Workspace();
+  int init();  // binds to the current device, creates the stream
+  cudaStream_t stream() const { return stream_; }
+  void* dalloc(size_t bytes) { return dev_.alloc(bytes); }
+  void* halloc(size_t bytes) { return host_.alloc(bytes); }
+  void rewind() { dev_.rewind(); host_.rewind(); }
+  const float* luts() const { return luts_; }
+  int sync();
+
+ private:
+  Arena dev_{false}, host_{true};
+  cudaStream_t stream_ = nullptr;
+  const float* luts_ = nullptr;
+  int device_ = -1;
+};
+
+}  // namespace uhdr_b200

@@ -1,0 +1,228 @@
+"""GPU parity of the four per-pixel stages against the CPU checker (reference build when present,
+else the C restatement), called through the C ABI with host buffers.  Bit-exact bar for the packed
+integer outputs and for the RGBA-F16 / metadata floats (tolerance 0 ULP is asserted; the tests that
+involve float powf with a continuous argument state their own bound)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import uhdr_testlib as T
+from libultrahdr_b200 import ctypes_api as A
+
+pytestmark = pytest.mark.gpu
+W, H = 96, 64
+
+
+def _hdr(kind, fmt, cg, ct, w=W, h=H):
+    if fmt == "p010":
+        b = T.make_p010(w, h, kind)
+        img, keep = A.p010_image(b, w, h, cg, ct, A.CR_LIMITED)
+    elif fmt == "p010full":
+        b = T.make_p010(w, h, kind, limited=False)
+        img, keep = A.p010_image(b, w, h, cg, ct, A.CR_FULL)
+    elif fmt == "1010102":
+        b = T.make_rgba1010102(w, h)
+        img, keep = A.raw_image(A.FMT_RGBA1010102, cg, ct, A.CR_FULL, w, h, [b], [w]), b
+    else:
+        b = T.make_rgbaf16(w, h)
+        img, keep = A.raw_image(A.FMT_RGBAF16, cg, A.CT_LINEAR, A.CR_FULL, w, h, [b], [w]), b
+    return img, (b, keep)
+
+
+def _sdr(kind, cg, w=W, h=H):
+    b = T.make_yuv420(w, h, kind)
+    img, keep = A.yuv420_image(b, w, h, cg)
+    return img, (b, keep)
+
+
+GEN_CASES = list(itertools.product(["noise", "smooth", "black"], [A.CT_HLG, A.CT_PQ], [0, 1, 2],
+                                   [0, 1, 2], [0, 1], [1, 2, 4], [0, 1]))
+
+
+def test_generate_matrix(gpu, checker):
+    bad = []
+    for kind, hct, hcg, scg, multi, scale, preset in GEN_CASES:
+        hdr, k1 = _hdr(kind, "p010", hcg, hct)
+        sdr, k2 = _sdr(kind, scg)
+        cfg = A.default_gm_config(scale_factor=scale, multichannel=multi, preset=preset)
+        g1, m1 = gpu.generate(sdr, hdr, cfg)
+        g2, m2 = checker.generate(sdr, hdr, cfg)
+        if not ((g1 == g2).all() and T.md_equal(m1, m2)):
+            bad.append((kind, hct, hcg, scg, multi, scale, preset, int((g1 != g2).sum())))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("fmt,ct", [("p010full", A.CT_HLG), ("1010102", A.CT_PQ), ("1010102", A.CT_HLG),
+                                    ("f16", A.CT_LINEAR)])
+@pytest.mark.parametrize("multi,preset", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_generate_formats(gpu, checker, fmt, ct, multi, preset):
+    hdr, k1 = _hdr("noise", fmt, 2, ct)
+    sdr, k2 = _sdr("noise", 0)
+    for extra in ({}, {"use_luminance": 0}, {"sdr_is_601": 1}, {"scale_factor": 2}):
+        cfg = A.default_gm_config(multichannel=multi, preset=preset, **extra)
+        g1, m1 = gpu.generate(sdr, hdr, cfg)
+        g2, m2 = checker.generate(sdr, hdr, cfg)
+        assert (g1 == g2).all(), (extra, int((g1 != g2).sum()))
+        assert T.md_equal(m1, m2), (m1.as_dict(), m2.as_dict())
+
+
+def test_generate_rgba8888_sdr_and_boost_hints(gpu, checker):
+    hdr, k1 = _hdr("noise", "p010", 2, A.CT_HLG)
+    sb = T.make_rgba8888(W, H)
+    sdr = A.raw_image(A.FMT_RGBA8888, 0, A.CT_SRGB, A.CR_FULL, W, H, [sb], [W])
+    for kw in ({}, {"min_content_boost": 0.5, "max_content_boost": 6.0}, {"target_disp_peak_nits": 1600.0},
+               {"preset": 0, "target_disp_peak_nits": 800.0}):
+        cfg = A.default_gm_config(**kw)
+        g1, m1 = gpu.generate(sdr, hdr, cfg)
+        g2, m2 = checker.generate(sdr, hdr, cfg)
+        assert (g1 == g2).all() and T.md_equal(m1, m2), kw
+
+
+def _map_for(gpu_or_chk, kind, multi, scale):
+    hdr, k1 = _hdr(kind, "p010", 2, A.CT_HLG)
+    sdr, k2 = _sdr(kind, 0)
+    cfg = A.default_gm_config(scale_factor=scale, multichannel=multi)
+    g, m = gpu_or_chk.generate(sdr, hdr, cfg)
+    return sdr, k2, g, m
+
+
+@pytest.mark.parametrize("out_ct", [A.CT_LINEAR, A.CT_PQ])
+def test_apply_matrix(gpu, checker, out_ct):
+    bad = []
+    for kind, (multi, scale) in itertools.product(["noise", "smooth"], [(1, 1), (0, 1), (1, 4), (0, 4), (1, 2)]):
+        sdr, keep, g, m = _map_for(checker, kind, multi, scale)
+        variants = [g] if not multi else [g, np.concatenate([g, np.full(g.shape[:2] + (1,), 255, np.uint8)], -1)]
+        for gm in variants:
+            gm = np.ascontiguousarray(gm)
+            for gcg, boost in itertools.product([-1, 0, 1, 2], [A.FLT_MAX, 2.5]):
+                gi = T.gm_image(gm, gcg)
+                a = gpu.apply(sdr, gi, m, out_ct, boost)
+                b = checker.apply(sdr, gi, m, out_ct, boost)
+                if not (a == b).all():
+                    bad.append((kind, multi, scale, gm.shape[2], gcg, boost, int((a != b).sum())))
+    assert not bad, bad[:10]
+
+
+def test_apply_hlg_output(gpu, checker):
+    """HLG output goes through float powf(x, 1/1.2f) with a continuous argument; the device
+    evaluates it in double and narrows.  Bound: <= 1 code value in a 10-bit channel, on at most
+    1e-4 of the channels."""
+    sdr, keep, g, m = _map_for(checker, "noise", 1, 1)
+    gi = T.gm_image(g, 2)
+    a = gpu.apply(sdr, gi, m, A.CT_HLG)
+    b = checker.apply(sdr, gi, m, A.CT_HLG)
+    diff = 0
+    for sh in (0, 10, 20):
+        d = np.abs(((a >> sh) & 1023).astype(np.int32) - ((b >> sh) & 1023).astype(np.int32))
+        assert d.max() <= 1
+        diff += int((d != 0).sum())
+    assert diff <= 1e-4 * a.size * 3, diff
+    assert ((a >> 30) == 3).all()
+
+
+def test_apply_non_integer_scale(gpu, checker):
+    sdr, keep, g, m = _map_for(checker, "noise", 1, 1)
+    for ch in (1, 3):
+        gm = np.ascontiguousarray(g[:43, :64, :ch])
+        gi = T.gm_image(gm, 2)
+        for ct in (A.CT_LINEAR, A.CT_PQ):
+            a = gpu.apply(sdr, gi, m, ct)
+            b = checker.apply(sdr, gi, m, ct)
+            assert (a == b).all(), (ch, ct, int((a != b).sum()))
+
+
+def test_apply_gamma_metadata(gpu, checker):
+    """gamma != 1 routes through pow(double) on both sides (GainLUT::getGainFactor)."""
+    hdr, k1 = _hdr("noise", "p010", 2, A.CT_HLG)
+    sdr, k2 = _sdr("noise", 0)
+    cfg = A.default_gm_config(gamma=2.2)
+    g, m = checker.generate(sdr, hdr, cfg)
+    gi = T.gm_image(g, 2)
+    a = gpu.apply(sdr, gi, m, A.CT_LINEAR)
+    b = checker.apply(sdr, gi, m, A.CT_LINEAR)
+    # device pow() and glibc pow() are both <1-2 ulp in double; index flips need a tie
+    assert (a != b).sum() <= 1e-5 * a.size
+
+
+def test_tonemap(gpu, checker):
+    """toneMap uses float powf (srgbOetf) on a continuous argument: the device evaluates pow in
+    double.  Packed 8-bit outputs must agree except where that last-ulp difference straddles a
+    rounding boundary: bound 1 code value on <= 2e-5 of the samples."""
+    tot = 0
+    n = 0
+    for kind, hct, hcg in itertools.product(["noise", "smooth", "white"], [A.CT_HLG, A.CT_PQ], [0, 1, 2]):
+        hdr, k = _hdr(kind, "p010", hcg, hct)
+        a, _ = gpu.tonemap(hdr)
+        b, _ = checker.tonemap(hdr)
+        d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+        assert d.max() <= 1, (kind, hct, hcg)
+        tot += int((d != 0).sum())
+        n += a.size
+    assert tot <= max(2, 2e-5 * n), (tot, n)
+
+
+def test_tonemap_rgba(gpu, checker):
+    for fmt, ct in (("1010102", A.CT_PQ), ("f16", A.CT_LINEAR)):
+        hdr, k = _hdr("noise", fmt, 2, ct)
+        a, _ = gpu.tonemap(hdr)
+        b, _ = checker.tonemap(hdr)
+        d = np.abs(a.view(np.uint8).astype(np.int32) - b.view(np.uint8).astype(np.int32))
+        assert d.max() <= 1 and (d != 0).sum() <= 3
+
+
+def test_convert_yuv(gpu, checker):
+    for s, d in itertools.permutations([0, 1, 2], 2):
+        sb = T.make_yuv420(W, H, "noise")
+        a = gpu.convert_yuv(sb, W, H, s, d)
+        b = checker.convert_yuv(sb, W, H, s, d)
+        assert (a == b).all(), (s, d)
+
+
+def test_lut_blob_matches_checker(gpu, checker):
+    n = gpu.lib.uhdr_b200_lut_blob_floats
+    n.restype = np.ctypeslib.ctypes.c_size_t
+    blob = np.zeros(n(), np.float32)
+    assert gpu.lib.uhdr_b200_get_lut_blob(blob.ctypes.data_as(np.ctypeslib.ctypes.c_void_p)) == 0
+    off = 0
+    srgb, hlginv = blob[0:1024], blob[1024:5120]
+    pqinv = blob[9216:13312]
+    hlgo = blob[13312:13312 + 65536]
+    pqo = blob[13312 + 65536:13312 + 131072]
+    for mine, which in ((srgb, 0), (hlginv, 1), (pqinv, 2), (hlgo, 3), (pqo, 4)):
+        ref = checker.lut(which)
+        assert (mine.view(np.uint32) == ref.view(np.uint32)).all(), which
+
+
+@pytest.mark.parametrize("w,h", [(1280, 720), (3840, 2160)])
+def test_api1_stages_full_size(gpu, checker, w, h):
+    """config 1 / config 4 geometry on synthetic frames: default API-1 settings."""
+    hb = T.make_p010(w, h, "noise")
+    sb = T.make_yuv420(w, h, "noise")
+    hdr, k1 = A.p010_image(hb, w, h, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+    sdr, k2 = A.yuv420_image(sb, w, h, A.CG_BT709)
+    g1, m1 = gpu.generate(sdr, hdr)
+    g2, m2 = checker.generate(sdr, hdr)
+    assert T.md_equal(m1, m2), (m1.as_dict(), m2.as_dict())
+    assert (g1 == g2).all(), int((g1 != g2).sum())
+    a = gpu.convert_yuv(sb, w, h, 0, 1)
+    b = checker.convert_yuv(sb, w, h, 0, 1)
+    assert (a == b).all()
+
+
+def test_apply_8k(gpu, checker):
+    """config 3 geometry: 7680x4320, RGBA8888 map at scale 1 -> RGBA half float, bit exact."""
+    w, h = 7680, 4320
+    sb = T.make_yuv420(w, h, "noise")
+    sdr, k2 = A.yuv420_image(sb, w, h, A.CG_BT709)
+    rs = np.random.RandomState(7)
+    gm = rs.randint(0, 256, (h, w, 4)).astype(np.uint8)
+    md = A.GainmapMetadata()
+    for i, (mx, mn) in enumerate(((65.1, 4.9e-5), (845.9, 2.7e-3), (1283.8, 4.9e-5))):
+        md.max_content_boost[i], md.min_content_boost[i], md.gamma[i] = mx, mn, 1.0
+        md.offset_sdr[i] = md.offset_hdr[i] = 1e-7
+    md.hdr_capacity_min, md.hdr_capacity_max, md.use_base_cg = 1.0, 4.926108, 0
+    gi = T.gm_image(gm, A.CG_BT2100)
+    a = gpu.apply(sdr, gi, md, A.CT_LINEAR)
+    b = checker.apply(sdr, gi, md, A.CT_LINEAR)
+    assert (a == b).all(), int((a != b).sum())
