@@ -1,0 +1,294 @@
+#include "codec.h"
+
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+namespace uhdr_b200 {
+
+__attribute__((weak)) int jpeg_entropy_dev(Workspace&, JpegEncodeJob*) { return E_UNSUPPORTED; }
+__attribute__((weak)) bool gpu_entropy_available() { return false; }
+
+// ------------------------------------------------------------------------------------------------
+// encode
+// ------------------------------------------------------------------------------------------------
+static int entropy_or_fetch(Workspace& ws, JpegEncodeJob* job) {
+  if (gpu_entropy_available() && !job->frame.has_dummy_blocks()) return jpeg_entropy_dev(ws, job);
+  return jpeg_fetch_coefs(ws, job);
+}
+
+int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b200_gm_config_t& cfg_in,
+                       int base_quality, const uint8_t* exif, size_t exif_size, uint8_t* out, size_t cap,
+                       size_t* out_size) {
+  uhdr_b200_gm_config_t cfg = cfg_in;
+  DevImage sdr;
+  int rc;
+  if (sdr_in) {
+    sdr = *sdr_in;
+  } else {
+    // API-0: tone map first (jpegr.cpp:181-213); preset forced to REALTIME, max-RGB gain
+    int sdr_fmt;
+    if (hdr.v.fmt == F_P010) sdr_fmt = F_YUV420;
+    else if (hdr.v.fmt == F_YUV444_10) sdr_fmt = F_YUV444;
+    else if (hdr.v.fmt == F_RGBA1010102 || hdr.v.fmt == F_RGBAF16) sdr_fmt = F_RGBA8888;
+    else return fail(E_INVALID_PARAM, "unsupported hdr intent color format %d", hdr.v.fmt);
+    rc = alloc_dev_image(ws_, sdr_fmt, hdr.v.w, hdr.v.h, 64, &sdr);
+    if (rc) return rc;
+    rc = tonemap_dev(ws_, hdr, &sdr);
+    if (rc) return rc;
+    cfg.preset = UHDR_USAGE_REALTIME;
+    cfg.sdr_is_601 = 0;
+    cfg.use_luminance = 0;
+  }
+  GainmapJob gm;
+  rc = generate_gainmap_dev(ws_, sdr, hdr, cfg, 64, &gm);
+  if (rc) return rc;
+  JpegEncodeJob gm_jpeg, base_jpeg;
+  rc = jpeg_forward_dev(ws_, gm.map, cfg.quality, &gm_jpeg);
+  if (rc) return rc;
+  rc = entropy_or_fetch(ws_, &gm_jpeg);
+  if (rc) return rc;
+  // base image: icc of the sdr intent's gamut is chosen before the yuv re-encoding (:260)
+  const int sdr_cg = sdr.cg;
+  if (fmt_is_rgb_host(sdr.v.fmt))
+    return fail(E_UNSUPPORTED, "RGBA8888 sdr intent needs convert_raw_input_to_ycbcr (gainmapmath.cpp:1291) "
+                "which is not part of the B200 hot path yet");
+  if (sdr_in) {
+    rc = convert_yuv_dev(ws_, &sdr, sdr.cg, UHDR_CG_DISPLAY_P3);  // :277
+    if (rc) return rc;
+  }
+  rc = jpeg_forward_dev(ws_, sdr, base_quality, &base_jpeg);
+  if (rc) return rc;
+  rc = entropy_or_fetch(ws_, &base_jpeg);
+  if (rc) return rc;
+  rc = ws_.sync();
+  if (rc) return rc;
+  uhdr_gainmap_metadata_t md;
+  finish_gainmap_metadata(gm, &md);
+  size_t icc_gm_n = 0, icc_base_n = 0;
+  const uint8_t* icc_gm = icc_profile(gm.map.ct, gm.map.cg, &icc_gm_n);  // compressGainMap :520-528
+  const uint8_t* icc_base = icc_profile(UHDR_CT_SRGB, sdr_cg, &icc_base_n);
+  std::vector<uint8_t> gm_stream, base_stream;
+  rc = jpeg_finish_stream(gm_jpeg, icc_gm, icc_gm_n, jpeg_gainmap_comment(), &gm_stream);
+  if (rc) return rc;
+  rc = jpeg_finish_stream(base_jpeg, icc_base, icc_base_n, nullptr, &base_stream);
+  if (rc) return rc;
+  return assemble_jpegr(base_stream, gm_stream, exif, exif_size, md, out, cap, out_size);
+}
+
+int JpegRCodec::encode_host(const uhdr_raw_image_t& hdr, const uhdr_raw_image_t* sdr,
+                            const uhdr_b200_gm_config_t& cfg, int base_quality, const uint8_t* exif,
+                            size_t exif_size, uint8_t* out, size_t cap, size_t* out_size) {
+  ws_.rewind();
+  DevImage dh, ds;
+  int rc = upload_image(ws_, hdr, &dh);
+  if (rc) return rc;
+  if (sdr) {
+    rc = upload_image(ws_, *sdr, &ds);
+    if (rc) return rc;
+  }
+  return encode(dh, sdr ? &ds : nullptr, cfg, base_quality, exif, exif_size, out, cap, out_size);
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+static int sampling_format(const JpegFrame& f) {  // jpegdecoderhelper.cpp:141-166
+  if (f.ncomp == 1) return F_Y400;
+  float r[6];
+  for (int i = 0; i < 3; i++) {
+    r[i * 2] = ((float)f.comp[i].h_samp) / f.max_h;
+    r[i * 2 + 1] = ((float)f.comp[i].v_samp) / f.max_v;
+  }
+  if (r[0] == 1 && r[1] == 1 && r[2] == r[4] && r[3] == r[5]) {
+    if (r[2] == 1 && r[3] == 1) return F_YUV444;
+    if (r[2] == 1 && r[3] == 0.5) return 8;   // 440
+    if (r[2] == 0.5 && r[3] == 1) return F_YUV422;
+    if (r[2] == 0.5 && r[3] == 0.5) return F_YUV420;
+    if (r[2] == 0.25 && r[3] == 1) return 9;  // 411
+    if (r[2] == 0.25 && r[3] == 0.5) return 10;
+  }
+  return -1;
+}
+
+static int validate_header(const JpegHeader& h) {  // jpegdecoderhelper.cpp:244-342
+  const JpegFrame& f = h.frame;
+  if (f.width < 1 || f.height < 1)
+    return fail(E_ERROR, "received bad image width or height, wd = %d, ht = %d. wd and height shall be >= 1", f.width, f.height);
+  if (f.width > 8192 || f.height > 8192)
+    return fail(E_ERROR, "max width, max supported by library are %d, %d respectively. Current image width and height are %d, %d. "
+                "Recompile library with updated max supported dimensions to proceed", 8192, 8192, f.width, f.height);
+  if (f.ncomp != 1 && f.ncomp != 3)
+    return fail(E_ERROR, "ultrahdr primary image and supplimentary images are images encoded with 1 component (grayscale) "
+                "or 3 components (YCbCr / RGB). Unrecognized number of components %d", f.ncomp);
+  for (int i = 0, product = 0; i < f.ncomp; i++) {
+    if (f.comp[i].h_samp < 1 || f.comp[i].h_samp > 4 || f.comp[i].v_samp < 1 || f.comp[i].v_samp > 4)
+      return fail(E_ERROR, "received bad sampling factor for component index %d", i);
+    product += f.comp[i].h_samp * f.comp[i].v_samp;
+    if (product > 10) return fail(E_ERROR, "received bad sampling factors for components, sum of product of h_samp_factor, "
+                                  "v_samp_factor across all components exceeds 10");
+  }
+  if (f.ncomp == 3) {
+    if (f.comp[1].width > f.comp[0].width || f.comp[2].height > f.comp[0].height)
+      return fail(E_ERROR, "cb, cr planes are upsampled wrt luma plane");
+    if (f.comp[1].width != f.comp[2].width || f.comp[1].height != f.comp[2].height)
+      return fail(E_ERROR, "cb, cr planes are not sampled identically");
+  }
+  return E_OK;
+}
+
+static void grab_marker(const uint8_t* d, const JpegHeader& h, uint8_t id, const char* sig, size_t sig_len,
+                        std::vector<uint8_t>* out) {  // jpegdecoderhelper.cpp:119-139
+  out->clear();
+  for (const JpegMarker& m : h.markers)
+    if (m.id == id && m.length > sig_len && !memcmp(d + m.offset, sig, sig_len)) {
+      out->assign(d + m.offset, d + m.offset + m.length);
+      return;
+    }
+}
+
+int JpegRCodec::decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* h) {
+  if (!data) return fail(E_INVALID_PARAM, "received nullptr for compressed image data");
+  if (size == 0) return fail(E_INVALID_PARAM, "received bad compressed image size %zd", size);
+  int rc = jpeg_read_header(data, size, h);
+  if (rc) return rc;
+  rc = validate_header(*h);
+  if (rc) return rc;
+  const JpegFrame& f = h->frame;
+  if (mode == 2) mode = f.ncomp == 1 ? 0 : 1;  // DECODE_STREAM :344-346
+  if (h->adobe_transform == 0 && f.ncomp == 3)
+    return fail(E_UNSUPPORTED, "RGB (Adobe transform 0) JPEG input is not supported by the B200 decoder");
+  if (mode == 1 && f.ncomp == 1) return fail(E_ERROR, "expected input color space to be JCS_YCbCr or JCS_RGB but got %d", 1);
+  int16_t* h_coefs[3] = {nullptr, nullptr, nullptr};
+  for (int c = 0; c < f.ncomp; c++) {
+    h_coefs[c] = (int16_t*)ws_.halloc(f.blocks(c) * 128);
+    if (!h_coefs[c]) return E_MEM;
+  }
+  rc = jpeg_host_decode_coefs(data, size, *h, h_coefs);
+  if (rc) return rc;
+  memset(out, 0, sizeof *out);
+  out->cg = out->ct = -1;
+  out->range = UHDR_CR_FULL_RANGE;
+  out->v.full_range = 1;
+  out->v.w = f.width;
+  out->v.h = f.height;
+  uint8_t* planes[3] = {nullptr, nullptr, nullptr};
+  int strides[3] = {0, 0, 0};
+  for (int c = 0; c < f.ncomp; c++) {
+    strides[c] = f.comp[c].wblocks * 8;
+    planes[c] = (uint8_t*)ws_.dalloc((size_t)strides[c] * f.comp[c].hblocks * 8);
+    if (!planes[c]) return E_MEM;
+  }
+  rc = jpeg_inverse_dev(ws_, *h, h_coefs, planes, strides);
+  if (rc) return rc;
+  if (mode == 1) {
+    if (f.max_h != 1 || f.max_v != 1)
+      return fail(E_UNSUPPORTED, "RGB output of chroma-subsampled JPEG (libjpeg fancy upsampling) is outside the B200 hot path");
+    DevImage rgba;
+    rc = alloc_dev_image(ws_, F_RGBA8888, f.width, f.height, 1, &rgba);
+    if (rc) return rc;
+    YccToRgbaParams p;
+    p.y = planes[0]; p.cb = planes[1]; p.cr = planes[2];
+    p.src_stride = strides[0];
+    p.w = f.width;
+    p.h = f.height;
+    p.dst = (uint8_t*)rgba.v.p[0];
+    p.dst_stride = rgba.v.stride[0];
+    CUDA_TRY(launch_ycc_to_rgba(p, ws_.stream()));
+    rgba.range = UHDR_CR_FULL_RANGE;
+    *out = rgba;
+    out->cg = out->ct = -1;
+    return E_OK;
+  }
+  const int fmt = sampling_format(f);
+  if (fmt < 0) return fail(E_ERROR, "unrecognized subsampling format for output color space JCS_YCbCr");
+  out->v.fmt = fmt;
+  for (int c = 0; c < f.ncomp; c++) {
+    out->v.p[c] = planes[c];
+    out->v.stride[c] = strides[c];
+  }
+  return E_OK;
+}
+
+int JpegRCodec::probe(const uint8_t* data, size_t size, DecodedInfo* info) {
+  size_t po, pl, go, gl;
+  int rc = split_jpegr(data, size, &po, &pl, &go, &gl);
+  if (rc) return rc;
+  JpegHeader ph, gh;
+  rc = jpeg_read_header(data + po, pl, &ph);
+  if (rc) return rc;
+  rc = validate_header(ph);
+  if (rc) return rc;
+  rc = jpeg_read_header(data + go, gl, &gh);
+  if (rc) return rc;
+  rc = validate_header(gh);
+  if (rc) return rc;
+  info->width = ph.frame.width;
+  info->height = ph.frame.height;
+  info->gm_width = gh.frame.width;
+  info->gm_height = gh.frame.height;
+  info->base_jpeg.assign(data + po, data + po + pl);
+  info->gainmap_jpeg.assign(data + go, data + go + gl);
+  grab_marker(data + po, ph, 0xE1, "Exif\0\0", 6, &info->exif);
+  grab_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12, &info->icc);
+  std::vector<uint8_t> iso;
+  grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &iso);
+  if (iso.empty())
+    return fail(E_UNSUPPORTED, "gain map metadata in XMP form only; the B200 decoder reads ISO 21496-1 metadata");
+  rc = iso_decode_metadata(iso.data() + 28, iso.size() - 28, &info->metadata);
+  if (rc) return rc;
+  info->has_metadata = true;
+  return E_OK;
+}
+
+int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt, float max_display_boost,
+                       uhdr_raw_image_t* dest, uhdr_raw_image_t* gainmap_out, uhdr_gainmap_metadata_t* md_out) {
+  (void)out_fmt;
+  ws_.rewind();
+  size_t po, pl, go, gl;
+  int rc = split_jpegr(data, size, &po, &pl, &go, &gl);
+  if (rc) return rc;
+  if (out_ct == UHDR_CT_SRGB)
+    return fail(E_UNSUPPORTED, "sdr (UHDR_CT_SRGB) output is a plain libjpeg decode with chroma upsampling; outside the B200 hot path");
+  DevImage sdr, map;
+  JpegHeader ph, gh;
+  rc = decode_jpeg_dev(data + po, pl, 0, &sdr, &ph);  // DECODE_TO_YCBCR_CS :1479-1481
+  if (rc) return rc;
+  rc = decode_jpeg_dev(data + go, gl, 2, &map, &gh);  // DECODE_STREAM :1486
+  if (rc) return rc;
+  std::vector<uint8_t> blob;
+  grab_marker(data + go, gh, 0xE2, "ICC_PROFILE", 12, &blob);
+  map.cg = icc_read_gamut(blob.data(), blob.size());
+  grab_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12, &blob);
+  sdr.cg = icc_read_gamut(blob.data(), blob.size());
+  grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &blob);
+  if (blob.empty())
+    return fail(E_UNSUPPORTED, "gain map metadata in XMP form only; the B200 decoder reads ISO 21496-1 metadata");
+  uhdr_gainmap_metadata_t md;
+  rc = iso_decode_metadata(blob.data() + 28, blob.size() - 28, &md);
+  if (rc) return rc;
+  if (md_out) *md_out = md;
+  if (gainmap_out && gainmap_out->planes[0]) {
+    gainmap_out->fmt = (uhdr_img_fmt_t)map.v.fmt;
+    gainmap_out->w = map.v.w;
+    gainmap_out->h = map.v.h;
+    gainmap_out->cg = UHDR_CG_UNSPECIFIED;
+    gainmap_out->ct = UHDR_CT_UNSPECIFIED;
+    gainmap_out->range = UHDR_CR_FULL_RANGE;
+    rc = download_image(ws_, map, gainmap_out);
+    if (rc) return rc;
+  }
+  DevImage dst;
+  rc = alloc_dev_image(ws_, dest->fmt, sdr.v.w, sdr.v.h, 64, &dst);
+  if (rc) return rc;
+  rc = apply_gainmap_dev(ws_, sdr, map, md, out_ct, max_display_boost, &dst);
+  if (rc) return rc;
+  dest->cg = (uhdr_color_gamut_t)dst.cg;
+  dest->ct = (uhdr_color_transfer_t)out_ct;
+  dest->range = UHDR_CR_FULL_RANGE;
+  rc = download_image(ws_, dst, dest);
+  if (rc) return rc;
+  return ws_.sync();
+}
+
+}  // namespace uhdr_b200

@@ -1,0 +1,51 @@
+// Codec orchestration: the B200 counterpart of ultrahdr::JpegR (lib/include/ultrahdr/jpegr.h:52-222).
+// encodeJPEGR API-0 / API-1 and decodeJPEGR run their pixel and block stages on the device;
+// the marker/container layer is host code.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "container.h"
+#include "engine.h"
+#include "jpeg.h"
+
+namespace uhdr_b200 {
+
+struct DecodedInfo {
+  int width = 0, height = 0, gm_width = 0, gm_height = 0;
+  std::vector<uint8_t> exif, icc, base_jpeg, gainmap_jpeg;
+  uhdr_gainmap_metadata_t metadata{};
+  bool has_metadata = false;
+};
+
+class JpegRCodec {
+ public:
+  int init() { return ws_.init(); }
+  Workspace& ws() { return ws_; }
+
+  // JpegR::encodeJPEGR API-1 (jpegr.cpp:247-291) when sdr_dev != nullptr, API-0 (:179-244)
+  // otherwise.  Inputs are device images previously uploaded on ws().stream().
+  int encode(const DevImage& hdr, const DevImage* sdr, const uhdr_b200_gm_config_t& cfg, int base_quality,
+             const uint8_t* exif, size_t exif_size, uint8_t* out, size_t cap, size_t* out_size);
+  // convenience: host descriptors
+  int encode_host(const uhdr_raw_image_t& hdr, const uhdr_raw_image_t* sdr, const uhdr_b200_gm_config_t& cfg,
+                  int base_quality, const uint8_t* exif, size_t exif_size, uint8_t* out, size_t cap,
+                  size_t* out_size);
+
+  // JpegR::getJPEGRInfo (jpegr.cpp:1417-1430): sizes, exif/icc, metadata; no pixel work
+  int probe(const uint8_t* data, size_t size, DecodedInfo* info);
+  // JpegR::decodeJPEGR (jpegr.cpp:1469-1531).  dest: host descriptor with planes allocated by the
+  // caller (fmt/stride set); gainmap_out optional host descriptor (planes allocated, Y400/RGBA8888).
+  int decode(const uint8_t* data, size_t size, int out_ct, int out_fmt, float max_display_boost,
+             uhdr_raw_image_t* dest, uhdr_raw_image_t* gainmap_out, uhdr_gainmap_metadata_t* md_out);
+
+  // JpegDecoderHelper::decompressImage equivalent producing a device image
+  int decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* hdr);
+
+ private:
+  Workspace ws_;
+};
+
+bool gpu_entropy_available();
+
+}  // namespace uhdr_b200

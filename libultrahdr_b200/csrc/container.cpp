@@ -1,0 +1,395 @@
+#include "container.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "runtime.h"
+
+namespace uhdr_b200 {
+
+#include "icc_blobs.inc"
+
+// ---- rational conversion (gainmapmath.cpp:1616-1680), all intermediate math in double ---------
+static bool to_unsigned_fraction(float v, uint32_t max_num, uint32_t* num, uint32_t* den) {
+  if (std::isnan(v) || v < 0 || v > (float)max_num) return false;
+  const uint64_t max_d = (v <= 1) ? UINT32_MAX : (uint64_t)std::floor((double)((float)max_num / v));
+  *den = 1;
+  uint32_t prev_d = 0;
+  double cur = (double)v - std::floor((double)v);
+  for (int it = 0; it < 39; it++) {
+    const double nd = (double)(*den) * (double)v;
+    if (nd > (double)max_num) return false;
+    *num = (uint32_t)std::round(nd);
+    if (std::fabs(nd - (double)(*num)) == 0.0) return true;
+    cur = 1.0 / cur;
+    const double new_d = (double)prev_d + std::floor(cur) * (double)(*den);
+    if (new_d > (double)max_d) return true;
+    prev_d = *den;
+    if (new_d > (double)UINT32_MAX) return false;
+    *den = (uint32_t)new_d;
+    cur -= std::floor(cur);
+  }
+  *num = (uint32_t)std::round((double)(*den) * (double)v);
+  return true;
+}
+static bool to_signed_fraction(float v, int32_t* num, uint32_t* den) {
+  uint32_t pos;
+  if (!to_unsigned_fraction(std::fabs(v), INT32_MAX, &pos, den)) return false;
+  *num = (int32_t)pos;
+  if (v < 0) *num *= -1;
+  return true;
+}
+
+namespace {
+struct Frac {
+  int32_t min_n[3], max_n[3], base_off_n[3], alt_off_n[3];
+  uint32_t min_d[3], max_d[3], gamma_n[3], gamma_d[3], base_off_d[3], alt_off_d[3];
+  uint32_t base_headroom_n, base_headroom_d, alt_headroom_n, alt_headroom_d;
+  bool backward, use_base;
+};
+void be16(std::vector<uint8_t>& o, unsigned v) { o.push_back(v >> 8); o.push_back(v & 0xff); }
+void be32(std::vector<uint8_t>& o, uint32_t v) { for (int s = 24; s >= 0; s -= 8) o.push_back((v >> s) & 0xff); }
+bool md_single(const uhdr_gainmap_metadata_t& m) {
+  auto same = [](const float* a) { return a[0] == a[1] && a[0] == a[2]; };
+  return same(m.max_content_boost) && same(m.min_content_boost) && same(m.gamma) && same(m.offset_sdr) && same(m.offset_hdr);
+}
+}  // namespace
+
+int validate_metadata(const uhdr_gainmap_metadata_t& m) {  // ultrahdr_api.cpp:431-503
+  int rc = E_OK;
+  for (int i = 0; i < 3; i++) {
+    if (!std::isfinite(m.min_content_boost[i]) || !std::isfinite(m.max_content_boost[i]) ||
+        !std::isfinite(m.offset_sdr[i]) || !std::isfinite(m.offset_hdr[i]) || !std::isfinite(m.hdr_capacity_min) ||
+        !std::isfinite(m.hdr_capacity_max) || !std::isfinite(m.gamma[i]))
+      rc = fail(E_INVALID_PARAM, "Field(s) of gainmap metadata descriptor are either NaN or infinite.");
+    else if (m.max_content_boost[i] < m.min_content_boost[i])
+      rc = fail(E_INVALID_PARAM, "received bad value for content boost max %f, expects to be >= content boost min %f",
+                m.max_content_boost[i], m.min_content_boost[i]);
+    else if (m.min_content_boost[i] <= 0.0f)
+      return fail(E_INVALID_PARAM, "received bad value for min boost %f, expects > 0.0f", m.min_content_boost[i]);
+    else if (m.gamma[i] <= 0.0f)
+      rc = fail(E_INVALID_PARAM, "received bad value for gamma %f, expects > 0.0f", m.gamma[i]);
+    else if (m.offset_sdr[i] < 0.0f)
+      rc = fail(E_INVALID_PARAM, "received bad value for offset sdr %f, expects to be >= 0.0f", m.offset_sdr[i]);
+    else if (m.offset_hdr[i] < 0.0f)
+      rc = fail(E_INVALID_PARAM, "received bad value for offset hdr %f, expects to be >= 0.0f", m.offset_hdr[i]);
+    else if (m.hdr_capacity_max <= m.hdr_capacity_min)
+      rc = fail(E_INVALID_PARAM, "received bad value for hdr capacity max %f, expects to be > hdr capacity min %f",
+                m.hdr_capacity_max, m.hdr_capacity_min);
+    else if (m.hdr_capacity_min < 1.0f)
+      rc = fail(E_INVALID_PARAM, "received bad value for hdr capacity min %f, expects to be >= 1.0f", m.hdr_capacity_min);
+  }
+  return rc;
+}
+
+int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, std::vector<uint8_t>* out) {
+  Frac f;
+  memset(&f, 0, sizeof f);
+  f.backward = false;
+  f.use_base = md.use_base_cg != 0;
+  const bool single = md_single(md);
+#define SFRAC(v, n, d) if (!to_signed_fraction((float)(v), n, d)) return fail(E_INVALID_PARAM, "encountered error while representing float %f as a rational number (p/q form) ", (double)(v))
+#define UFRAC(v, n, d) if (!to_unsigned_fraction((float)(v), UINT32_MAX, n, d)) return fail(E_INVALID_PARAM, "encountered error while representing float %f as a rational number (p/q form) ", (double)(v))
+  for (int i = 0; i < (single ? 1 : 3); i++) {  // double log2 narrowed to float (gainmapmetadata.cpp:388-399)
+    SFRAC(std::log2((double)md.max_content_boost[i]), &f.max_n[i], &f.max_d[i]);
+    SFRAC(std::log2((double)md.min_content_boost[i]), &f.min_n[i], &f.min_d[i]);
+    UFRAC(md.gamma[i], &f.gamma_n[i], &f.gamma_d[i]);
+    SFRAC(md.offset_sdr[i], &f.base_off_n[i], &f.base_off_d[i]);
+    SFRAC(md.offset_hdr[i], &f.alt_off_n[i], &f.alt_off_d[i]);
+  }
+  if (single)
+    for (int i = 1; i < 3; i++) {
+      f.max_n[i] = f.max_n[0]; f.max_d[i] = f.max_d[0]; f.min_n[i] = f.min_n[0]; f.min_d[i] = f.min_d[0];
+      f.gamma_n[i] = f.gamma_n[0]; f.gamma_d[i] = f.gamma_d[0];
+      f.base_off_n[i] = f.base_off_n[0]; f.base_off_d[i] = f.base_off_d[0];
+      f.alt_off_n[i] = f.alt_off_n[0]; f.alt_off_d[i] = f.alt_off_d[0];
+    }
+  UFRAC(std::log2((double)md.hdr_capacity_min), &f.base_headroom_n, &f.base_headroom_d);
+  UFRAC(std::log2((double)md.hdr_capacity_max), &f.alt_headroom_n, &f.alt_headroom_d);
+#undef SFRAC
+#undef UFRAC
+  // serialisation gainmapmetadata.cpp:113-193
+  auto ident = [](const auto* a) { return a[0] == a[1] && a[0] == a[2]; };
+  const bool one = ident(f.min_n) && ident(f.min_d) && ident(f.max_n) && ident(f.max_d) && ident(f.gamma_n) &&
+                   ident(f.gamma_d) && ident(f.base_off_n) && ident(f.base_off_d) && ident(f.alt_off_n) && ident(f.alt_off_d);
+  const int channels = one ? 1 : 3;
+  std::vector<uint8_t>& o = *out;
+  o.clear();
+  be16(o, 0);
+  be16(o, 0);
+  uint8_t flags = 0;
+  if (channels == 3) flags |= 0x80;
+  if (f.use_base) flags |= 0x40;
+  if (f.backward) flags |= 4;
+  const uint32_t denom = f.base_headroom_d;
+  bool common = f.alt_headroom_d == denom;
+  for (int c = 0; c < channels; c++)
+    if (f.min_d[c] != denom || f.max_d[c] != denom || f.gamma_d[c] != denom || f.base_off_d[c] != denom || f.alt_off_d[c] != denom)
+      common = false;
+  if (common) flags |= 8;
+  o.push_back(flags);
+  if (common) {
+    be32(o, denom);
+    be32(o, f.base_headroom_n);
+    be32(o, f.alt_headroom_n);
+    for (int c = 0; c < channels; c++) {
+      be32(o, (uint32_t)f.min_n[c]); be32(o, (uint32_t)f.max_n[c]); be32(o, f.gamma_n[c]);
+      be32(o, (uint32_t)f.base_off_n[c]); be32(o, (uint32_t)f.alt_off_n[c]);
+    }
+  } else {
+    be32(o, f.base_headroom_n); be32(o, f.base_headroom_d); be32(o, f.alt_headroom_n); be32(o, f.alt_headroom_d);
+    for (int c = 0; c < channels; c++) {
+      be32(o, (uint32_t)f.min_n[c]); be32(o, f.min_d[c]); be32(o, (uint32_t)f.max_n[c]); be32(o, f.max_d[c]);
+      be32(o, f.gamma_n[c]); be32(o, f.gamma_d[c]); be32(o, (uint32_t)f.base_off_n[c]); be32(o, f.base_off_d[c]);
+      be32(o, (uint32_t)f.alt_off_n[c]); be32(o, f.alt_off_d[c]);
+    }
+  }
+  return E_OK;
+}
+
+int iso_decode_metadata(const uint8_t* d, size_t n, uhdr_gainmap_metadata_t* md) {
+  size_t p = 0;
+  auto need = [&](size_t k) { return p <= n && n - p >= k; };
+  auto r16 = [&](unsigned& v) { if (!need(2)) return false; v = (d[p] << 8) | d[p + 1]; p += 2; return true; };
+  auto r32 = [&](uint32_t& v) { if (!need(4)) return false; v = ((uint32_t)d[p] << 24) | (d[p + 1] << 16) | (d[p + 2] << 8) | d[p + 3]; p += 4; return true; };
+#define RD(x) if (!(x)) return fail(E_MEM, "attempting to read past the end of the gain map metadata (size %d)", (int)n)
+  unsigned minv = 0xffff, wv = 0xffff;
+  RD(r16(minv));
+  if (minv != 0) return fail(E_UNSUPPORTED, "received unexpected minimum version %d, expected 0", minv);
+  RD(r16(wv));
+  RD(need(1));
+  const uint8_t flags = d[p++];
+  const int channels = (flags & 0x80) ? 3 : 1;
+  Frac f;
+  memset(&f, 0, sizeof f);
+  f.use_base = (flags & 0x40) != 0;
+  f.backward = (flags & 4) != 0;
+  uint32_t u;
+  if (flags & 8) {
+    uint32_t den = 1;
+    RD(r32(den)); RD(r32(f.base_headroom_n)); f.base_headroom_d = den; RD(r32(f.alt_headroom_n)); f.alt_headroom_d = den;
+    for (int c = 0; c < channels; c++) {
+      RD(r32(u)); f.min_n[c] = (int32_t)u; f.min_d[c] = den;
+      RD(r32(u)); f.max_n[c] = (int32_t)u; f.max_d[c] = den;
+      RD(r32(f.gamma_n[c])); f.gamma_d[c] = den;
+      RD(r32(u)); f.base_off_n[c] = (int32_t)u; f.base_off_d[c] = den;
+      RD(r32(u)); f.alt_off_n[c] = (int32_t)u; f.alt_off_d[c] = den;
+    }
+  } else {
+    RD(r32(f.base_headroom_n)); RD(r32(f.base_headroom_d)); RD(r32(f.alt_headroom_n)); RD(r32(f.alt_headroom_d));
+    for (int c = 0; c < channels; c++) {
+      RD(r32(u)); f.min_n[c] = (int32_t)u; RD(r32(f.min_d[c]));
+      RD(r32(u)); f.max_n[c] = (int32_t)u; RD(r32(f.max_d[c]));
+      RD(r32(f.gamma_n[c])); RD(r32(f.gamma_d[c]));
+      RD(r32(u)); f.base_off_n[c] = (int32_t)u; RD(r32(f.base_off_d[c]));
+      RD(r32(u)); f.alt_off_n[c] = (int32_t)u; RD(r32(f.alt_off_d[c]));
+    }
+  }
+#undef RD
+  for (int c = channels; c < 3; c++) {
+    f.min_n[c] = f.min_n[0]; f.min_d[c] = f.min_d[0]; f.max_n[c] = f.max_n[0]; f.max_d[c] = f.max_d[0];
+    f.gamma_n[c] = f.gamma_n[0]; f.gamma_d[c] = f.gamma_d[0]; f.base_off_n[c] = f.base_off_n[0];
+    f.base_off_d[c] = f.base_off_d[0]; f.alt_off_n[c] = f.alt_off_n[0]; f.alt_off_d[c] = f.alt_off_d[0];
+  }
+  // gainmapMetadataFractionToFloat :301-347 (double exp2 of a float quotient, narrowed)
+  if (!f.base_headroom_d || !f.alt_headroom_d) return fail(E_INVALID_PARAM, "received 0 (bad value) for field HdrHeadroom denominator");
+  for (int i = 0; i < 3; i++)
+    if (!f.max_d[i] || !f.gamma_d[i] || !f.min_d[i] || !f.base_off_d[i] || !f.alt_off_d[i])
+      return fail(E_INVALID_PARAM, "received 0 (bad value) for a gain map metadata denominator");
+  if (f.backward) return fail(E_UNSUPPORTED, "hdr intent as base rendition is not supported");
+  for (int i = 0; i < 3; i++) {
+    md->max_content_boost[i] = (float)std::exp2((double)((float)f.max_n[i] / f.max_d[i]));
+    md->min_content_boost[i] = (float)std::exp2((double)((float)f.min_n[i] / f.min_d[i]));
+    md->gamma[i] = (float)f.gamma_n[i] / f.gamma_d[i];
+    md->offset_sdr[i] = (float)f.base_off_n[i] / f.base_off_d[i];
+    md->offset_hdr[i] = (float)f.alt_off_n[i] / f.alt_off_d[i];
+  }
+  md->hdr_capacity_max = (float)std::exp2((double)((float)f.alt_headroom_n / f.alt_headroom_d));
+  md->hdr_capacity_min = (float)std::exp2((double)((float)f.base_headroom_n / f.base_headroom_d));
+  md->use_base_cg = f.use_base;
+  return validate_metadata(*md);
+}
+
+const uint8_t* icc_profile(int ct, int cg, size_t* size) {
+  if (ct < 0 || ct > 3 || cg < 0 || cg > 2) return nullptr;
+  *size = kIccSizes[ct * 3 + cg];
+  return kIccBlobs[ct * 3 + cg];
+}
+
+int icc_read_gamut(const uint8_t* d, size_t n) {
+  const size_t kPrefix = 14, kHeader = 132;
+  if (!d || n < kHeader + kPrefix || memcmp(d, "ICC_PROFILE", 12) != 0) return UHDR_CG_UNSPECIFIED;
+  const uint8_t* icc = d + kPrefix;
+  const size_t psize = n - kPrefix;
+  auto be = [](const uint8_t* p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; };
+  const size_t tags = be(icc + 128);
+  if (tags > (psize - kHeader) / 12) return UHDR_CG_UNSPECIFIED;
+  size_t off[4] = {0, 0, 0, 0}, len[4] = {0, 0, 0, 0};  // rXYZ gXYZ bXYZ cicp
+  static const char* sig[4] = {"rXYZ", "gXYZ", "bXYZ", "cicp"};
+  for (size_t t = 0; t < tags; t++) {
+    const uint8_t* e = icc + kHeader + t * 12;
+    for (int k = 0; k < 4; k++)
+      if (off[k] == 0 && !memcmp(e, sig[k], 4)) { off[k] = be(e + 4); len[k] = be(e + 8); break; }
+  }
+  if (off[3] && len[3] == 12 && off[3] <= psize && len[3] <= psize - off[3]) {
+    const uint8_t prim = icc[off[3] + 8];
+    if (prim == 1) return UHDR_CG_BT_709;
+    if (prim == 12) return UHDR_CG_DISPLAY_P3;
+    if (prim == 9) return UHDR_CG_BT_2100;
+  }
+  for (int k = 0; k < 3; k++)
+    if (off[k] == 0 || len[k] != 20 || off[k] > psize || len[k] > psize - off[k]) return UHDR_CG_UNSPECIFIED;
+  // colorant matrices icc.h:125-145
+  const float F = 1.52587890625e-5f;
+  const float mats[3][3][3] = {
+      {{0x6FA2 * F, 0x6299 * F, 0x24A0 * F}, {0x38F5 * F, 0xB785 * F, 0x0F84 * F}, {0x0390 * F, 0x18DA * F, 0xB6CF * F}},
+      {{0.515102f, 0.291965f, 0.157153f}, {0.241182f, 0.692236f, 0.0665819f}, {-0.00104941f, 0.0418818f, 0.784378f}},
+      {{0.673459f, 0.165661f, 0.125100f}, {0.279033f, 0.675338f, 0.0456288f}, {-0.00193139f, 0.0299794f, 0.797162f}}};
+  for (int g = 0; g < 3; g++) {
+    bool ok = true;
+    for (int col = 0; col < 3 && ok; col++)
+      for (int row = 0; row < 3; row++) {
+        const float v = (float)(int32_t)be(icc + off[col] + 8 + 4 * row) * F;
+        if (std::fabs(v - mats[g][row][col]) > 0.001f) { ok = false; break; }
+      }
+    if (ok) return g;
+  }
+  return UHDR_CG_UNSPECIFIED;
+}
+
+// ---- MPF (multipictureformat.cpp) ---------------------------------------------------------------
+static void make_mpf(size_t primary_size, size_t secondary_size, size_t secondary_offset, std::vector<uint8_t>* o) {
+  o->clear();
+  static const uint8_t head[8] = {'M', 'P', 'F', 0, 0x4D, 0x4D, 0x00, 0x2A};
+  o->insert(o->end(), head, head + 8);
+  be32(*o, 8);            // index IFD offset
+  be16(*o, 3);            // tag count
+  be16(*o, 0xB000); be16(*o, 7); be32(*o, 4); o->insert(o->end(), {'0', '1', '0', '0'});
+  be16(*o, 0xB001); be16(*o, 4); be32(*o, 1); be32(*o, 2);
+  be16(*o, 0xB002); be16(*o, 7); be32(*o, 32);
+  be32(*o, (uint32_t)(o->size() - 4 + 4 + 4));  // MP entry offset
+  be32(*o, 0);                                   // attribute IFD offset
+  be32(*o, 0x030000); be32(*o, (uint32_t)primary_size); be32(*o, 0); be16(*o, 0); be16(*o, 0);
+  be32(*o, 0); be32(*o, (uint32_t)secondary_size); be32(*o, (uint32_t)secondary_offset); be16(*o, 0); be16(*o, 0);
+}
+
+int assemble_jpegr(const std::vector<uint8_t>& base, const std::vector<uint8_t>& gm, const uint8_t* exif,
+                   size_t exif_size, const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size) {
+  static const char kIsoNs[] = "urn:iso:std:iso:ts:21496:-1";  // 27 chars + NUL
+  const size_t ns_len = sizeof kIsoNs;
+  std::vector<uint8_t> iso;
+  int rc = iso_encode_metadata(md, &iso);
+  if (rc) return rc;
+  const size_t iso_secondary_len = 2 + ns_len + iso.size();
+  const size_t secondary_size = gm.size() + 2 + iso_secondary_len;
+  size_t pos = 0;
+  auto put = [&](const void* p, size_t n) {
+    if (pos + n > cap) return false;
+    memcpy(out + pos, p, n);
+    pos += n;
+    return true;
+  };
+  auto put_marker = [&](uint8_t m, size_t payload_len) {
+    const uint8_t h[4] = {0xFF, m, (uint8_t)(((payload_len + 2) >> 8) & 0xff), (uint8_t)((payload_len + 2) & 0xff)};
+    return put(h, 4);
+  };
+#define W(x) if (!(x)) return fail(E_MEM, "output buffer of %zu bytes is too small for the encoded stream", cap)
+  const uint8_t soi[2] = {0xFF, 0xD8};
+  W(put(soi, 2));
+  const uint8_t* b = base.data();
+  const size_t bn = base.size();
+  size_t bp = 2;
+  if (bn >= 6 && b[2] == 0xFF && b[3] == 0xE0) {  // JFIF first
+    const size_t l = (b[4] << 8) | b[5];
+    if (2 + 2 + l <= bn) W(put(b + 2, 2 + l));
+    bp += 2 + l;
+  }
+  if (exif && exif_size) { W(put_marker(0xE1, exif_size)); W(put(exif, exif_size)); }
+  // ICC carried by the base stream is re-emitted here (jpegr.cpp:1214-1217,1266-1275)
+  const uint8_t* icc = nullptr;
+  size_t icc_len = 0;
+  for (size_t q = bp; q + 4 <= bn && b[q] == 0xFF && b[q + 1] != 0xDA;) {
+    const size_t l = (b[q + 2] << 8) | b[q + 3];
+    if (b[q + 1] == 0xE2 && l > 2 + 12 && !memcmp(b + q + 4, "ICC_PROFILE", 12) && !icc) { icc = b + q + 4; icc_len = l - 2; }
+    q += 2 + l;
+  }
+  if (icc) { W(put_marker(0xE2, icc_len)); W(put(icc, icc_len)); }
+  {  // ISO version-only block
+    const uint8_t zeros[4] = {0, 0, 0, 0};
+    W(put_marker(0xE2, ns_len + 4)); W(put(kIsoNs, ns_len)); W(put(zeros, 4));
+  }
+  size_t sos = 0;
+  while (bp < bn) {  // DQT / SOF / DHT up to SOS, APPn dropped (:1313-1336)
+    if (b[bp] != 0xFF || bp + 1 >= bn) break;
+    const uint8_t m = b[bp + 1];
+    if (m == 0xDA) { sos = bp; break; }
+    if (m == 0x00 || m == 0xFF || (m >= 0xD0 && m <= 0xD7)) { bp += 2; continue; }
+    if (m == 0xD9 || bp + 4 > bn) break;
+    const size_t l = (b[bp + 2] << 8) | b[bp + 3];
+    if (bp + 2 + l > bn) break;
+    if (!(m >= 0xE0 && m <= 0xEF)) W(put(b + bp, 2 + l));
+    bp += 2 + l;
+  }
+  if (!sos) return fail(E_INVALID_PARAM, "SOS marker not found while reordering base jpeg segments, unable to append gainmap");
+  {
+    const size_t mpf_len = 2 + 86;
+    const size_t primary_size = pos + 2 + mpf_len + (bn - sos);
+    const size_t secondary_offset = primary_size - pos - 8;
+    std::vector<uint8_t> mpf;
+    make_mpf(primary_size, secondary_size, secondary_offset, &mpf);
+    W(put_marker(0xE2, mpf.size())); W(put(mpf.data(), mpf.size()));
+  }
+  W(put(b + sos, bn - sos));
+  W(put(soi, 2));
+  W(put_marker(0xE2, ns_len + iso.size())); W(put(kIsoNs, ns_len)); W(put(iso.data(), iso.size()));
+  W(put(gm.data() + 2, gm.size() - 2));
+#undef W
+  *out_size = pos;
+  return E_OK;
+}
+
+// ---- splitter: what image_io's JpegScanner + JpegInfoBuilder(limit 2) report -----------------------
+static bool scan_one(const uint8_t* d, size_t n, size_t start, size_t* end) {
+  size_t p = start + 2;
+  while (p + 4 <= n) {
+    if (d[p] != 0xFF) return false;
+    const uint8_t m = d[p + 1];
+    if (m == 0xFF) { p++; continue; }
+    if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { p += 2; continue; }
+    if (m == 0xD9) { *end = p + 2; return true; }
+    const size_t l = (d[p + 2] << 8) | d[p + 3];
+    if (l < 2 || p + 2 + l > n) return false;
+    p += 2 + l;
+    if (m == 0xDA) {  // entropy-coded data up to the next real marker
+      while (p + 1 < n) {
+        if (d[p] == 0xFF && d[p + 1] != 0x00 && !(d[p + 1] >= 0xD0 && d[p + 1] <= 0xD7) && d[p + 1] != 0xFF) break;
+        p++;
+      }
+    }
+  }
+  return false;
+}
+int split_jpegr(const uint8_t* d, size_t n, size_t* po, size_t* pl, size_t* go, size_t* gl) {
+  size_t found = 0, p = 0, off[2], len[2];
+  while (found < 2 && p + 4 <= n) {
+    if (d[p] == 0xFF && d[p + 1] == 0xD8) {
+      size_t e;
+      if (!scan_one(d, n, p, &e)) break;
+      off[found] = p;
+      len[found] = e - p;
+      found++;
+      p = e;
+    } else {
+      p++;
+    }
+  }
+  if (found == 0) return fail(E_INVALID_PARAM, "input uhdr image does not contain any valid images");
+  *po = off[0];
+  *pl = len[0];
+  if (found == 1) return fail(E_INVALID_PARAM, "input uhdr image does not contain gainmap image");
+  *go = off[1];
+  *gl = len[1];
+  return E_OK;
+}
+
+}  // namespace uhdr_b200

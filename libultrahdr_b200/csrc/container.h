@@ -1,0 +1,37 @@
+// Host container layer of the JPEG/R file: the byte-shuffling the reference does in
+// JpegR::appendGainMap (lib/src/jpegr.cpp:1105-1415), gainmapmetadata.cpp (ISO 21496-1 codec),
+// multipictureformat.cpp (MPF) and the image splitter (jpegr.cpp:1833-1900).  Pure CPU, tiny;
+// only its observable bytes matter (SURVEY.md section 2 marks it out of the hot path) but the
+// drop-in C API needs it to produce/consume real files.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/ultrahdr_api.h"
+
+namespace uhdr_b200 {
+
+// ISO 21496-1 payload for the gain-map image (gainmapmetadata.cpp:113-193 after
+// gainmapMetadataFloatToFraction :349-425). Returns uhdr_codec_err_t.
+int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, std::vector<uint8_t>* out);
+// inverse (:195-347); validates like uhdr_validate_gainmap_metadata_descriptor
+int iso_decode_metadata(const uint8_t* data, size_t size, uhdr_gainmap_metadata_t* md);
+int validate_metadata(const uhdr_gainmap_metadata_t& md);
+
+// ICC profile (with "ICC_PROFILE" prefix) the reference writes for (ct, cg); nullptr if unknown
+const uint8_t* icc_profile(int ct, int cg, size_t* size);
+// IccHelper::readIccColorGamut (icc.cpp:640-748)
+int icc_read_gamut(const uint8_t* data, size_t size);
+
+// appendGainMap with UHDR_WRITE_ISO on / UHDR_WRITE_XMP off (the reference's default build).
+// primary / gainmap are complete JFIF streams as the JPEG encoder produced them.
+int assemble_jpegr(const std::vector<uint8_t>& primary, const std::vector<uint8_t>& gainmap,
+                   const uint8_t* exif, size_t exif_size, const uhdr_gainmap_metadata_t& md,
+                   uint8_t* out, size_t cap, size_t* out_size);
+
+// locate primary image and gain-map image inside a JPEG/R file
+int split_jpegr(const uint8_t* data, size_t size, size_t* p_off, size_t* p_len, size_t* g_off,
+                size_t* g_len);
+
+}  // namespace uhdr_b200

@@ -55,6 +55,12 @@ int alloc_dev_image(Workspace& ws, int fmt, int w, int h, int stride_align, DevI
     // 8 spare rows: the JPEG block stage reads whole 8-row blocks
     void* p = ws.dalloc((size_t)stride * (ph + 8) * esz);
     if (!p) return E_MEM;
+    // bytes between the plane width and its stride must be defined: the JPEG block stage reads
+    // whole 8-sample blocks, and the reference's internal copies are zero initialised
+    // (uhdr_memory_block, ultrahdr_api.cpp:50-117)
+    if (pw % 8 != 0 || fmt == F_RGB888)
+      if (cudaMemsetAsync(p, 0, (size_t)stride * (ph + 8) * esz, ws.stream()) != cudaSuccess)
+        return fail(E_ERROR, "cudaMemsetAsync failed");
     out->v.p[i] = p;
     out->v.stride[i] = stride;
   }

@@ -16,6 +16,7 @@ struct DevImage {  // a uhdr_raw_image_t whose planes live in device memory
 };
 
 int fmt_planes(int fmt);
+inline bool fmt_is_rgb_host(int f) { return f == F_RGBAF16 || f == F_RGBA8888 || f == F_RGBA1010102; }
 // elements per row (w or chroma width), rows and element size of plane `i`
 void fmt_plane_geom(int fmt, int w, int h, int i, int* pw, int* ph, int* esz);
 

@@ -150,3 +150,15 @@ REF_API int ref_jpeg_encode(uhdr_raw_image_t* img, int quality, const void* icc,
   memcpy(out, e.getCompressedImagePtr(), *out_size);
   return 0;
 }
+
+/* ICC profile as the reference writes it (lib/src/icc.cpp:404); data includes the
+ * "ICC_PROFILE\0" + chunk bytes prefix.  Used by tools/make_icc_blobs.py */
+#include "ultrahdr/icc.h"
+REF_API int ref_icc_profile(int ct, int cg, uint8_t* out, size_t cap) {
+  std::shared_ptr<DataStruct> icc = IccHelper::writeIccProfile((uhdr_color_transfer_t)ct, (uhdr_color_gamut_t)cg);
+  if (!icc) return -1;
+  if ((size_t)icc->getLength() > cap) return -(int)icc->getLength();
+  memcpy(out, icc->getData(), icc->getLength());
+  return icc->getLength();
+}
+REF_API int ref_icc_gamut(void* data, size_t n) { return IccHelper::readIccColorGamut(data, n); }

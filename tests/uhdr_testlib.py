@@ -215,3 +215,165 @@ def gm_image(gm, cg=-1, ct=-1, rng=-1):
 
 def md_equal(a, b):
     return bytes(a) == bytes(b)
+
+
+# ------------------------------------------------------------------------------------------------
+# JPEG helpers: oracle codec structs (oracle/jpeg_oracle.h) and thin wrappers
+# ------------------------------------------------------------------------------------------------
+class JoComp(C.Structure):
+    _fields_ = [(n, C.c_int) for n in "h_samp v_samp width height wblocks hblocks tq".split()]
+
+
+class JoFrame(C.Structure):
+    _fields_ = [(n, C.c_int) for n in "ncomp width height max_h max_v mcus_per_row mcu_rows".split()] + \
+               [("comp", JoComp * 3), ("qt", (C.c_uint16 * 64) * 2)]
+
+
+class JoMarker(C.Structure):
+    _fields_ = [("id", C.c_uint8), ("offset", C.c_size_t), ("length", C.c_size_t)]
+
+
+class JoHeader(C.Structure):
+    _fields_ = [("frame", JoFrame), ("comp_id", C.c_int * 3), ("restart_interval", C.c_int),
+                ("scan_offset", C.c_size_t), ("scan_end", C.c_size_t), ("markers", JoMarker * 64),
+                ("nmarkers", C.c_int), ("bits", ((C.c_uint8 * 17) * 2) * 2),
+                ("vals", ((C.c_uint8 * 256) * 2) * 2), ("have_tbl", (C.c_int * 2) * 2),
+                ("dc_sel", C.c_int * 3), ("ac_sel", C.c_int * 3)]
+
+
+def _planes3(img):
+    return (C.c_void_p * 3)(img.planes[0], img.planes[1], img.planes[2]), \
+        (C.c_uint * 3)(img.stride[0], img.stride[1], img.stride[2])
+
+
+def oracle_forward(lib, img, quality):
+    """-> (JoFrame, [coef arrays (nblocks,64) int16])"""
+    f = JoFrame()
+    assert lib.jo_frame_init(C.byref(f), img.fmt, img.w, img.h, quality) == 0
+    coefs = [np.zeros((f.comp[c].wblocks * f.comp[c].hblocks, 64), np.int16) for c in range(f.ncomp)]
+    cp = (C.c_void_p * 3)(*([c.ctypes.data for c in coefs] + [None] * (3 - f.ncomp)))
+    P, S = _planes3(img)
+    assert lib.jo_forward(C.byref(f), img.fmt, P, S, cp) == 0
+    return f, coefs
+
+
+def oracle_encode(lib, img, quality, icc=None, comment=None):
+    P, S = _planes3(img)
+    out = C.c_void_p()
+    n = C.c_size_t()
+    iccb = (C.c_uint8 * len(icc)).from_buffer_copy(icc) if icc else None
+    rc = lib.jo_encode(P, S, img.w, img.h, img.fmt, quality, iccb, C.c_size_t(len(icc) if icc else 0),
+                       comment, C.byref(out), C.byref(n))
+    assert rc == 0
+    return C.string_at(out, n.value)
+
+
+def oracle_decode(lib, data):
+    """-> (JoHeader, padded planes list)"""
+    h = JoHeader()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    assert lib.jo_read_header(buf, C.c_size_t(len(data)), C.byref(h)) == 0
+    f = h.frame
+    coefs = [np.zeros((f.comp[c].hblocks * f.comp[c].wblocks, 64), np.int16) for c in range(f.ncomp)]
+    cp = (C.c_void_p * 3)(*([c.ctypes.data for c in coefs] + [None] * (3 - f.ncomp)))
+    assert lib.jo_decode_coefs(buf, C.c_size_t(len(data)), C.byref(h), cp) == 0
+    planes = [np.zeros((f.comp[c].hblocks * 8, f.comp[c].wblocks * 8), np.uint8) for c in range(f.ncomp)]
+    pp = (C.c_void_p * 3)(*([p.ctypes.data for p in planes] + [None] * (3 - f.ncomp)))
+    lib.jo_inverse(C.byref(h), cp, pp)
+    return h, planes
+
+
+GM_COMMENT = b"Source: google libuhdr v2.0.2, Coder: libjpeg v62, Attrib: GainMap Image"
+
+
+def gpu_jpeg_forward(gpu, img, quality, frame):
+    coefs = [np.zeros((frame.comp[c].wblocks * frame.comp[c].hblocks, 64), np.int16) for c in range(frame.ncomp)]
+    cp = (C.c_void_p * 3)(*([c.ctypes.data for c in coefs] + [None] * (3 - frame.ncomp)))
+    rc = gpu.lib.uhdr_b200_jpeg_forward(C.byref(img), quality, cp)
+    assert rc == 0, gpu_err(gpu)
+    return coefs
+
+
+def gpu_err(gpu):
+    gpu.lib.uhdr_b200_last_error.restype = C.c_char_p
+    return gpu.lib.uhdr_b200_last_error()
+
+
+def gpu_jpeg_encode(gpu, img, quality, icc=None):
+    cap = img.w * img.h * 6 + (1 << 16)
+    out = np.zeros(cap, np.uint8)
+    n = C.c_size_t()
+    iccb = (C.c_uint8 * len(icc)).from_buffer_copy(icc) if icc else None
+    rc = gpu.lib.uhdr_b200_jpeg_encode(C.byref(img), quality, iccb, C.c_size_t(len(icc) if icc else 0),
+                                       out.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(n))
+    assert rc == 0, gpu_err(gpu)
+    return bytes(out[:n.value])
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference C API (ultrahdr_api.h), usable with either libuhdr_ref.so or libuhdr_b200.so
+# ------------------------------------------------------------------------------------------------
+class UhdrApi:
+    def __init__(self, lib):
+        self.lib = lib
+        lib.uhdr_create_encoder.restype = C.c_void_p
+        lib.uhdr_create_decoder.restype = C.c_void_p
+        for f in ("uhdr_enc_set_raw_image", "uhdr_encode", "uhdr_dec_set_image", "uhdr_decode",
+                  "uhdr_enc_set_quality", "uhdr_enc_set_gainmap_scale_factor", "uhdr_enc_set_preset",
+                  "uhdr_enc_set_using_multi_channel_gainmap", "uhdr_dec_set_out_img_format",
+                  "uhdr_dec_set_out_color_transfer", "uhdr_dec_set_out_max_display_boost", "uhdr_dec_probe",
+                  "uhdr_enc_set_gainmap_gamma", "uhdr_enc_set_min_max_content_boost"):
+            getattr(lib, f).restype = A.ErrorInfo
+        lib.uhdr_get_encoded_stream.restype = C.POINTER(A.CompressedImage)
+        lib.uhdr_get_decoded_image.restype = C.POINTER(A.RawImage)
+        lib.uhdr_get_decoded_gainmap_image.restype = C.POINTER(A.RawImage)
+        lib.uhdr_dec_get_gainmap_metadata.restype = C.POINTER(A.GainmapMetadata)
+        lib.uhdr_enc_set_gainmap_gamma.argtypes = [C.c_void_p, C.c_float]
+        lib.uhdr_dec_set_out_max_display_boost.argtypes = [C.c_void_p, C.c_float]
+        lib.uhdr_enc_set_min_max_content_boost.argtypes = [C.c_void_p, C.c_float, C.c_float]
+
+    @staticmethod
+    def _ck(e):
+        assert e.error_code == 0, (e.error_code, e.detail)
+
+    def encode(self, hdr, sdr=None, quality=95, gm_quality=95, scale=1, multichannel=1, preset=None):
+        L = self.lib
+        enc = C.c_void_p(L.uhdr_create_encoder())
+        try:
+            self._ck(L.uhdr_enc_set_raw_image(enc, C.byref(hdr), A.HDR_IMG))
+            if sdr is not None:
+                self._ck(L.uhdr_enc_set_raw_image(enc, C.byref(sdr), A.SDR_IMG))
+            self._ck(L.uhdr_enc_set_quality(enc, quality, A.BASE_IMG))
+            self._ck(L.uhdr_enc_set_quality(enc, gm_quality, A.GAIN_MAP_IMG))
+            self._ck(L.uhdr_enc_set_gainmap_scale_factor(enc, scale))
+            self._ck(L.uhdr_enc_set_using_multi_channel_gainmap(enc, multichannel))
+            if preset is not None:
+                self._ck(L.uhdr_enc_set_preset(enc, preset))
+            self._ck(L.uhdr_encode(enc))
+            o = L.uhdr_get_encoded_stream(enc).contents
+            return C.string_at(o.data, o.data_sz)
+        finally:
+            L.uhdr_release_encoder(enc)
+
+    def decode(self, data, out_fmt=A.FMT_RGBAF16, out_ct=A.CT_LINEAR, boost=None):
+        L = self.lib
+        dec = C.c_void_p(L.uhdr_create_decoder())
+        try:
+            buf = np.frombuffer(data, np.uint8).copy()
+            ci = A.CompressedImage(buf.ctypes.data, len(data), len(data), -1, -1, -1)
+            self._ck(L.uhdr_dec_set_image(dec, C.byref(ci)))
+            self._ck(L.uhdr_dec_set_out_img_format(dec, out_fmt))
+            self._ck(L.uhdr_dec_set_out_color_transfer(dec, out_ct))
+            if boost is not None:
+                self._ck(L.uhdr_dec_set_out_max_display_boost(dec, boost))
+            self._ck(L.uhdr_decode(dec))
+            d = L.uhdr_get_decoded_image(dec).contents
+            bpp = 8 if out_fmt == A.FMT_RGBAF16 else 4
+            px = np.ctypeslib.as_array(C.cast(d.planes[0], C.POINTER(C.c_uint8)), (d.h, d.stride[0] * bpp)).copy()
+            g = L.uhdr_get_decoded_gainmap_image(dec).contents
+            gb = 1 if g.fmt == A.FMT_Y400 else 4
+            gm = np.ctypeslib.as_array(C.cast(g.planes[0], C.POINTER(C.c_uint8)), (g.h, g.stride[0] * gb)).copy()
+            md = A.GainmapMetadata.from_buffer_copy(bytes(L.uhdr_dec_get_gainmap_metadata(dec).contents))
+            return px[:, :d.w * bpp], gm[:, :g.w * gb], md, d.cg
+        finally:
+            L.uhdr_release_decoder(dec)
