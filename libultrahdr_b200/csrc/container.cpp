@@ -351,12 +351,13 @@ int assemble_jpegr(const std::vector<uint8_t>& base, const std::vector<uint8_t>&
 // ---- splitter: what image_io's JpegScanner + JpegInfoBuilder(limit 2) report -----------------------
 static bool scan_one(const uint8_t* d, size_t n, size_t start, size_t* end) {
   size_t p = start + 2;
-  while (p + 4 <= n) {
+  while (p + 2 <= n) {
     if (d[p] != 0xFF) return false;
     const uint8_t m = d[p + 1];
     if (m == 0xFF) { p++; continue; }
     if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { p += 2; continue; }
     if (m == 0xD9) { *end = p + 2; return true; }
+    if (p + 4 > n) return false;
     const size_t l = (d[p + 2] << 8) | d[p + 3];
     if (l < 2 || p + 2 + l > n) return false;
     p += 2 + l;
@@ -371,7 +372,7 @@ static bool scan_one(const uint8_t* d, size_t n, size_t start, size_t* end) {
 }
 int split_jpegr(const uint8_t* d, size_t n, size_t* po, size_t* pl, size_t* go, size_t* gl) {
   size_t found = 0, p = 0, off[2], len[2];
-  while (found < 2 && p + 4 <= n) {
+  while (found < 2 && p + 2 <= n) {
     if (d[p] == 0xFF && d[p + 1] == 0xD8) {
       size_t e;
       if (!scan_one(d, n, p, &e)) break;

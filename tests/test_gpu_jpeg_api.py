@@ -75,22 +75,29 @@ def test_decode_planes(gpu, oracle_libs):
             buf = np.zeros(w * h * 4 + 65536, np.uint8)
             out = A.raw_image(-1, -1, -1, -1, 0, 0, [buf], [0])
             cbuf = (C.c_uint8 * len(data)).from_buffer_copy(data)
-            rc = gpu.lib.uhdr_b200_jpeg_decode(cbuf, C.c_size_t(len(data)), 2, C.byref(out), C.c_size_t(buf.size))
+            mode = 0 if fmt == A.FMT_YUV420 else 2
+            rc = gpu.lib.uhdr_b200_jpeg_decode(cbuf, C.c_size_t(len(data)), mode, C.byref(out), C.c_size_t(buf.size))
             assert rc == 0, T.gpu_err(gpu)
             if f.ncomp == 1:
                 got = buf[:w * h].reshape(h, w)
                 assert (got == planes[0][:h, :w]).all()
+            elif mode == 0:  # raw planes laid out like JpegDecoderHelper::getDecompressedImage
+                assert out.fmt == A.FMT_YUV420 and out.stride[0] == w and out.stride[1] == w // 2
+                off = 0
+                for c, (pw, ph) in enumerate(((w, h), (w // 2, h // 2), (w // 2, h // 2))):
+                    got = buf[off:off + pw * ph].reshape(ph, pw)
+                    assert (got == planes[c][:ph, :pw]).all(), (w, h, c)
+                    off += pw * ph
             else:  # DECODE_STREAM of a 3-component stream -> RGBA8888 through jdcolor.c
                 assert out.fmt == A.FMT_RGBA8888
                 got = buf[:w * h * 4].reshape(h, w, 4)
                 r = np.zeros(1, np.uint8); g = np.zeros(1, np.uint8); b = np.zeros(1, np.uint8)
-                if f.max_h == 1:
-                    rs = np.random.RandomState(0)
-                    for _ in range(200):
-                        yy, xx = rs.randint(h), rs.randint(w)
-                        o.jo_ycc_to_rgb(int(planes[0][yy, xx]), int(planes[1][yy, xx]), int(planes[2][yy, xx]),
-                                        r.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
-                        assert tuple(got[yy, xx]) == (r[0], g[0], b[0], 255)
+                rs = np.random.RandomState(0)
+                for _ in range(200):
+                    yy, xx = rs.randint(h), rs.randint(w)
+                    o.jo_ycc_to_rgb(int(planes[0][yy, xx]), int(planes[1][yy, xx]), int(planes[2][yy, xx]),
+                                    r.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+                    assert tuple(got[yy, xx]) == (r[0], g[0], b[0], 255)
 
 
 def _frames(w, h, kind="smooth"):
