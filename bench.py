@@ -1,0 +1,483 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of libuhdr_b200 (contract: see the task statement).
+
+Workload (BASELINE.json metric "MPix/s encode(API-1)+decode at 4K/8K"): one *step* = API-1 encode of
+a batch of F independent 3840x2160 frames (P010 HLG BT.2100 limited range + YUV420 BT.709, default
+encoder settings: q95/q95, multichannel gain map at scale 1, BEST_QUALITY two-pass) per GPU, through
+the drop-in C ABI (uhdr_create_encoder / uhdr_enc_set_raw_image / uhdr_encode /
+uhdr_get_encoded_stream).  Frames shard across ranks with no data-path collective ("scaling":
+"weak"); the only collective is one NCCL broadcast of the OETF/inverse-OETF LUT blob at start-up.
+
+  value : MPix/s with inputs already resident in HBM (uploaded by uhdr_enc_set_raw_image outside the
+          timed region; the timed region is uhdr_encode ... uhdr_get_encoded_stream: kernels,
+          entropy coding, D2H of the streams, container assembly).
+  e2e   : the same metric through the whole C-ABI sequence with HOST buffers every step (H2D of both
+          inputs and D2H of the stream inside the timed region).
+  extra : 8K decode (config 3) and 4K API-0 (config 2) device-resident numbers + applyGainMap roofline.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref: the reference sources
+compiled in place; JPEG arithmetic through oracle/jpeg_oracle.c) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from libultrahdr_b200 import ctypes_api as A  # noqa: E402
+
+W4K, H4K = 3840, 2160
+W8K, H8K = 7680, 4320
+MPIX_4K = W4K * H4K / 1e6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic frames: natural-image-like (smooth + texture) so the entropy coder sees realistic
+# statistics; every frame differs (phase shift) so a batch does not fit in L2 (8 x 37 MB > 126 MB)
+# ------------------------------------------------------------------------------------------------
+def make_frame(w, h, idx):
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    ph = 0.37 * idx
+    base = 0.5 + 0.35 * np.sin(xx / 211.0 + ph) * np.cos(yy / 173.0 - ph) + 0.1 * np.sin((xx + yy) / 37.0 + ph)
+    rs = np.random.RandomState(1000 + idx)
+    tex = rs.randn(h // 8, w // 8).astype(np.float32)
+    tex = np.kron(tex, np.ones((8, 8), np.float32)) * 0.02 + rs.randn(h, w).astype(np.float32) * 0.004
+    lum = np.clip(base + tex, 0, 1)
+    y10 = (64 + 876 * lum).astype(np.uint16)
+    cy, cx = np.mgrid[0:h // 2, 0:w // 2].astype(np.float32)
+    u = 512 + 180 * np.sin(cx / 97.0 + ph)
+    v = 512 + 180 * np.cos(cy / 83.0 - ph)
+    uv10 = np.stack([u, v], -1).astype(np.uint16)
+    p010 = np.concatenate([y10.ravel(), uv10.ravel()]).astype(np.uint16) << 6
+    # sdr: a tone-compressed rendition of the same scene
+    sl = np.clip(lum ** 0.8 * 0.9, 0, 1)
+    y8 = (255 * sl).astype(np.uint8)
+    u8 = (128 + 45 * np.sin(cx / 97.0 + ph)).astype(np.uint8)
+    v8 = (128 + 45 * np.cos(cy / 83.0 - ph)).astype(np.uint8)
+    yuv = np.concatenate([y8.ravel(), u8.ravel(), v8.ravel()])
+    return np.ascontiguousarray(p010), np.ascontiguousarray(yuv)
+
+
+def frame_descs(p010, yuv, w, h):
+    hdr, k1 = A.p010_image(p010, w, h, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+    sdr, k2 = A.yuv420_image(yuv, w, h, A.CG_BT709)
+    return hdr, sdr, (k1, k2)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in o.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def load_api(path):
+    lib = C.CDLL(path)
+    import uhdr_testlib as T
+    return T.UhdrApi(lib), lib
+
+
+def run_threads(n, fn):
+    errs = []
+
+    def wrap(i):
+        try:
+            fn(i)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=wrap, args=(i,)) for i in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise RuntimeError(errs[0])
+
+
+class EncoderSlot:
+    """one reusable encoder handle of the C API"""
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.h = C.c_void_p(lib.uhdr_create_encoder())
+
+    def set_inputs(self, hdr, sdr):
+        L = self.lib
+        e = L.uhdr_enc_set_raw_image(self.h, C.byref(hdr), A.HDR_IMG)
+        assert e.error_code == 0, e.detail
+        if sdr is not None:
+            e = L.uhdr_enc_set_raw_image(self.h, C.byref(sdr), A.SDR_IMG)
+            assert e.error_code == 0, e.detail
+
+    def encode(self):
+        e = self.lib.uhdr_encode(self.h)
+        assert e.error_code == 0, e.detail
+        return self.lib.uhdr_get_encoded_stream(self.h).contents.data_sz
+
+    def rearm(self):
+        assert self.lib.uhdr_b200_enc_rearm(self.h) == 0
+
+    def reset(self):
+        self.lib.uhdr_reset_encoder(self.h)
+
+
+def kernel_report(lib, reset=True):
+    buf = C.create_string_buffer(1 << 16)
+    n = lib.uhdr_b200_kernel_timing_report(buf, C.c_size_t(len(buf)), 1 if reset else 0)
+    out = {}
+    if n > 0:
+        for line in buf.value.decode().strip().split("\n"):
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+    return out
+
+
+# algorithmic bytes per launch (DESIGN.md "Kernels"), per full-resolution pixel, for the API-1
+# default configuration (P010 + YUV420 in, RGB888 map at scale 1)
+ALG_BYTES_PER_PX = {
+    "gainmap_pass1": 4.5 + 12.0,   # read P010 3 + YUV420 1.5, write 3 float gains
+    "gainmap_affine": 12.0 + 3.0,  # read gains, write RGB888
+    "gainmap_onepass": 4.5 + 3.0,
+    "yuv_convert": 3.0,            # in place 1.5 read + 1.5 written
+    "tonemap": 4.5,
+    "apply_gainmap": 13.5,         # YUV420 1.5 + RGBA8888 map 4 read, RGBA-F16 8 written
+}
+
+
+def bench_b200(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as G
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    so = os.path.join(ROOT, "libultrahdr_b200", "libuhdr_b200.so")
+    if not os.path.exists(so):
+        G.build()
+    api, lib = load_api(so)
+    lib.uhdr_b200_kernel_launches.restype = C.c_ulonglong
+    lib.uhdr_b200_lut_blob_floats.restype = C.c_size_t
+
+    # --- the one collective: rank 0 builds the LUT blob with the reference's host expressions,
+    #     broadcasts it over NCCL, every rank installs the received copy ---
+    nlut = lib.uhdr_b200_lut_blob_floats()
+    lut = torch.empty(nlut, dtype=torch.float32, device="cuda")
+    if rank == 0:
+        host = np.zeros(nlut, np.float32)
+        assert lib.uhdr_b200_build_lut_blob(host.ctypes.data_as(C.c_void_p)) == 0
+        lut.copy_(torch.from_numpy(host))
+    if world > 1:
+        dist.broadcast(lut, src=0)
+    torch.cuda.synchronize()
+    assert lib.uhdr_b200_install_lut_blob_dev(C.c_void_p(lut.data_ptr())) == 0
+
+    F = args.frames
+    slots_n = min(args.slots, F)
+    frames = [make_frame(W4K, H4K, rank * F + i) for i in range(F)]
+    descs = [frame_descs(p, y, W4K, H4K) for (p, y) in frames]
+    in_bytes = sum(p.nbytes + y.nbytes for (p, y) in frames)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(t):
+        if world == 1:
+            return t
+        x = torch.tensor([t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        return float(x.item())
+
+    # ---------------- device-resident: one handle per frame, inputs uploaded once ----------------
+    handles = [EncoderSlot(lib) for _ in range(F)]
+    for hnd, (hdr, sdr, _) in zip(handles, descs):
+        hnd.set_inputs(hdr, sdr)
+    out_bytes = [0] * F
+
+    def resident_step():
+        def work(s):
+            for i in range(s, F, slots_n):
+                handles[i].rearm()
+                out_bytes[i] = handles[i].encode()
+        run_threads(slots_n, work)
+
+    for _ in range(args.warmup):
+        resident_step()
+    lib.uhdr_b200_set_kernel_timing(1)
+    kernel_report(lib)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = lib.uhdr_b200_kernel_launches()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        resident_step()
+    torch.cuda.synchronize()
+    t_res = max_over_ranks(time.perf_counter() - t0)
+    launches = lib.uhdr_b200_kernel_launches() - l0
+    barrier()
+    sampler.stop_flag = True
+    kt = kernel_report(lib)
+    lib.uhdr_b200_set_kernel_timing(0)
+    value = world * F * args.steps * MPIX_4K / t_res
+
+    # ---------------- end to end: host buffers through the whole C-ABI sequence -----------------
+    e2e_slots = [EncoderSlot(lib) for _ in range(slots_n)]
+    e2e_out = [0] * F
+
+    def e2e_step():
+        def work(s):
+            sl = e2e_slots[s]
+            for i in range(s, F, slots_n):
+                sl.reset()
+                sl.set_inputs(descs[i][0], descs[i][1])
+                e2e_out[i] = sl.encode()
+        run_threads(slots_n, work)
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * F * args.steps * MPIX_4K / t_e2e
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    hbm = pk["hbm_gbs"]
+    # dominant kernel of the timed region
+    dom = max(kt.items(), key=lambda kv: kv[1][1]) if kt else (None, (0, 0.0))
+    roof = None
+    if dom[0]:
+        name, (cnt, ms) = dom
+        avg_ms = ms / cnt
+        bpp = ALG_BYTES_PER_PX.get(name)
+        if name == "fdct_quant":
+            # three launches per image (components); report the average launch: 3 B/sample
+            alg = (W4K * H4K * 1.5 + W4K * H4K * 3.0) * 3.0 / 6.0
+        else:
+            alg = bpp * W4K * H4K if bpp else None
+        if alg:
+            ach = alg / (avg_ms * 1e-3) / 1e9
+            roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
+                    "frac": round(ach / hbm, 4), "traffic": None, "avg_launch_ms": round(avg_ms, 4),
+                    "alg_bytes_per_launch": int(alg), "peak_kind": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
+    kernels = {k: {"launches": v[0], "avg_ms": round(v[1] / v[0], 4)} for k, v in sorted(kt.items())}
+
+    extra = extra_measurements(lib, api, hbm)
+
+    # ---------------- CPU baseline: the reference's own code on this box's host cores --------------
+    cpu = cpu_baseline(frames[:2])
+
+    line = {
+        "metric": "MPix/s encode(API-1) at 4K",
+        "value": round(value, 1), "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(t_res / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "api1_encode_3840x2160_p010hlg_bt2100+yuv420_bt709", "frames_per_gpu_per_step": F,
+                   "encoder_slots": slots_n, "quality": 95, "gainmap": "multichannel scale 1 two-pass",
+                   "l2_policy": "inputs larger than L2 (%d MB of frames per step, distinct per frame)" % (in_bytes >> 20),
+                   "timing": "wall clock between device-wide synchronisations around exactly K steps, max over ranks; "
+                             "per-kernel times from CUDA events on the launching streams"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": int(in_bytes),
+                "d2h_bytes_per_step": int(sum(e2e_out)), "ms_per_step": round(t_e2e / args.steps * 1e3, 3)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roof,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "extra": extra,
+        "stream_bytes_per_frame": int(sum(out_bytes) / max(1, F)),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_measurements(lib, api, hbm):
+    """config 3 (8K decode -> RGBA half float) and config 2 (4K API-0), device timings of the
+    kernels named by the north star; small step counts, not the headline."""
+    import uhdr_testlib as T
+    out = {}
+    try:
+        gpu = T.Gpu()
+        # applyGainMap at 8K: RGBA8888 map, scale 1 (13.5 B/px)
+        sb = T.make_yuv420(W8K, H8K, "noise")
+        sdr, k2 = A.yuv420_image(sb, W8K, H8K, A.CG_BT709)
+        gm = np.random.RandomState(7).randint(0, 256, (H8K, W8K, 4)).astype(np.uint8)
+        md = A.GainmapMetadata()
+        for i, (mx, mn) in enumerate(((65.1, 4.9e-5), (845.9, 2.7e-3), (1283.8, 4.9e-5))):
+            md.max_content_boost[i], md.min_content_boost[i], md.gamma[i] = mx, mn, 1.0
+            md.offset_sdr[i] = md.offset_hdr[i] = 1e-7
+        md.hdr_capacity_min, md.hdr_capacity_max, md.use_base_cg = 1.0, 4.926108, 0
+        gi = T.gm_image(gm, A.CG_BT2100)
+        lib.uhdr_b200_set_kernel_timing(1)
+        kernel_report(lib)
+        for _ in range(6):
+            gpu.apply(sdr, gi, md, A.CT_LINEAR)
+        kt = kernel_report(lib)
+        if "apply_gainmap" in kt:
+            cnt, ms = kt["apply_gainmap"]
+            avg = ms / cnt
+            alg = 13.5 * W8K * H8K
+            out["apply_gainmap_8k"] = {"avg_launch_ms": round(avg, 4), "mpix_s": round(W8K * H8K / 1e6 / (avg * 1e-3), 1),
+                                       "roofline": {"bound": "hbm", "achieved": round(alg / (avg * 1e-3) / 1e9, 1), "peak": hbm,
+                                                    "unit": "GB/s", "frac": round(alg / (avg * 1e-3) / 1e9 / hbm, 4),
+                                                    "alg_bytes_per_launch": int(alg)}}
+        # API-0 4K through the C API (resident inputs)
+        p010, _ = make_frame(W4K, H4K, 99)
+        hdr, _k = A.p010_image(p010, W4K, H4K, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+        sl = EncoderSlot(lib)
+        sl.set_inputs(hdr, None)
+        sl.encode()
+        kernel_report(lib)
+        t0 = time.perf_counter()
+        n = 5
+        for _ in range(n):
+            sl.rearm()
+            sl.encode()
+        dt = (time.perf_counter() - t0) / n
+        kt = kernel_report(lib)
+        out["api0_encode_4k"] = {"mpix_s_resident_1slot": round(MPIX_4K / dt, 1), "ms_per_frame": round(dt * 1e3, 3),
+                                 "kernels_avg_ms": {k: round(v[1] / v[0], 4) for k, v in kt.items()}}
+        lib.uhdr_b200_set_kernel_timing(0)
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)
+    return out
+
+
+def cpu_baseline(frames, reps=1):
+    """reference CPU path (oracle/_ref) on the host cores: API-1 4K encode of a bounded sample."""
+    import uhdr_testlib as T
+    if not T.have_ref():
+        return {"value": None, "unit": "MPix/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    api, lib = load_api(T.REF_SO)
+    ncpu = os.cpu_count() or 1
+    conc = max(1, min(len(frames), ncpu // 4))  # the reference uses min(hw,4) threads per call
+    descs = [frame_descs(p, y, W4K, H4K) for (p, y) in frames]
+    t0 = time.perf_counter()
+    done = [0]
+
+    def work(i):
+        for r in range(reps):
+            api.encode(descs[i % len(descs)][0], descs[i % len(descs)][1])
+            done[0] += 1
+    run_threads(conc, work)
+    dt = time.perf_counter() - t0
+    return {"value": round(done[0] * MPIX_4K / dt, 2), "unit": "MPix/s", "cores": min(ncpu, conc * 4), "kind": "reference",
+            "sample": "%d x 4K API-1 uhdr_encode calls, %d concurrent (each call uses the reference's own 4 worker threads), "
+                      "%.1f s; JPEG entropy/DCT via oracle/jpeg_oracle.c in place of libjpeg-turbo" % (done[0], conc, dt),
+            "host_cpus": ncpu}
+
+
+def bench_reference(args, rank, world):
+    if rank != 0:
+        return
+    import uhdr_testlib as T
+    T.ensure_oracle_built()
+    if not T.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libuhdr_ref.so not built (needs /root/reference at build time)"}))
+        return
+    api, lib = load_api(T.REF_SO)
+    ncpu = os.cpu_count() or 1
+    conc = max(1, ncpu // 4)
+    frames = [make_frame(W4K, H4K, i) for i in range(min(conc, 4))]
+    descs = [frame_descs(p, y, W4K, H4K) for (p, y) in frames]
+    per_step = conc
+
+    def step():
+        run_threads(conc, lambda i: api.encode(descs[i % len(descs)][0], descs[i % len(descs)][1]))
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps * MPIX_4K / dt
+    sample = "%d concurrent 4K API-1 uhdr_encode calls per step (reference uses 4 worker threads per call)" % conc
+    print(json.dumps({
+        "impl": "reference", "metric": "MPix/s encode(API-1) at 4K", "value": round(v, 2), "unit": "MPix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "api1_encode_3840x2160_p010hlg_bt2100+yuv420_bt709", "frames_per_step": per_step},
+        "cpu_baseline": {"value": round(v, 2), "unit": "MPix/s", "cores": min(ncpu, conc * 4), "kind": "reference", "sample": sample},
+        "e2e": {"value": round(v, 2), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=8, help="4K frames per GPU per step")
+    ap.add_argument("--slots", type=int, default=4, help="concurrent encoder handles (host threads) per GPU")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        if args.steps > 3:
+            args.steps = 3  # bounded sample: each step is seconds of CPU work
+        bench_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        bench_b200(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

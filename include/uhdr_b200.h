@@ -65,6 +65,14 @@ UHDR_EXTERN int uhdr_b200_jpeg_forward(const uhdr_raw_image_t* img, int quality,
 UHDR_EXTERN int uhdr_b200_jpeg_decode(const void* data, size_t size, int mode, uhdr_raw_image_t* out,
                                       size_t cap);
 
+/* Measurement hooks.  Kernel timing brackets every kernel launch with CUDA events on the
+ * launching stream and accumulates per-kernel totals ("name count total_ms" lines).
+ * uhdr_b200_enc_rearm() makes a finished encoder handle runnable again while keeping the inputs
+ * it uploaded at uhdr_enc_set_raw_image() time resident in HBM (streaming re-encode). */
+UHDR_EXTERN void uhdr_b200_set_kernel_timing(int on);
+UHDR_EXTERN int uhdr_b200_kernel_timing_report(char* buf, size_t cap, int reset);
+UHDR_EXTERN int uhdr_b200_enc_rearm(uhdr_codec_private_t* enc);
+
 /* LUT blob (OETF / inverse-OETF tables): build on the host with the reference's libm
  * expressions, or install a blob that was broadcast from rank 0 (NCCL) into device memory. */
 UHDR_EXTERN size_t uhdr_b200_lut_blob_floats(void);

@@ -63,7 +63,8 @@ struct Encoder : uhdr_codec_private {
   int scale = 1, multichannel = 1, preset = UHDR_USAGE_BEST_QUALITY, output_format = UHDR_CODEC_JPG;
   float gamma = 1.0f, min_boost = FLT_MIN, max_boost = FLT_MAX, target_nits = -1.0f;
   bool has_compressed = false;
-  std::vector<uint8_t> out;
+  std::unique_ptr<uint8_t[]> out;  // kept across resets; never zero-filled
+  size_t out_cap = 0;
   uhdr_compressed_image_t out_desc{};
   uhdr_error_info_t status = ok();
   void defaults() {
@@ -76,10 +77,9 @@ struct Encoder : uhdr_codec_private {
     gamma = 1.0f; min_boost = FLT_MIN; max_boost = FLT_MAX; target_nits = -1.0f;
     has_compressed = false;
     sailed = false;
-    out.clear();
     memset(&out_desc, 0, sizeof out_desc);
     status = ok();
-    if (ready && !init_rc) codec.ws().rewind();
+    if (ready && !init_rc) codec.ws().clear_floor();
   }
   Encoder() { defaults(); }
 };
@@ -196,6 +196,7 @@ UHDR_API uhdr_error_info_t uhdr_enc_set_raw_image(uhdr_codec_private_t* enc, uhd
   if (rc) return from_rc(rc);
   if (cudaStreamSynchronize(h->codec.ws().stream()) != cudaSuccess) return err(UHDR_CODEC_ERROR, "upload failed");
   h->raw[intent] = d;
+  h->codec.ws().set_floor();  // inputs stay resident; per-encode scratch is recycled above them
   return ok();
 }
 
@@ -304,7 +305,12 @@ UHDR_API uhdr_error_info_t uhdr_encode(uhdr_codec_private_t* enc) {
   }
   auto sdr = h->raw.find(UHDR_SDR_IMG);
   const size_t cap = std::max<size_t>(64 * 1024, (size_t)hdr->second.v.w * hdr->second.v.h * 3 * 2);  // :1294
-  h->out.resize(cap);
+  if (h->out_cap < cap) {
+    h->out.reset(new (std::nothrow) uint8_t[cap]);
+    h->out_cap = h->out ? cap : 0;
+  }
+  if (!h->out) { h->status = err(UHDR_CODEC_MEM_ERROR, "unable to allocate %zu bytes for the encoded stream", cap); return h->status; }
+  h->codec.ws().rewind();
   uhdr_b200_gm_config_t cfg;
   cfg.scale_factor = h->scale;
   cfg.quality = h->quality[UHDR_GAIN_MAP_IMG];
@@ -318,10 +324,10 @@ UHDR_API uhdr_error_info_t uhdr_encode(uhdr_codec_private_t* enc) {
   cfg.use_luminance = 1;
   size_t n = 0;
   int rc = h->codec.encode(hdr->second, sdr == h->raw.end() ? nullptr : &sdr->second, cfg, h->quality[UHDR_BASE_IMG],
-                           h->exif.empty() ? nullptr : h->exif.data(), h->exif.size(), h->out.data(), cap, &n);
+                           h->exif.empty() ? nullptr : h->exif.data(), h->exif.size(), h->out.get(), cap, &n);
   h->status = from_rc(rc);
   if (rc == E_OK) {
-    h->out_desc.data = h->out.data();
+    h->out_desc.data = h->out.get();
     h->out_desc.data_sz = n;
     h->out_desc.capacity = cap;
     h->out_desc.cg = UHDR_CG_UNSPECIFIED;
@@ -491,6 +497,22 @@ UHDR_API uhdr_error_info_t uhdr_add_effect_mirror(uhdr_codec_private_t* c, uhdr_
 UHDR_API uhdr_error_info_t uhdr_add_effect_rotate(uhdr_codec_private_t* c, int) { return no_effects(c); }
 UHDR_API uhdr_error_info_t uhdr_add_effect_crop(uhdr_codec_private_t* c, int, int, int, int) { return no_effects(c); }
 UHDR_API uhdr_error_info_t uhdr_add_effect_resize(uhdr_codec_private_t* c, int, int) { return no_effects(c); }
+
+// ---- measurement hooks (include/uhdr_b200.h) -------------------------------------------------------
+UHDR_API void uhdr_b200_set_kernel_timing(int on) { set_kernel_timing(on != 0); }
+UHDR_API int uhdr_b200_kernel_timing_report(char* buf, size_t cap, int reset) {
+  const std::string r = kernel_timing_report(reset != 0);
+  if (r.size() + 1 > cap) return -(int)r.size();
+  memcpy(buf, r.c_str(), r.size() + 1);
+  return (int)r.size();
+}
+UHDR_API int uhdr_b200_enc_rearm(uhdr_codec_private_t* enc) {
+  Encoder* h = as<Encoder>(enc);
+  if (!h) return fail(E_INVALID_PARAM, "received nullptr for uhdr codec instance");
+  h->sailed = false;
+  h->status = ok();
+  return E_OK;
+}
 
 // ---- stage-level JPEG entry points (include/uhdr_b200.h) ---------------------------------------------
 static JpegRCodec* tls_codec() {

@@ -194,7 +194,7 @@ int JpegRCodec::decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevI
     p.h = f.height;
     p.dst = (uint8_t*)rgba.v.p[0];
     p.dst_stride = rgba.v.stride[0];
-    CUDA_TRY(launch_ycc_to_rgba(p, ws_.stream()));
+    TIMED(ws_, "ycc_to_rgba", launch_ycc_to_rgba(p, ws_.stream()));
     rgba.range = UHDR_CR_FULL_RANGE;
     *out = rgba;
     out->cg = out->ct = -1;

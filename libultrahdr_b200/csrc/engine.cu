@@ -179,7 +179,7 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
     p.log2_min = std::log2(p.min_boost);  // float overloads: jpegr.cpp has `using namespace std`
     p.log2_max = std::log2(p.max_boost);
     p.gamma = cfg.gamma;
-    CUDA_TRY(launch_gainmap_onepass(p, ws.stream()));
+    TIMED(ws, "gainmap_onepass", launch_gainmap_onepass(p, ws.stream()));
     return E_OK;
   }
   p.gains = (float*)ws.dalloc(sizeof(float) * (size_t)mw * mh * p.nch);
@@ -188,7 +188,7 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   job->h_minmax = (float*)ws.halloc(64);
   if (!p.gains || !p.minmax || !d_minmax_f || !job->h_minmax) return E_MEM;
   CUDA_TRY(launch_gainmap_init_minmax(p.minmax, ws.stream()));
-  CUDA_TRY(launch_gainmap_pass1(p, ws.stream()));
+  TIMED(ws, "gainmap_pass1", launch_gainmap_pass1(p, ws.stream()));
   GainmapFinalizeParams f;
   f.minmax = p.minmax;
   f.minmax_f = d_minmax_f;
@@ -197,7 +197,7 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   f.has_user_min = cfg.min_content_boost != FLT_MIN;
   f.log2_user_max = f.has_user_max ? std::log2(cfg.max_content_boost) : 0.0f;
   f.log2_user_min = f.has_user_min ? std::log2(cfg.min_content_boost) : 0.0f;
-  CUDA_TRY(launch_gainmap_finalize(f, ws.stream()));
+  TIMED(ws, "gainmap_finalize", launch_gainmap_finalize(f, ws.stream()));
   AffineParams a;
   a.gains = p.gains;
   a.minmax_f = d_minmax_f;
@@ -207,7 +207,7 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   a.nch = p.nch;
   a.dst_stride = p.dst_stride;
   a.gamma = cfg.gamma;
-  CUDA_TRY(launch_gainmap_affine(a, ws.stream()));
+  TIMED(ws, "gainmap_affine", launch_gainmap_affine(a, ws.stream()));
   CUDA_TRY(cudaMemcpyAsync(job->h_minmax, d_minmax_f, 6 * sizeof(float), cudaMemcpyDeviceToHost, ws.stream()));
   return E_OK;
 }
@@ -326,7 +326,7 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
   p.luts = ws.luts();
   p.dst = (void*)dst->v.p[0];
   p.dst_stride = dst->v.stride[0];
-  CUDA_TRY(launch_apply_gainmap(p, ws.stream()));
+  TIMED(ws, "apply_gainmap", launch_apply_gainmap(p, ws.stream()));
   return E_OK;
 }
 
@@ -365,7 +365,7 @@ int tonemap_dev(Workspace& ws, const DevImage& hdr, DevImage* sdr) {
     p.dst_stride[i] = sdr->v.stride[i];
   }
   p.dst_fmt = sdr->v.fmt;
-  CUDA_TRY(launch_tonemap(p, ws.stream()));
+  TIMED(ws, "tonemap", launch_tonemap(p, ws.stream()));
   return E_OK;
 }
 
@@ -385,7 +385,7 @@ int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg) {
   p.w = img->v.w;
   p.h = img->v.h;
   p.fmt = img->v.fmt;
-  CUDA_TRY(launch_yuv_convert(p, ws.stream()));
+  TIMED(ws, "yuv_convert", launch_yuv_convert(p, ws.stream()));
   return E_OK;
 }
 

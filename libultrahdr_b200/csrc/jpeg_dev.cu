@@ -43,7 +43,7 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
       p.fill = c == 0 ? 0 : 128;
       p.rgb_comp = -1;
     }
-    CUDA_TRY(launch_fdct_quant(p, ws.stream()));
+    TIMED(ws, "fdct_quant", launch_fdct_quant(p, ws.stream()));
   }
   return E_OK;
 }
@@ -76,7 +76,7 @@ int jpeg_inverse_dev(Workspace& ws, const JpegHeader& h, int16_t* const h_coefs[
     p.dst_stride = plane_stride[c];
     p.dst_w = k.wblocks * 8 < plane_stride[c] ? k.wblocks * 8 : plane_stride[c];
     p.dst_h = k.hblocks * 8;
-    CUDA_TRY(launch_idct_dequant(p, ws.stream()));
+    TIMED(ws, "idct_dequant", launch_idct_dequant(p, ws.stream()));
   }
   return E_OK;
 }

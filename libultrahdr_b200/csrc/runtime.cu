@@ -1,7 +1,9 @@
 #include "runtime.h"
 
 #include <cstdarg>
+#include <atomic>
 #include <cstdio>
+#include <new>
 #include <map>
 #include <mutex>
 
@@ -104,11 +106,17 @@ void* Arena::alloc(size_t bytes, size_t align) {
          cudaGetErrorString(e));
     return nullptr;
   }
-  blocks_.push_back({base, sz, bytes});
+  blocks_.push_back({base, sz, bytes, 0});
   return base;
 }
 void Arena::rewind() {
-  for (auto& b : blocks_) b.used = 0;
+  for (auto& b : blocks_) b.used = b.floor;
+}
+void Arena::set_floor() {
+  for (auto& b : blocks_) b.floor = b.used;
+}
+void Arena::clear_floor() {
+  for (auto& b : blocks_) b.floor = b.used = 0;
 }
 size_t Arena::reserved() const {
   size_t s = 0;
@@ -130,7 +138,59 @@ int Workspace::init() {
 }
 int Workspace::sync() {
   CUDA_TRY(cudaStreamSynchronize(stream_));
+  if (!spans_.empty()) t_collect();
   return E_OK;
+}
+// ---- kernel timing ------------------------------------------------------------------------------
+static std::atomic<bool> g_timing{false};
+static std::mutex g_timing_mu;
+static std::map<std::string, std::pair<unsigned long long, double>> g_timing_acc;
+void set_kernel_timing(bool on) { g_timing = on; }
+bool kernel_timing_enabled() { return g_timing; }
+std::string kernel_timing_report(bool reset) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  std::string out;
+  char line[256];
+  for (auto& kv : g_timing_acc) {
+    snprintf(line, sizeof line, "%s %llu %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (reset) g_timing_acc.clear();
+  return out;
+}
+cudaEvent_t Workspace::get_event() {
+  if (!ev_pool_.empty()) {
+    cudaEvent_t e = ev_pool_.back();
+    ev_pool_.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void Workspace::t_begin(const char* name) {
+  if (!g_timing) return;
+  Span s{name, get_event(), get_event()};
+  cudaEventRecord(s.a, stream_);
+  spans_.push_back(s);
+}
+void Workspace::t_end() {
+  if (!g_timing || spans_.empty()) return;
+  cudaEventRecord(spans_.back().b, stream_);
+}
+void Workspace::t_collect() {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (auto& s : spans_) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      auto& acc = g_timing_acc[s.name];
+      acc.first++;
+      acc.second += ms;
+    }
+    ev_pool_.push_back(s.a);
+    ev_pool_.push_back(s.b);
+  }
+  spans_.clear();
 }
 
 }  // namespace uhdr_b200

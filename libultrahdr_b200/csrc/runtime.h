@@ -33,16 +33,33 @@ const float* device_luts();
 int install_luts_from_device(const void* dptr);
 int read_back_luts(float* host_out);
 
+void set_kernel_timing(bool on);
+bool kernel_timing_enabled();
+// "name count total_ms\n" lines; resets the accumulators when `reset`
+std::string kernel_timing_report(bool reset);
+
+#define TIMED(ws, name, call)        \
+  do {                               \
+    (ws).t_begin(name);              \
+    cudaError_t _te = (call);        \
+    (ws).t_end();                    \
+    CUDA_TRY(_te);                   \
+  } while (0)
+
 class Arena {
  public:
   explicit Arena(bool pinned_host) : pinned_(pinned_host) {}
   ~Arena();
   void* alloc(size_t bytes, size_t align = 256);  // nullptr on failure (last error set)
   void rewind();
+  // keep everything allocated so far, release what comes later (inputs stay resident while the
+  // per-encode scratch is recycled)
+  void set_floor();
+  void clear_floor();
   size_t reserved() const;
 
  private:
-  struct Block { char* base; size_t size, used; };
+  struct Block { char* base; size_t size, used, floor; };
   std::vector<Block> blocks_;
   bool pinned_;
 };
@@ -56,6 +73,13 @@ class Workspace {
   void* dalloc(size_t bytes) { return dev_.alloc(bytes); }
   void* halloc(size_t bytes) { return host_.alloc(bytes); }
   void rewind() { dev_.rewind(); host_.rewind(); }
+  void set_floor() { dev_.set_floor(); host_.set_floor(); }
+  void clear_floor() { dev_.clear_floor(); host_.clear_floor(); }
+  // per-kernel CUDA-event timing (enabled globally with set_kernel_timing); begin/end bracket one
+  // launch on this workspace's stream, collect() must run after the stream was synchronised
+  void t_begin(const char* name);
+  void t_end();
+  void t_collect();
   const float* luts() const { return luts_; }
   int sync();
 
@@ -64,6 +88,10 @@ class Workspace {
   cudaStream_t stream_ = nullptr;
   const float* luts_ = nullptr;
   int device_ = -1;
+  struct Span { const char* name; cudaEvent_t a, b; };
+  std::vector<Span> spans_;
+  std::vector<cudaEvent_t> ev_pool_;
+  cudaEvent_t get_event();
 };
 
 }  // namespace uhdr_b200
