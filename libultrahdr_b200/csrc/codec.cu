@@ -6,15 +6,20 @@
 
 namespace uhdr_b200 {
 
-__attribute__((weak)) int jpeg_entropy_dev(Workspace&, JpegEncodeJob*) { return E_UNSUPPORTED; }
-__attribute__((weak)) bool gpu_entropy_available() { return false; }
 
 // ------------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------------
-static int entropy_or_fetch(Workspace& ws, JpegEncodeJob* job) {
-  if (gpu_entropy_available() && !job->frame.has_dummy_blocks()) return jpeg_entropy_dev(ws, job);
-  return jpeg_fetch_coefs(ws, job);
+static bool use_device_entropy(int fmt, int w, int h) {
+  JpegFrame f;
+  if (jpeg_frame_init(&f, fmt, w, h, 90) != E_OK) return false;
+  return gpu_entropy_available() && !f.has_dummy_blocks();
+}
+static int block_stage(Workspace& ws, const DevImage& img, int quality, JpegEncodeJob* job) {
+  const bool dev = use_device_entropy(img.v.fmt, img.v.w, img.v.h);
+  int rc = jpeg_forward_dev(ws, img, quality, job, dev);
+  if (rc) return rc;
+  return dev ? jpeg_entropy_dev(ws, job) : jpeg_fetch_coefs(ws, job);
 }
 
 int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b200_gm_config_t& cfg_in,
@@ -44,9 +49,7 @@ int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b
   rc = generate_gainmap_dev(ws_, sdr, hdr, cfg, 64, &gm);
   if (rc) return rc;
   JpegEncodeJob gm_jpeg, base_jpeg;
-  rc = jpeg_forward_dev(ws_, gm.map, cfg.quality, &gm_jpeg);
-  if (rc) return rc;
-  rc = entropy_or_fetch(ws_, &gm_jpeg);
+  rc = block_stage(ws_, gm.map, cfg.quality, &gm_jpeg);
   if (rc) return rc;
   // base image: icc of the sdr intent's gamut is chosen before the yuv re-encoding (:260)
   const int sdr_cg = sdr.cg;
@@ -57,12 +60,16 @@ int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b
     rc = convert_yuv_dev(ws_, &sdr, sdr.cg, UHDR_CG_DISPLAY_P3);  // :277
     if (rc) return rc;
   }
-  rc = jpeg_forward_dev(ws_, sdr, base_quality, &base_jpeg);
-  if (rc) return rc;
-  rc = entropy_or_fetch(ws_, &base_jpeg);
+  rc = block_stage(ws_, sdr, base_quality, &base_jpeg);
   if (rc) return rc;
   rc = ws_.sync();
   if (rc) return rc;
+  if (gm_jpeg.h_scan_bytes || base_jpeg.h_scan_bytes) {  // sizes are known now: fetch the segments
+    if (gm_jpeg.h_scan_bytes && (rc = jpeg_entropy_fetch(ws_, &gm_jpeg))) return rc;
+    if (base_jpeg.h_scan_bytes && (rc = jpeg_entropy_fetch(ws_, &base_jpeg))) return rc;
+    rc = ws_.sync();
+    if (rc) return rc;
+  }
   uhdr_gainmap_metadata_t md;
   finish_gainmap_metadata(gm, &md);
   size_t icc_gm_n = 0, icc_base_n = 0;

@@ -44,17 +44,20 @@ struct JpegEncodeJob {
   uint8_t* d_scan = nullptr;      // stuffed entropy-coded segment
   unsigned* d_scan_bytes = nullptr;
   uint8_t* h_scan = nullptr;      // pinned copy
-  unsigned* h_scan_bytes = nullptr;
+  unsigned* h_scan_bytes = nullptr;  // pinned control words: [3] = bytes, [4] = overflow flag
   size_t scan_capacity = 0;
+  bool zigzag = false;            // d_coefs hold zigzag-ordered blocks
   int16_t* h_coefs[3] = {nullptr, nullptr, nullptr};  // pinned (host Huffman path)
 };
 
 // Enqueue the block stage for `img` (device image): colour conversion (RGB888 only), level
 // shift, FDCT, quantise.  Mirrors JpegEncoderHelper::compressImage's input handling
 // (jpegencoderhelper.cpp:131-309) including libjpeg's edge rules.
-int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncodeJob* job);
+int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncodeJob* job, bool zigzag = false);
 // Enqueue entropy coding on the device + async copy of the scan to pinned memory.
 int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job);
+// second phase, once the stream was synchronised and the sizes are on the host
+int jpeg_entropy_fetch(Workspace& ws, JpegEncodeJob* job);
 // Enqueue D2H of coefficients for the host entropy coder.
 int jpeg_fetch_coefs(Workspace& ws, JpegEncodeJob* job);
 // After stream sync: assemble SOI..EOI.  `comment` != nullptr adds the COM marker the reference

@@ -6,10 +6,11 @@
 
 namespace uhdr_b200 {
 
-int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncodeJob* job) {
+int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncodeJob* job, bool zigzag) {
   int rc = jpeg_frame_init(&job->frame, img.v.fmt, img.v.w, img.v.h, quality);
   if (rc) return rc;
   const JpegFrame& f = job->frame;
+  job->zigzag = zigzag;
   for (int c = 0; c < f.ncomp; c++) {
     const JpegComp& k = f.comp[c];
     job->d_coefs[c] = (int16_t*)ws.dalloc(f.blocks(c) * 128);
@@ -19,6 +20,7 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
     p.wblocks = k.wblocks;
     p.hblocks = k.hblocks;
     p.coefs = job->d_coefs[c];
+    p.zigzag_out = zigzag ? 1 : 0;
     memcpy(p.q, f.qt[k.tq], sizeof p.q);
     if (img.v.fmt == F_RGB888) {
       // jpeg_write_scanlines path: jccolor.c conversion, edges replicated (jcsample.c/jcprepct.c)

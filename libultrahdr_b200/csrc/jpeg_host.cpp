@@ -292,13 +292,12 @@ int jpeg_finish_stream(const JpegEncodeJob& job, const void* icc, size_t icc_siz
                        std::vector<uint8_t>* out) {
   out->clear();
   const JpegFrame& f = job.frame;
-  out->reserve(1024 + icc_size + (job.h_scan_bytes ? *job.h_scan_bytes : f.total_blocks() * 24));
+  out->reserve(1024 + icc_size + (job.h_scan_bytes ? job.h_scan_bytes[3] : f.total_blocks() * 24));
   write_headers(f, icc, icc_size, comment, out);
   if (job.h_scan_bytes) {
-    if (*job.h_scan_bytes > job.scan_capacity)
-      return fail(E_MEM, "entropy-coded segment (%u bytes) exceeds the device scan buffer (%zu)",
-                  *job.h_scan_bytes, job.scan_capacity);
-    out->insert(out->end(), job.h_scan, job.h_scan + *job.h_scan_bytes);
+    if (job.h_scan_bytes[4] || !job.h_scan)
+      return fail(E_MEM, "entropy-coded segment exceeds the device scan buffer (%zu bytes)", job.scan_capacity);
+    out->insert(out->end(), job.h_scan, job.h_scan + job.h_scan_bytes[3]);
   } else {
     const int16_t* c[3] = {job.h_coefs[0], job.h_coefs[1], job.h_coefs[2]};
     jpeg_host_entropy(f, c, out);

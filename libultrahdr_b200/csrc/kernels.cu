@@ -770,8 +770,17 @@ __device__ __forceinline__ int rgb_to_ycc_comp(int comp, int r, int g, int b) { 
   return (32768 * r - 27439 * g - 5329 * b + OFF + HALF - 1) >> 16;
 }
 
+// zigzag position -> natural index; after full unrolling the loads fold to constants
+__device__ __forceinline__ constexpr int zig(int i) {
+  constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                         41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                         30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+  return t[i];
+}
+
 // one thread = one 8x8 block; a warp covers 32 horizontally adjacent blocks so every row load of
 // the warp is one contiguous 256-byte segment.
+template <bool ZIGZAG>
 __global__ void __launch_bounds__(128) k_fdct_quant(const DctPlaneParams p) {
   const int bx = blockIdx.x * blockDim.x + threadIdx.x;
   const int by = blockIdx.y;
@@ -833,8 +842,9 @@ __global__ void __launch_bounds__(128) k_fdct_quant(const DctPlaneParams p) {
     unsigned w[4];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const int d = (int)sq[i + k] << 3;
-      int t = v[i + k];
+      const int src = ZIGZAG ? zig(i + k) : i + k;
+      const int d = (int)sq[src] << 3;
+      int t = v[src];
       const int a = abs(t) + (d >> 1);
       int qv = a >= d ? a / d : 0;
       qv = t < 0 ? -qv : qv;
@@ -1008,7 +1018,8 @@ cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s) {
 cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s) {
   dim3 b(128, 1);
   dim3 g((p.wblocks + 127) / 128, p.hblocks);
-  k_fdct_quant<<<g, b, 0, s>>>(p);
+  if (p.zigzag_out) k_fdct_quant<true><<<g, b, 0, s>>>(p);
+  else k_fdct_quant<false><<<g, b, 0, s>>>(p);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }

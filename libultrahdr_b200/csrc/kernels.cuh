@@ -101,6 +101,7 @@ struct DctPlaneParams {             // forward: samples -> coefficients
   int pad_mode;                     // 0: rows >= h read as `fill`; 1: replicate edges
   int fill;
   int rgb_comp;                     // -1 plane; 0/1/2 = Y/Cb/Cr computed from RGB888
+  int zigzag_out;                   // 1: store each block in zigzag order (device entropy coder)
   uint16_t q[64];                   // natural order
   int16_t* coefs;                   // [hblocks*wblocks][64]
 };
