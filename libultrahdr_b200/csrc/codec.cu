@@ -75,12 +75,15 @@ int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b
   size_t icc_gm_n = 0, icc_base_n = 0;
   const uint8_t* icc_gm = icc_profile(gm.map.ct, gm.map.cg, &icc_gm_n);  // compressGainMap :520-528
   const uint8_t* icc_base = icc_profile(UHDR_CT_SRGB, sdr_cg, &icc_base_n);
-  std::vector<uint8_t> gm_stream, base_stream;
-  rc = jpeg_finish_stream(gm_jpeg, icc_gm, icc_gm_n, jpeg_gainmap_comment(), &gm_stream);
+  std::vector<uint8_t> gm_head, base_head, gm_hs, base_hs;
+  JpegPieces pg, pb;
+  rc = jpeg_stream_pieces(gm_jpeg, icc_gm, icc_gm_n, jpeg_gainmap_comment(), &gm_head, &gm_hs, &pg.scan, &pg.scan_len);
   if (rc) return rc;
-  rc = jpeg_finish_stream(base_jpeg, icc_base, icc_base_n, nullptr, &base_stream);
+  rc = jpeg_stream_pieces(base_jpeg, icc_base, icc_base_n, nullptr, &base_head, &base_hs, &pb.scan, &pb.scan_len);
   if (rc) return rc;
-  return assemble_jpegr(base_stream, gm_stream, exif, exif_size, md, out, cap, out_size);
+  pg.head = gm_head.data(); pg.head_len = gm_head.size();
+  pb.head = base_head.data(); pb.head_len = base_head.size();
+  return assemble_jpegr(pb, pg, exif, exif_size, md, out, cap, out_size);
 }
 
 int JpegRCodec::encode_host(const uhdr_raw_image_t& hdr, const uhdr_raw_image_t* sdr,

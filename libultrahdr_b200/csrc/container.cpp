@@ -273,15 +273,15 @@ static void make_mpf(size_t primary_size, size_t secondary_size, size_t secondar
   be32(*o, 0); be32(*o, (uint32_t)secondary_size); be32(*o, (uint32_t)secondary_offset); be16(*o, 0); be16(*o, 0);
 }
 
-int assemble_jpegr(const std::vector<uint8_t>& base, const std::vector<uint8_t>& gm, const uint8_t* exif,
-                   size_t exif_size, const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size) {
+int assemble_jpegr(const JpegPieces& base, const JpegPieces& gm, const uint8_t* exif, size_t exif_size,
+                   const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size) {
   static const char kIsoNs[] = "urn:iso:std:iso:ts:21496:-1";  // 27 chars + NUL
   const size_t ns_len = sizeof kIsoNs;
   std::vector<uint8_t> iso;
   int rc = iso_encode_metadata(md, &iso);
   if (rc) return rc;
   const size_t iso_secondary_len = 2 + ns_len + iso.size();
-  const size_t secondary_size = gm.size() + 2 + iso_secondary_len;
+  const size_t secondary_size = gm.total() + 2 + iso_secondary_len;
   size_t pos = 0;
   auto put = [&](const void* p, size_t n) {
     if (pos + n > cap) return false;
@@ -294,12 +294,12 @@ int assemble_jpegr(const std::vector<uint8_t>& base, const std::vector<uint8_t>&
     return put(h, 4);
   };
 #define W(x) if (!(x)) return fail(E_MEM, "output buffer of %zu bytes is too small for the encoded stream", cap)
-  const uint8_t soi[2] = {0xFF, 0xD8};
+  const uint8_t soi[2] = {0xFF, 0xD8}, eoi[2] = {0xFF, 0xD9};
   W(put(soi, 2));
-  const uint8_t* b = base.data();
-  const size_t bn = base.size();
+  const uint8_t* b = base.head;
+  const size_t bn = base.head_len;
   size_t bp = 2;
-  if (bn >= 6 && b[2] == 0xFF && b[3] == 0xE0) {  // JFIF first
+  if (bn >= 6 && b[2] == 0xFF && b[3] == 0xE0) {  // JFIF first (:1225-1237)
     const size_t l = (b[4] << 8) | b[5];
     if (2 + 2 + l <= bn) W(put(b + 2, 2 + l));
     bp += 2 + l;
@@ -314,7 +314,7 @@ int assemble_jpegr(const std::vector<uint8_t>& base, const std::vector<uint8_t>&
     q += 2 + l;
   }
   if (icc) { W(put_marker(0xE2, icc_len)); W(put(icc, icc_len)); }
-  {  // ISO version-only block
+  {  // ISO version-only block (:1277-1292)
     const uint8_t zeros[4] = {0, 0, 0, 0};
     W(put_marker(0xE2, ns_len + 4)); W(put(kIsoNs, ns_len)); W(put(zeros, 4));
   }
@@ -333,16 +333,21 @@ int assemble_jpegr(const std::vector<uint8_t>& base, const std::vector<uint8_t>&
   if (!sos) return fail(E_INVALID_PARAM, "SOS marker not found while reordering base jpeg segments, unable to append gainmap");
   {
     const size_t mpf_len = 2 + 86;
-    const size_t primary_size = pos + 2 + mpf_len + (bn - sos);
+    const size_t tail = (bn - sos) + base.scan_len + 2;  // SOS header + entropy-coded data + EOI
+    const size_t primary_size = pos + 2 + mpf_len + tail;
     const size_t secondary_offset = primary_size - pos - 8;
     std::vector<uint8_t> mpf;
     make_mpf(primary_size, secondary_size, secondary_offset, &mpf);
     W(put_marker(0xE2, mpf.size())); W(put(mpf.data(), mpf.size()));
   }
   W(put(b + sos, bn - sos));
+  W(put(base.scan, base.scan_len));
+  W(put(eoi, 2));
   W(put(soi, 2));
   W(put_marker(0xE2, ns_len + iso.size())); W(put(kIsoNs, ns_len)); W(put(iso.data(), iso.size()));
-  W(put(gm.data() + 2, gm.size() - 2));
+  W(put(gm.head + 2, gm.head_len - 2));
+  W(put(gm.scan, gm.scan_len));
+  W(put(eoi, 2));
 #undef W
   *out_size = pos;
   return E_OK;

@@ -24,11 +24,20 @@ const uint8_t* icc_profile(int ct, int cg, size_t* size);
 // IccHelper::readIccColorGamut (icc.cpp:640-748)
 int icc_read_gamut(const uint8_t* data, size_t size);
 
+// One JFIF stream handed over in two pieces so that the (large) entropy-coded segment is copied
+// exactly once, straight from the pinned buffer the device wrote it to: `head` = SOI .. SOS header
+// (what libjpeg writes before the first MCU), `scan` = entropy-coded bytes; EOI is implied.
+struct JpegPieces {
+  const uint8_t* head;
+  size_t head_len;
+  const uint8_t* scan;
+  size_t scan_len;
+  size_t total() const { return head_len + scan_len + 2; }
+};
+
 // appendGainMap with UHDR_WRITE_ISO on / UHDR_WRITE_XMP off (the reference's default build).
-// primary / gainmap are complete JFIF streams as the JPEG encoder produced them.
-int assemble_jpegr(const std::vector<uint8_t>& primary, const std::vector<uint8_t>& gainmap,
-                   const uint8_t* exif, size_t exif_size, const uhdr_gainmap_metadata_t& md,
-                   uint8_t* out, size_t cap, size_t* out_size);
+int assemble_jpegr(const JpegPieces& primary, const JpegPieces& gainmap, const uint8_t* exif, size_t exif_size,
+                   const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size);
 
 // locate primary image and gain-map image inside a JPEG/R file
 int split_jpegr(const uint8_t* data, size_t size, size_t* p_off, size_t* p_len, size_t* g_off,

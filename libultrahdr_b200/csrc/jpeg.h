@@ -64,6 +64,11 @@ int jpeg_fetch_coefs(Workspace& ws, JpegEncodeJob* job);
 // writes for gain-map images (jpegencoderhelper.cpp:205-211).
 int jpeg_finish_stream(const JpegEncodeJob& job, const void* icc, size_t icc_size,
                        const char* comment, std::vector<uint8_t>* out);
+// Head (SOI .. SOS header) only, and the entropy-coded segment as a pointer: device path = the
+// pinned buffer, host path = `host_scan` filled here.  No copy of the segment is made.
+int jpeg_stream_pieces(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment,
+                       std::vector<uint8_t>* head, std::vector<uint8_t>* host_scan, const uint8_t** scan,
+                       size_t* scan_len);
 // host Huffman coder over [block][64] coefficient arrays
 void jpeg_host_entropy(const JpegFrame& f, const int16_t* const coefs[3], std::vector<uint8_t>* scan);
 

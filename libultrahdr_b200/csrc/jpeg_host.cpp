@@ -307,6 +307,26 @@ int jpeg_finish_stream(const JpegEncodeJob& job, const void* icc, size_t icc_siz
   return E_OK;
 }
 
+int jpeg_stream_pieces(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment,
+                       std::vector<uint8_t>* head, std::vector<uint8_t>* host_scan, const uint8_t** scan,
+                       size_t* scan_len) {
+  head->clear();
+  write_headers(job.frame, icc, icc_size, comment, head);
+  if (job.h_scan_bytes) {
+    if (job.h_scan_bytes[4] || !job.h_scan)
+      return fail(E_MEM, "entropy-coded segment exceeds the device scan buffer (%zu bytes)", job.scan_capacity);
+    *scan = job.h_scan;
+    *scan_len = job.h_scan_bytes[3];
+  } else {
+    host_scan->clear();
+    const int16_t* c[3] = {job.h_coefs[0], job.h_coefs[1], job.h_coefs[2]};
+    jpeg_host_entropy(job.frame, c, host_scan);
+    *scan = host_scan->data();
+    *scan_len = host_scan->size();
+  }
+  return E_OK;
+}
+
 // ---- decoder: marker parser (jdmarker.c subset) + Huffman decoder (jdhuff.c semantics) ----------
 int jpeg_read_header(const uint8_t* d, size_t n, JpegHeader* h) {
   *h = JpegHeader();
