@@ -1,0 +1,267 @@
+// applyGainMap fast path (jpegr.cpp:1714-1811) for the configurations that matter at scale:
+// YUV 4:2:0 base image (what JpegDecoderHelper hands over), integer map scale, gamma 1.
+// Same arithmetic as k_apply_gainmap (kernels.cu) -- operand order, rounding and tables are
+// identical -- but specialised at compile time and restructured for instruction issue, which is
+// what bounds this kernel (13.5 B/px of traffic against ~400 instructions/px in the generic one):
+//   * one thread = a 4x2 pixel tile: the two chroma samples and their products are computed once,
+//     loads are 4/2/2/16 bytes wide, every store instruction writes 16 B per lane (512 B per warp)
+//   * all tables in shared memory: sRGB-inverse LUT (4 KB) and, at scale 1, a 3x256 table that
+//     maps a gain-map byte straight to its gain factor (mapUintToFloat -> IDW {1,0,0,0} ->
+//     GainLUT index -> table value composed on the host with the reference's expressions);
+//     other integer scales keep the 3x1024 gain LUT + u8/255 + IDW weights in shared memory
+//   * floatToHalf: values are clamped to [0, 10000/203] first, so the normal-number branch is
+//     (bits + 0x1000) >> 13 - (112 << 10); the denormal branch is kept for tiny values
+#include "kernels.cuh"
+#include "tables.h"
+
+namespace uhdr_b200 {
+
+namespace {
+
+__device__ __forceinline__ int idx1023(float x) {  // x in [0, 1]: int32(double(x*1023) + 0.5)
+  const float v = x * 1023.0f;
+  const int i = __float2int_rz(v);
+  return i + ((v - (float)i) >= 0.5f ? 1 : 0);
+}
+__device__ __forceinline__ unsigned half_bits(float f) {  // f in [-0, 10000/203]
+  const unsigned b = __float_as_uint(f) + 0x00001000u;
+  if (b - (113u << 23) < (31u << 23)) return (b >> 13) - (112u << 10);  // positive, 113 <= e <= 143
+  const int e = (int)((b & 0x7F800000u) >> 23);
+  const unsigned m = b & 0x007FFFFFu;
+  unsigned r = (b & 0x80000000u) >> 16;
+  if (e > 112) r |= ((((unsigned)(e - 112)) << 10) & 0x7C00u) | (m >> 13);
+  if (e < 113 && e > 101) r |= (((0x007FF000u + m) >> (125 - e)) + 1) >> 1;
+  if (e > 143) r |= 0x7FFFu;
+  return r & 0xFFFFu;
+}
+
+struct FastSmem {
+  float srgb[1024];
+  float gain[3 * 1024];  // scale 1: first 3*256 entries hold the byte -> factor tables
+  float u8f[256];
+};
+
+template <int BPP, bool SCALE1, int GAMUT /*0 none 1 sdr side 2 hdr side*/, int OUT /*0 F16 1 PQ 2 HLG*/>
+__global__ void __launch_bounds__(128) k_apply_fast(const ApplyParams p, const float* __restrict__ gain_u8) {
+  extern __shared__ float smem_raw[];
+  FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+  float* idw = smem_raw + sizeof(FastSmem) / sizeof(float);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  for (int i = tid; i < 1024; i += nt) sm.srgb[i] = __ldg(p.luts + kLutSrgbInv + i);
+  if (SCALE1) {
+    for (int i = tid; i < 768; i += nt) sm.gain[i] = __ldg(gain_u8 + i);
+  } else {
+    for (int i = tid; i < 3072; i += nt) sm.gain[i] = __ldg(p.gain_lut + i);
+    for (int i = tid; i < 256; i += nt) sm.u8f[i] = __ldg(p.luts + kLutU8Div255 + i);
+    const int n = 16 * p.scale_int * p.scale_int;
+    for (int i = tid; i < n; i += nt) idw[i] = __ldg(p.idw + i);
+  }
+  __syncthreads();
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
+  if (x >= p.sdr.w || y >= p.sdr.h) return;
+  const uint8_t* __restrict__ Y = (const uint8_t*)p.sdr.p[0];
+  const unsigned y0 = __ldg((const unsigned*)(Y + (size_t)y * p.sdr.stride[0] + x));
+  const unsigned y1 = __ldg((const unsigned*)(Y + (size_t)(y + 1) * p.sdr.stride[0] + x));
+  const size_t coff = (size_t)(y >> 1) * p.sdr.stride[1] + (x >> 1);
+  const unsigned uu = __ldg((const uint16_t*)((const uint8_t*)p.sdr.p[1] + coff));
+  const unsigned vv = __ldg((const uint16_t*)((const uint8_t*)p.sdr.p[2] + (size_t)(y >> 1) * p.sdr.stride[2] + (x >> 1)));
+  // chroma terms of p3YuvToRgb, shared by the 2x2 pixels under each chroma sample
+  float crv[2], gcbu[2], gcrv[2], cbu[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const float u = (float)((int)((uu >> (8 * k)) & 0xff) - 128) * (1 / 255.0f);
+    const float v = (float)((int)((vv >> (8 * k)) & 0xff) - 128) * (1 / 255.0f);
+    crv[k] = p.y2r[0] * v;
+    cbu[k] = p.y2r[1] * u;
+    gcbu[k] = p.y2r[2] * u;
+    gcrv[k] = p.y2r[3] * v;
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const unsigned yw = r ? y1 : y0;
+    const int yy = y + r;
+    unsigned out[8];
+    // gain-map taps for the 4 pixels of this row
+    uint4 m4 = make_uint4(0, 0, 0, 0);
+    unsigned m3[3] = {0, 0, 0};
+    if (SCALE1) {
+      const uint8_t* mrow = p.map + ((size_t)yy * p.map_stride + x) * BPP;
+      if (BPP == 4) m4 = __ldg((const uint4*)mrow);
+      else if (BPP == 3) { m3[0] = __ldg((const unsigned*)mrow); m3[1] = __ldg((const unsigned*)mrow + 1); m3[2] = __ldg((const unsigned*)mrow + 2); }
+      else m3[0] = __ldg((const unsigned*)mrow);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = i >> 1;
+      const float yf = (float)((yw >> (8 * i)) & 0xff) * (1 / 255.0f);
+      // p3YuvToRgb with clampPixelFloat (saturate == clamp for the finite values that occur)
+      const float rg = __saturatef(yf + crv[k]);
+      const float gg = __saturatef(yf - gcbu[k] - gcrv[k]);
+      const float bg = __saturatef(yf + cbu[k]);
+      float lr = sm.srgb[idx1023(rg)], lg = sm.srgb[idx1023(gg)], lb = sm.srgb[idx1023(bg)];
+      if (GAMUT == 1) {
+        const float a = p.gamut[0] * lr + p.gamut[1] * lg + p.gamut[2] * lb;
+        const float b = p.gamut[3] * lr + p.gamut[4] * lg + p.gamut[5] * lb;
+        const float c = p.gamut[6] * lr + p.gamut[7] * lg + p.gamut[8] * lb;
+        lr = a; lg = b; lb = c;
+      }
+      float fr, fg, fb;
+      if (SCALE1) {
+        unsigned b0, b1, b2;
+        if (BPP == 4) {
+          const unsigned w = i == 0 ? m4.x : i == 1 ? m4.y : i == 2 ? m4.z : m4.w;
+          b0 = w & 0xff; b1 = (w >> 8) & 0xff; b2 = (w >> 16) & 0xff;
+        } else if (BPP == 3) {
+          const unsigned long long lo = m3[0] | ((unsigned long long)m3[1] << 32);
+          const unsigned long long all_lo = lo;
+          const unsigned hi = m3[2];
+          // 12 bytes: pixel i occupies bytes 3i..3i+2
+          auto byte_at = [&](int n) -> unsigned { return n < 8 ? (unsigned)((all_lo >> (8 * n)) & 0xff) : ((hi >> (8 * (n - 8))) & 0xff); };
+          b0 = byte_at(3 * i); b1 = byte_at(3 * i + 1); b2 = byte_at(3 * i + 2);
+        } else {
+          b0 = b1 = b2 = (m3[0] >> (8 * i)) & 0xff;
+        }
+        fr = sm.gain[b0];
+        fg = BPP == 1 ? fr : sm.gain[256 + b1];
+        fb = BPP == 1 ? fr : sm.gain[512 + b2];
+      } else {
+        const int s = p.scale_int;
+        const int px = x + i;
+        int xl = px / s, yl = yy / s;
+        const int xu = min(xl + 1, p.map_w - 1), yu = min(yl + 1, p.map_h - 1);
+        xl = min(xl, p.map_w - 1);
+        yl = min(yl, p.map_h - 1);
+        int variant = 0;
+        if (xl == xu && yl == yu) variant = 3;
+        else if (xl == xu) variant = 1;
+        else if (yl == yu) variant = 2;
+        const float* w = idw + (variant * s * s + (yy % s) * s + (px % s)) * 4;
+        const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        const uint8_t* m = p.map;
+        const size_t i1 = ((size_t)yl * p.map_stride + xl) * BPP, i2 = ((size_t)yu * p.map_stride + xl) * BPP;
+        const size_t i3 = ((size_t)yl * p.map_stride + xu) * BPP, i4 = ((size_t)yu * p.map_stride + xu) * BPP;
+        float g[3];
+#pragma unroll
+        for (int c = 0; c < (BPP == 1 ? 1 : 3); c++) {
+          const float e1 = sm.u8f[__ldg(m + i1 + c)], e2 = sm.u8f[__ldg(m + i2 + c)];
+          const float e3 = sm.u8f[__ldg(m + i3 + c)], e4 = sm.u8f[__ldg(m + i4 + c)];
+          g[c] = e1 * w0 + e2 * w1 + e3 * w2 + e4 * w3;
+        }
+        // GainLUT::getGainFactor, gamma 1; gains are >= 0; taps are <= 1 but their weighted sum
+        // may exceed 1 by an ulp, hence the clamp of the index
+        fr = sm.gain[min(idx1023(g[0]), 1023)];
+        fg = BPP == 1 ? fr : sm.gain[1024 + min(idx1023(g[1]), 1023)];
+        fb = BPP == 1 ? fr : sm.gain[2048 + min(idx1023(g[2]), 1023)];
+      }
+      const int o1 = BPP == 1 ? 0 : 1, o2 = BPP == 1 ? 0 : 2;
+      float hr = ((lr + p.off_sdr[0]) * fr) - p.off_hdr[0];
+      float hg = ((lg + p.off_sdr[o1]) * fg) - p.off_hdr[o1];
+      float hb = ((lb + p.off_sdr[o2]) * fb) - p.off_hdr[o2];
+      if (OUT == 0) {
+        if (GAMUT == 2) {
+          const float a = p.gamut[0] * hr + p.gamut[1] * hg + p.gamut[2] * hb;
+          const float b = p.gamut[3] * hr + p.gamut[4] * hg + p.gamut[5] * hb;
+          const float c = p.gamut[6] * hr + p.gamut[7] * hg + p.gamut[8] * hb;
+          hr = a; hg = b; hb = c;
+        }
+        const float kMax = 10000.0f / 203.0f;
+        hr = hr < 0.0f ? 0.0f : (hr > kMax ? kMax : hr);
+        hg = hg < 0.0f ? 0.0f : (hg > kMax ? kMax : hg);
+        hb = hb < 0.0f ? 0.0f : (hb > kMax ? kMax : hb);
+        out[2 * i] = half_bits(hr) | (half_bits(hg) << 16);
+        out[2 * i + 1] = half_bits(hb) | (0x3C00u << 16);
+      } else {
+        hr = hr * 203.0f / p.out_nits;
+        hg = hg * 203.0f / p.out_nits;
+        hb = hb * 203.0f / p.out_nits;
+        if (GAMUT == 2) {
+          const float a = p.gamut[0] * hr + p.gamut[1] * hg + p.gamut[2] * hb;
+          const float b = p.gamut[3] * hr + p.gamut[4] * hg + p.gamut[5] * hb;
+          const float c = p.gamut[6] * hr + p.gamut[7] * hg + p.gamut[8] * hb;
+          hr = a; hg = b; hb = c;
+        }
+        hr = hr < 0.0f ? 0.0f : (hr > 1.0f ? 1.0f : hr);
+        hg = hg < 0.0f ? 0.0f : (hg > 1.0f ? 1.0f : hg);
+        hb = hb < 0.0f ? 0.0f : (hb > 1.0f ? 1.0f : hb);
+        const float* t = p.luts + (OUT == 2 ? kLutHlgOetf : kLutPqOetf);
+        if (OUT == 2) {
+          const double ex = (double)(1.0f / 1.2f);
+          hr = (float)pow((double)hr, ex);
+          hg = (float)pow((double)hg, ex);
+          hb = (float)pow((double)hb, ex);
+        }
+        float e[3] = {hr, hg, hb};
+        unsigned px = 0x3u << 30;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float v = e[c] * 65535.0f;
+          int j = 0;
+          if (v > 0.0f) {
+            j = __float2int_rz(v);
+            j += ((v - (float)j) >= 0.5f) ? 1 : 0;
+            j = min(j, 65535);
+          }
+          float q = __ldg(t + j) * 1023.0f + 0.5f;
+          q = q < 0.0f ? 0.0f : (q > 1023.0f ? 1023.0f : q);
+          px |= (unsigned)__float2int_rz(q) << (10 * c);
+        }
+        out[i] = px;
+      }
+    }
+    if (OUT == 0) {
+      uint4* d = (uint4*)((uint2*)p.dst + (size_t)yy * p.dst_stride + x);
+      d[0] = make_uint4(out[0], out[1], out[2], out[3]);
+      d[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    } else {
+      *(uint4*)((unsigned*)p.dst + (size_t)yy * p.dst_stride + x) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+  }
+}
+
+template <int BPP, bool S1, int G>
+cudaError_t launch_out(const ApplyParams& p, const float* gain_u8, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+  if (p.out_ct == CT_LINEAR) k_apply_fast<BPP, S1, G, 0><<<grid, block, smem, s>>>(p, gain_u8);
+  else if (p.out_ct == CT_PQ) k_apply_fast<BPP, S1, G, 1><<<grid, block, smem, s>>>(p, gain_u8);
+  else k_apply_fast<BPP, S1, G, 2><<<grid, block, smem, s>>>(p, gain_u8);
+  return cudaGetLastError();
+}
+template <int BPP, bool S1>
+cudaError_t launch_gamut(const ApplyParams& p, const float* gain_u8, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+  const int g = p.gamut_identity ? 0 : (p.gamut_on_sdr ? 1 : 2);
+  if (g == 0) return launch_out<BPP, S1, 0>(p, gain_u8, grid, block, smem, s);
+  if (g == 1) return launch_out<BPP, S1, 1>(p, gain_u8, grid, block, smem, s);
+  return launch_out<BPP, S1, 2>(p, gain_u8, grid, block, smem, s);
+}
+
+}  // namespace
+
+bool apply_fast_eligible(const ApplyParams& p) {
+  if (p.sdr.fmt != F_YUV420 || !p.scale_int) return false;
+  if (p.gamma_inv[0] != 1.0f || p.gamma_inv[1] != 1.0f || p.gamma_inv[2] != 1.0f) return false;
+  if ((p.sdr.w & 3) || (p.sdr.h & 1)) return false;
+  if ((p.sdr.stride[0] & 3) || (p.sdr.stride[1] & 1) || (p.sdr.stride[2] & 1)) return false;
+  if (((size_t)p.sdr.p[0] & 3) || ((size_t)p.sdr.p[1] & 1) || ((size_t)p.sdr.p[2] & 1)) return false;
+  if (((size_t)p.dst & 15) || (p.dst_stride & 3)) return false;
+  if (p.scale_int == 1) {
+    if (p.map_w < p.sdr.w || p.map_h < p.sdr.h) return false;  // no edge clamping in the vector path
+    const int row_bytes = p.map_stride * p.map_bpp;
+    if ((row_bytes & 3) || ((size_t)p.map & 15) || (p.map_bpp == 4 && (row_bytes & 15))) return false;
+  } else if (p.scale_int > 16) {
+    return false;  // IDW tables beyond shared-memory budget
+  }
+  return true;
+}
+
+// gain_u8: device pointer to the 3x256 composed table (scale 1 only)
+cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaStream_t s) {
+  dim3 block(32, 4);
+  dim3 grid((p.sdr.w / 4 + 31) / 32, (p.sdr.h / 2 + 3) / 4);
+  const bool s1 = p.scale_int == 1;
+  const size_t smem = sizeof(FastSmem) + (s1 ? 0 : sizeof(float) * 16 * p.scale_int * p.scale_int);
+  if (p.map_bpp == 4) return s1 ? launch_gamut<4, true>(p, gain_u8, grid, block, smem, s) : launch_gamut<4, false>(p, gain_u8, grid, block, smem, s);
+  if (p.map_bpp == 3) return s1 ? launch_gamut<3, true>(p, gain_u8, grid, block, smem, s) : launch_gamut<3, false>(p, gain_u8, grid, block, smem, s);
+  return s1 ? launch_gamut<1, true>(p, gain_u8, grid, block, smem, s) : launch_gamut<1, false>(p, gain_u8, grid, block, smem, s);
+}
+
+}  // namespace uhdr_b200

@@ -295,16 +295,27 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
   static_assert(sizeof(GainmapMetadata) == sizeof(uhdr_gainmap_metadata_t), "layout");
   memcpy(&m, &md, sizeof m);
   const size_t idw_floats = integer && p.scale_int > 1 ? (size_t)16 * p.scale_int * p.scale_int : 0;
-  float* h_tab = (float*)ws.halloc(sizeof(float) * (3 * 1024 + idw_floats));
-  float* d_tab = (float*)ws.dalloc(sizeof(float) * (3 * 1024 + idw_floats));
+  float* h_tab = (float*)ws.halloc(sizeof(float) * (3 * 1024 + idw_floats + 768));
+  float* d_tab = (float*)ws.dalloc(sizeof(float) * (3 * 1024 + idw_floats + 768));
   if (!h_tab || !d_tab) return E_MEM;
   build_gain_lut(m, weight, h_tab);
+  {  // scale-1 shortcut table: gain-map byte -> gain factor.  mapUintToFloat (b / 255.0f), IDW
+     // weights {1,0,0,0} and GainLUT::getGainFactor's index (gamma 1) composed on the host
+    float* g8 = h_tab + 3 * 1024 + idw_floats;
+    for (int c = 0; c < 3; c++)
+      for (int b = 0; b < 256; b++) {
+        const float g = static_cast<float>(b) / 255.0f;
+        int32_t idx = static_cast<int32_t>(g * (1024 - 1) + 0.5);
+        idx = idx < 0 ? 0 : (idx > 1023 ? 1023 : idx);
+        g8[c * 256 + b] = h_tab[c * 1024 + idx];
+      }
+  }
   if (idw_floats) {
     std::vector<float> idw;
     build_idw_tables(p.scale_int, idw);
     memcpy(h_tab + 3 * 1024, idw.data(), sizeof(float) * idw_floats);
   }
-  CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, sizeof(float) * (3 * 1024 + idw_floats), cudaMemcpyHostToDevice, ws.stream()));
+  CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, sizeof(float) * (3 * 1024 + idw_floats + 768), cudaMemcpyHostToDevice, ws.stream()));
   p.gain_lut = d_tab;
   p.idw = d_tab + 3 * 1024;
   const bool single = metadata_single_channel(m);
@@ -326,7 +337,10 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
   p.luts = ws.luts();
   p.dst = (void*)dst->v.p[0];
   p.dst_stride = dst->v.stride[0];
-  TIMED(ws, "apply_gainmap", launch_apply_gainmap(p, ws.stream()));
+  if (apply_fast_eligible(p))
+    TIMED(ws, "apply_gainmap", launch_apply_fast(p, d_tab + 3 * 1024 + idw_floats, ws.stream()));
+  else
+    TIMED(ws, "apply_gainmap", launch_apply_gainmap(p, ws.stream()));
   return E_OK;
 }
 

@@ -128,6 +128,9 @@ cudaError_t launch_gainmap_init_minmax(unsigned* minmax, cudaStream_t s);
 cudaError_t launch_gainmap_finalize(const GainmapFinalizeParams& p, cudaStream_t s);
 cudaError_t launch_gainmap_affine(const AffineParams& p, cudaStream_t s);
 cudaError_t launch_apply_gainmap(const ApplyParams& p, cudaStream_t s);
+// fast path (apply_fast.cu): YUV420 base, integer scale, gamma 1.  gain_u8 = 3x256 composed table
+bool apply_fast_eligible(const ApplyParams& p);
+cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaStream_t s);
 cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s);
 cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s);
 cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s);
