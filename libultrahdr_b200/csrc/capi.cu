@@ -23,8 +23,18 @@ struct uhdr_codec_private {
   bool sailed = false;
   bool ready = false;
   int init_rc = 0;
+  int device = -1;  // the CUDA device that was current when the handle was created
   std::string init_err;
+  uhdr_codec_private() {
+    if (cudaGetDevice(&device) != cudaSuccess) device = -1;
+  }
+  // CUDA's current device is per host thread: a handle may be driven from any thread, so every
+  // entry point that touches the device re-selects the handle's own GPU first.
+  void bind() {
+    if (device >= 0) cudaSetDevice(device);
+  }
   void ensure() {
+    bind();
     if (ready) return;
     init_rc = codec.init();
     if (init_rc) init_err = last_error();
@@ -79,7 +89,7 @@ struct Encoder : uhdr_codec_private {
     sailed = false;
     memset(&out_desc, 0, sizeof out_desc);
     status = ok();
-    if (ready && !init_rc) codec.ws().clear_floor();
+    if (ready && !init_rc) { bind(); codec.ws().clear_floor(); }
   }
   Encoder() { defaults(); }
 };
@@ -298,6 +308,7 @@ UHDR_API uhdr_error_info_t uhdr_encode(uhdr_codec_private_t* enc) {
   if (!h) return err(UHDR_CODEC_INVALID_PARAM, "received nullptr for uhdr codec instance");
   if (h->sailed) return h->status;
   h->sailed = true;
+  h->bind();
   auto hdr = h->raw.find(UHDR_HDR_IMG);
   if (hdr == h->raw.end()) {
     h->status = err(UHDR_CODEC_INVALID_OPERATION, "resources required for uhdr_encode() operation are not present");
