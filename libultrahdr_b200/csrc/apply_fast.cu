@@ -18,14 +18,12 @@ namespace uhdr_b200 {
 
 namespace {
 
-__device__ __forceinline__ int idx1023(float x) {  // x in [0, 1]: int32(double(x*1023) + 0.5)
-  const float v = x * 1023.0f;
-  const int i = __float2int_rz(v);
-  return i + ((v - (float)i) >= 0.5f ? 1 : 0);
-}
-__device__ __forceinline__ unsigned half_bits(float f) {  // f in [-0, 10000/203]
+constexpr int kRowsPerThread = 8;   // 4 tile rows of 2
+constexpr int kBlockX = 64, kBlockY = 4;
+
+// reference floatToHalf (gainmapmath.h:160-173), generic form for the rare cases
+__device__ __forceinline__ unsigned half_bits_slow(float f) {
   const unsigned b = __float_as_uint(f) + 0x00001000u;
-  if (b - (113u << 23) < (31u << 23)) return (b >> 13) - (112u << 10);  // positive, 113 <= e <= 143
   const int e = (int)((b & 0x7F800000u) >> 23);
   const unsigned m = b & 0x007FFFFFu;
   unsigned r = (b & 0x80000000u) >> 16;
@@ -34,20 +32,45 @@ __device__ __forceinline__ unsigned half_bits(float f) {  // f in [-0, 10000/203
   if (e > 143) r |= 0x7FFFu;
   return r & 0xFFFFu;
 }
+// three channels + alpha 1.0 -> two 32-bit words.  Normal half range (the common case after the
+// clamp to [0, 10000/203]): ((bits + 0x1000) >> 13) - (112 << 10), with the bias folded into the
+// rounding add.  Anything else (tiny values, negative zero) takes the generic path.
+__device__ __forceinline__ void pack_half4(float r, float g, float b, unsigned& lo, unsigned& hi) {
+  const int kAdd = 0x00001000 - (112 << 23);
+  const int br = __float_as_int(r) + kAdd, bg = __float_as_int(g) + kAdd, bb = __float_as_int(b) + kAdd;
+  if (min(br, min(bg, bb)) >= (1 << 23)) {
+    lo = ((unsigned)br >> 13) | (((unsigned)bg << 3) & 0xFFFF0000u);
+    hi = ((unsigned)bb >> 13) | 0x3C000000u;
+  } else {
+    lo = half_bits_slow(r) | (half_bits_slow(g) << 16);
+    hi = half_bits_slow(b) | 0x3C000000u;
+  }
+}
 
+// Shared-memory tables, byte-offset addressed.
+//   srgb2[j] = srgbInvOetfLUT[(j + 1) >> 1], j = floor(2 * x * 1023): the reference index
+//   int32(double(x*1023) + 0.5) equals (floor(2v) + 1) >> 1, and floor(4a) & ~3 == 4 * floor(a),
+//   so the byte offset of the entry is  int(x * 8184.0f) & ~3  (x*8184 == 8*(x*1023) exactly).
 struct FastSmem {
-  float srgb[1024];
+  float srgb2[2048];
   float gain[3 * 1024];  // scale 1: first 3*256 entries hold the byte -> factor tables
   float u8f[256];
 };
+__device__ __forceinline__ float srgb_fetch(const FastSmem& sm, float x) {  // x in [0, 1]
+  const int off = __float2int_rz(x * 8184.0f) & ~3;
+  return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(sm.srgb2) + off);
+}
+__device__ __forceinline__ int idx1023(float x) {  // x >= 0: int32(double(x*1023) + 0.5)
+  return (__float2int_rz(x * 2046.0f) + 1) >> 1;
+}
 
 template <int BPP, bool SCALE1, int GAMUT /*0 none 1 sdr side 2 hdr side*/, int OUT /*0 F16 1 PQ 2 HLG*/>
-__global__ void __launch_bounds__(128) k_apply_fast(const ApplyParams p, const float* __restrict__ gain_u8) {
+__global__ void __launch_bounds__(kBlockX* kBlockY) k_apply_fast(const ApplyParams p, const float* __restrict__ gain_u8) {
   extern __shared__ float smem_raw[];
   FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
   float* idw = smem_raw + sizeof(FastSmem) / sizeof(float);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
-  for (int i = tid; i < 1024; i += nt) sm.srgb[i] = __ldg(p.luts + kLutSrgbInv + i);
+  for (int i = tid; i < 2048; i += nt) sm.srgb2[i] = __ldg(p.luts + kLutSrgbInv + ((i + 1) >> 1 > 1023 ? 1023 : (i + 1) >> 1));
   if (SCALE1) {
     for (int i = tid; i < 768; i += nt) sm.gain[i] = __ldg(gain_u8 + i);
   } else {
@@ -58,9 +81,13 @@ __global__ void __launch_bounds__(128) k_apply_fast(const ApplyParams p, const f
   }
   __syncthreads();
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
-  if (x >= p.sdr.w || y >= p.sdr.h) return;
+  if (x >= p.sdr.w) return;
   const uint8_t* __restrict__ Y = (const uint8_t*)p.sdr.p[0];
+  const int ybase = blockIdx.y * (kBlockY * kRowsPerThread) + threadIdx.y * 2;
+#pragma unroll 1
+  for (int it = 0; it < kRowsPerThread / 2; it++) {
+  const int y = ybase + it * (kBlockY * 2);
+  if (y >= p.sdr.h) break;
   const unsigned y0 = __ldg((const unsigned*)(Y + (size_t)y * p.sdr.stride[0] + x));
   const unsigned y1 = __ldg((const unsigned*)(Y + (size_t)(y + 1) * p.sdr.stride[0] + x));
   const size_t coff = (size_t)(y >> 1) * p.sdr.stride[1] + (x >> 1);
@@ -99,7 +126,7 @@ __global__ void __launch_bounds__(128) k_apply_fast(const ApplyParams p, const f
       const float rg = __saturatef(yf + crv[k]);
       const float gg = __saturatef(yf - gcbu[k] - gcrv[k]);
       const float bg = __saturatef(yf + cbu[k]);
-      float lr = sm.srgb[idx1023(rg)], lg = sm.srgb[idx1023(gg)], lb = sm.srgb[idx1023(bg)];
+      float lr = srgb_fetch(sm, rg), lg = srgb_fetch(sm, gg), lb = srgb_fetch(sm, bg);
       if (GAMUT == 1) {
         const float a = p.gamut[0] * lr + p.gamut[1] * lg + p.gamut[2] * lb;
         const float b = p.gamut[3] * lr + p.gamut[4] * lg + p.gamut[5] * lb;
@@ -108,23 +135,23 @@ __global__ void __launch_bounds__(128) k_apply_fast(const ApplyParams p, const f
       }
       float fr, fg, fb;
       if (SCALE1) {
-        unsigned b0, b1, b2;
+        // byte c of the pixel, pre-scaled to a byte offset into its 256-float table
+        unsigned o0, o1, o2;
+        const char* gt = reinterpret_cast<const char*>(sm.gain);
         if (BPP == 4) {
           const unsigned w = i == 0 ? m4.x : i == 1 ? m4.y : i == 2 ? m4.z : m4.w;
-          b0 = w & 0xff; b1 = (w >> 8) & 0xff; b2 = (w >> 16) & 0xff;
+          o0 = (w << 2) & 0x3FCu; o1 = (w >> 6) & 0x3FCu; o2 = (w >> 14) & 0x3FCu;
         } else if (BPP == 3) {
           const unsigned long long lo = m3[0] | ((unsigned long long)m3[1] << 32);
-          const unsigned long long all_lo = lo;
           const unsigned hi = m3[2];
-          // 12 bytes: pixel i occupies bytes 3i..3i+2
-          auto byte_at = [&](int n) -> unsigned { return n < 8 ? (unsigned)((all_lo >> (8 * n)) & 0xff) : ((hi >> (8 * (n - 8))) & 0xff); };
-          b0 = byte_at(3 * i); b1 = byte_at(3 * i + 1); b2 = byte_at(3 * i + 2);
+          auto byte_at = [&](int n) -> unsigned { return n < 8 ? (unsigned)((lo >> (8 * n)) & 0xff) : ((hi >> (8 * (n - 8))) & 0xff); };
+          o0 = byte_at(3 * i) << 2; o1 = byte_at(3 * i + 1) << 2; o2 = byte_at(3 * i + 2) << 2;
         } else {
-          b0 = b1 = b2 = (m3[0] >> (8 * i)) & 0xff;
+          o0 = o1 = o2 = ((m3[0] >> (8 * i)) & 0xff) << 2;
         }
-        fr = sm.gain[b0];
-        fg = BPP == 1 ? fr : sm.gain[256 + b1];
-        fb = BPP == 1 ? fr : sm.gain[512 + b2];
+        fr = *reinterpret_cast<const float*>(gt + o0);
+        fg = BPP == 1 ? fr : *reinterpret_cast<const float*>(gt + 1024 + o1);
+        fb = BPP == 1 ? fr : *reinterpret_cast<const float*>(gt + 2048 + o2);
       } else {
         const int s = p.scale_int;
         const int px = x + i;
@@ -148,8 +175,8 @@ __global__ void __launch_bounds__(128) k_apply_fast(const ApplyParams p, const f
           const float e3 = sm.u8f[__ldg(m + i3 + c)], e4 = sm.u8f[__ldg(m + i4 + c)];
           g[c] = e1 * w0 + e2 * w1 + e3 * w2 + e4 * w3;
         }
-        // GainLUT::getGainFactor, gamma 1; gains are >= 0; taps are <= 1 but their weighted sum
-        // may exceed 1 by an ulp, hence the clamp of the index
+        // GainLUT::getGainFactor, gamma 1; gains are >= 0; the weighted sum of taps <= 1 may
+        // exceed 1 by an ulp, hence the clamp of the index
         fr = sm.gain[min(idx1023(g[0]), 1023)];
         fg = BPP == 1 ? fr : sm.gain[1024 + min(idx1023(g[1]), 1023)];
         fb = BPP == 1 ? fr : sm.gain[2048 + min(idx1023(g[2]), 1023)];
@@ -165,12 +192,13 @@ __global__ void __launch_bounds__(128) k_apply_fast(const ApplyParams p, const f
           const float c = p.gamut[6] * hr + p.gamut[7] * hg + p.gamut[8] * hb;
           hr = a; hg = b; hb = c;
         }
+        // clampPixelFloatLinear; min/max form is equivalent here: no NaN and no negative zero can
+        // reach this point (sums of a positive-leading gamut row, x - x == +0)
         const float kMax = 10000.0f / 203.0f;
-        hr = hr < 0.0f ? 0.0f : (hr > kMax ? kMax : hr);
-        hg = hg < 0.0f ? 0.0f : (hg > kMax ? kMax : hg);
-        hb = hb < 0.0f ? 0.0f : (hb > kMax ? kMax : hb);
-        out[2 * i] = half_bits(hr) | (half_bits(hg) << 16);
-        out[2 * i + 1] = half_bits(hb) | (0x3C00u << 16);
+        hr = fminf(fmaxf(hr, 0.0f), kMax);
+        hg = fminf(fmaxf(hg, 0.0f), kMax);
+        hb = fminf(fmaxf(hb, 0.0f), kMax);
+        pack_half4(hr, hg, hb, out[2 * i], out[2 * i + 1]);
       } else {
         hr = hr * 203.0f / p.out_nits;
         hg = hg * 203.0f / p.out_nits;
@@ -217,6 +245,7 @@ __global__ void __launch_bounds__(128) k_apply_fast(const ApplyParams p, const f
       *(uint4*)((unsigned*)p.dst + (size_t)yy * p.dst_stride + x) = make_uint4(out[0], out[1], out[2], out[3]);
     }
   }
+  }
 }
 
 template <int BPP, bool S1, int G>
@@ -255,8 +284,8 @@ bool apply_fast_eligible(const ApplyParams& p) {
 
 // gain_u8: device pointer to the 3x256 composed table (scale 1 only)
 cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaStream_t s) {
-  dim3 block(32, 4);
-  dim3 grid((p.sdr.w / 4 + 31) / 32, (p.sdr.h / 2 + 3) / 4);
+  dim3 block(kBlockX, kBlockY);
+  dim3 grid((p.sdr.w / 4 + kBlockX - 1) / kBlockX, (p.sdr.h + kBlockY * kRowsPerThread - 1) / (kBlockY * kRowsPerThread));
   const bool s1 = p.scale_int == 1;
   const size_t smem = sizeof(FastSmem) + (s1 ? 0 : sizeof(float) * 16 * p.scale_int * p.scale_int);
   if (p.map_bpp == 4) return s1 ? launch_gamut<4, true>(p, gain_u8, grid, block, smem, s) : launch_gamut<4, false>(p, gain_u8, grid, block, smem, s);
