@@ -45,6 +45,18 @@ UHDR_API int uhdr_b200_install_lut_blob_dev(const void* device_ptr) {
 }
 UHDR_API int uhdr_b200_get_lut_blob(float* host_out) { return read_back_luts(host_out); }
 
+UHDR_API int uhdr_b200_probe_log2(const float* in, float* out, int n) {
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  float* d_in = (float*)ws->dalloc((size_t)n * 4);
+  float* d_out = (float*)ws->dalloc((size_t)n * 4);
+  if (!d_in || !d_out) return E_MEM;
+  CUDA_TRY(cudaMemcpyAsync(d_in, in, (size_t)n * 4, cudaMemcpyHostToDevice, ws->stream()));
+  CUDA_TRY(launch_log2_probe(d_in, d_out, n, ws->stream()));
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ws->stream()));
+  return ws->sync();
+}
+
 UHDR_API int uhdr_b200_generate_gainmap(const uhdr_raw_image_t* sdr, const uhdr_raw_image_t* hdr,
                                         const uhdr_b200_gm_config_t* cfg,
                                         uhdr_gainmap_metadata_t* md_out,

@@ -179,7 +179,10 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
     p.log2_min = std::log2(p.min_boost);  // float overloads: jpegr.cpp has `using namespace std`
     p.log2_max = std::log2(p.max_boost);
     p.gamma = cfg.gamma;
-    TIMED(ws, "gainmap_onepass", launch_gainmap_onepass(p, ws.stream()));
+    if (gainmap_fast_eligible(p, true))
+      TIMED(ws, "gainmap_onepass", launch_gainmap_fast(p, true, ws.stream()));
+    else
+      TIMED(ws, "gainmap_onepass", launch_gainmap_onepass(p, ws.stream()));
     return E_OK;
   }
   p.gains = (float*)ws.dalloc(sizeof(float) * (size_t)mw * mh * p.nch);
@@ -188,7 +191,10 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   job->h_minmax = (float*)ws.halloc(64);
   if (!p.gains || !p.minmax || !d_minmax_f || !job->h_minmax) return E_MEM;
   CUDA_TRY(launch_gainmap_init_minmax(p.minmax, ws.stream()));
-  TIMED(ws, "gainmap_pass1", launch_gainmap_pass1(p, ws.stream()));
+  if (gainmap_fast_eligible(p, false))
+    TIMED(ws, "gainmap_pass1", launch_gainmap_fast(p, false, ws.stream()));
+  else
+    TIMED(ws, "gainmap_pass1", launch_gainmap_pass1(p, ws.stream()));
   GainmapFinalizeParams f;
   f.minmax = p.minmax;
   f.minmax_f = d_minmax_f;

@@ -1,0 +1,320 @@
+// generateGainMap fast path (jpegr.cpp:753-817 one-pass, :866-931 pass 1 of two-pass) for the
+// configuration the API-0/API-1 benchmarks exercise: P010 HDR intent (HLG or PQ) + YUV 4:2:0 SDR
+// intent, map scale 1.  Arithmetic, operand order and tables are those of the generic kernels in
+// kernels.cu; what changes is the instruction count:
+//   * one thread = a 4x2 pixel tile (chroma terms of both images computed once per 2x2)
+//   * inverse-OETF tables in shared memory in "doubled" form so that the reference's LUT index
+//     int32(double(x*(N-1)) + 0.5) becomes one multiply, one convert and one mask
+//   * computeGain's double-precision log2 of a float quotient through a 128-entry table + degree-8
+//     polynomial in fp64 (error < 2^-50 before narrowing to float, like glibc's / CUDA's log2,
+//     ~6x fewer instructions than the library routine)
+#include <cmath>
+#include <mutex>
+
+#include "kernels.cuh"
+#include "runtime.h"
+#include "tables.h"
+
+namespace uhdr_b200 {
+
+namespace {
+
+// ---- log2 ---------------------------------------------------------------------------------------
+// z = 2^k * m, m in [OFF, 2*OFF), OFF = 0x3f330000 (0.69921875); m's top 7 mantissa bits select
+// (invc, logc) with c near the centre of the sub-interval; the two sub-intervals touching 1.0 use
+// c = 1 exactly so that results near zero keep full relative accuracy.
+struct Log2Tab { double invc[128], logc[128]; };
+constexpr unsigned kLogOff = 0x3f330000u;
+
+__device__ __forceinline__ double log2_core(float q, const double* __restrict__ tab /* smem: invc[128], logc[128] */) {
+  const unsigned ix = __float_as_uint(q);
+  const unsigned tmp = ix - kLogOff;
+  const int i = (tmp >> 16) & 127;
+  const int k = (int)tmp >> 23;
+  const float m = __uint_as_float(ix - (tmp & 0xff800000u));
+  const double r = fma((double)m, tab[i], -1.0);
+  // log2(1+r) = r * P(r), P = sum_{j>=0} (-1)^j r^j / ((j+1) ln2)
+  double p = -0.18033688011112042;            // -1/(8 ln2)
+  p = fma(p, r, 0.20609929155556619);         //  1/(7 ln2)
+  p = fma(p, r, -0.24044917348149390);        // -1/(6 ln2)
+  p = fma(p, r, 0.28853900817779268);         //  1/(5 ln2)
+  p = fma(p, r, -0.36067376022224085);        // -1/(4 ln2)
+  p = fma(p, r, 0.48089834696298783);         //  1/(3 ln2)
+  p = fma(p, r, -0.72134752044448170);        // -1/(2 ln2)
+  p = fma(p, r, 1.4426950408889634);          //  1/ln2
+  return fma(p, r, (double)k + tab[128 + i]);
+}
+
+// ---- shared memory ------------------------------------------------------------------------------
+struct GmSmem {
+  double log2tab[256];
+  float srgb2[2048];   // srgb2[j] = srgbInvLUT[(j+1)>>1]
+  float hdr2[8192];    // hdr2[j]  = hdrInvLUT[(j+1)>>1], 4096-entry source table
+};
+__device__ __forceinline__ float fetch2(const float* t, float x, float scale8) {  // x in [0,1]
+  const int off = __float2int_rz(x * scale8) & ~3;
+  return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(t) + off);
+}
+
+template <bool ONEPASS, int NCH, int GAMUT /*0 none, 1 on sdr, 2 on hdr*/, bool LIMITED>
+__global__ void __launch_bounds__(256) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g) {
+  extern __shared__ double smem_d[];
+  GmSmem& sm = *reinterpret_cast<GmSmem*>(smem_d);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  for (int i = tid; i < 256; i += nt) sm.log2tab[i] = log2tab_g[i];
+  for (int i = tid; i < 2048; i += nt) sm.srgb2[i] = __ldg(p.luts + kLutSrgbInv + min((i + 1) >> 1, 1023));
+  const float* hsrc = p.luts + (p.hdr_ct == CT_HLG ? kLutHlgInvOotf : kLutPqInv);
+  for (int i = tid; i < 8192; i += nt) sm.hdr2[i] = __ldg(hsrc + min((i + 1) >> 1, 4095));
+  __syncthreads();
+
+  float mn[3] = {127.0f, 127.0f, 127.0f}, mx[3] = {-128.0f, -128.0f, -128.0f};
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int ybase = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
+  const int ystep = gridDim.y * blockDim.y * 2;
+  if (x < p.map_w) {
+#pragma unroll 1
+    for (int y = ybase; y < p.map_h; y += ystep) {
+      // ---- loads: 4x2 luma of both images, 2 chroma pairs each
+      const uint16_t* HY = (const uint16_t*)p.hdr.p[0];
+      const uint2 hy0 = __ldg((const uint2*)(HY + (size_t)y * p.hdr.stride[0] + x));
+      const uint2 hy1 = __ldg((const uint2*)(HY + (size_t)(y + 1) * p.hdr.stride[0] + x));
+      const uint2 huv = __ldg((const uint2*)((const uint16_t*)p.hdr.p[1] + (size_t)(y >> 1) * p.hdr.stride[1] + x));
+      const uint8_t* SY = (const uint8_t*)p.sdr.p[0];
+      const unsigned sy0 = __ldg((const unsigned*)(SY + (size_t)y * p.sdr.stride[0] + x));
+      const unsigned sy1 = __ldg((const unsigned*)(SY + (size_t)(y + 1) * p.sdr.stride[0] + x));
+      const unsigned su = __ldg((const uint16_t*)((const uint8_t*)p.sdr.p[1] + (size_t)(y >> 1) * p.sdr.stride[1] + (x >> 1)));
+      const unsigned sv = __ldg((const uint16_t*)((const uint8_t*)p.sdr.p[2] + (size_t)(y >> 1) * p.sdr.stride[2] + (x >> 1)));
+      // ---- chroma terms (yuv->rgb: r = y + cr*v, g = y - gcb*u - gcr*v, b = y + cb*u)
+      float h_crv[2], h_cbu[2], h_gcbu[2], h_gcrv[2], s_crv[2], s_cbu[2], s_gcbu[2], s_gcrv[2];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const unsigned uvw = k ? huv.y : huv.x;
+        const int u10 = (int)((uvw & 0xffff) >> 6), v10 = (int)(uvw >> 22);
+        float hu, hv;
+        if (LIMITED) {
+          hu = (float)(u10 - 64) * (1 / 896.0f) - 0.5f;
+          hv = (float)(v10 - 64) * (1 / 896.0f) - 0.5f;
+        } else {
+          hu = (float)u10 / 1023.0f - 0.5f;
+          hv = (float)v10 / 1023.0f - 0.5f;
+        }
+        h_crv[k] = p.hdr_y2r[0] * hv; h_cbu[k] = p.hdr_y2r[1] * hu;
+        h_gcbu[k] = p.hdr_y2r[2] * hu; h_gcrv[k] = p.hdr_y2r[3] * hv;
+        const float u = (float)((int)((su >> (8 * k)) & 0xff) - 128) * (1 / 255.0f);
+        const float v = (float)((int)((sv >> (8 * k)) & 0xff) - 128) * (1 / 255.0f);
+        s_crv[k] = p.sdr_y2r[0] * v; s_cbu[k] = p.sdr_y2r[1] * u;
+        s_gcbu[k] = p.sdr_y2r[2] * u; s_gcrv[k] = p.sdr_y2r[3] * v;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const uint2 hyw = r ? hy1 : hy0;
+        const unsigned syw = r ? sy1 : sy0;
+        float gout[12];
+        unsigned bout[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int k = i >> 1;
+          // sdr: getYuv420Pixel -> yuvToRgb -> srgbInvOetfLUT [-> gamut] -> clipNegatives
+          const float syf = (float)((syw >> (8 * i)) & 0xff) * (1 / 255.0f);
+          float sr = fetch2(sm.srgb2, __saturatef(syf + s_crv[k]), 8184.0f);
+          float sg = fetch2(sm.srgb2, __saturatef(syf - s_gcbu[k] - s_gcrv[k]), 8184.0f);
+          float sb = fetch2(sm.srgb2, __saturatef(syf + s_cbu[k]), 8184.0f);
+          // hdr: getP010Pixel -> yuvToRgb -> invOETF(+OOTF) LUT [-> gamut] -> clipNegatives
+          const unsigned hw = (i < 2) ? hyw.x : hyw.y;
+          const int y10 = (int)(((hw >> (16 * (i & 1))) & 0xffff) >> 6);
+          const float hyf = LIMITED ? (float)(y10 - 64) * (1 / 876.0f) : (float)y10 / 1023.0f;
+          float hr = fetch2(sm.hdr2, __saturatef(hyf + h_crv[k]), 32760.0f);
+          float hg = fetch2(sm.hdr2, __saturatef(hyf - h_gcbu[k] - h_gcrv[k]), 32760.0f);
+          float hb = fetch2(sm.hdr2, __saturatef(hyf + h_cbu[k]), 32760.0f);
+          if (GAMUT == 1) {
+            const float a = p.gamut[0] * sr + p.gamut[1] * sg + p.gamut[2] * sb;
+            const float b = p.gamut[3] * sr + p.gamut[4] * sg + p.gamut[5] * sb;
+            const float c = p.gamut[6] * sr + p.gamut[7] * sg + p.gamut[8] * sb;
+            sr = fmaxf(a, 0.0f); sg = fmaxf(b, 0.0f); sb = fmaxf(c, 0.0f);
+          } else if (GAMUT == 2) {
+            const float a = p.gamut[0] * hr + p.gamut[1] * hg + p.gamut[2] * hb;
+            const float b = p.gamut[3] * hr + p.gamut[4] * hg + p.gamut[5] * hb;
+            const float c = p.gamut[6] * hr + p.gamut[7] * hg + p.gamut[8] * hb;
+            hr = fmaxf(a, 0.0f); hg = fmaxf(b, 0.0f); hb = fmaxf(c, 0.0f);
+          }
+          float sv3[3], hv3[3];
+          if (NCH == 3) {
+            sv3[0] = sr * p.sdr_nits; sv3[1] = sg * p.sdr_nits; sv3[2] = sb * p.sdr_nits;
+            hv3[0] = hr * p.hdr_nits; hv3[1] = hg * p.hdr_nits; hv3[2] = hb * p.hdr_nits;
+          } else if (p.use_luminance) {
+            sv3[0] = (p.lum[0] * sr + p.lum[1] * sg + p.lum[2] * sb) * p.sdr_nits;
+            hv3[0] = (p.lum[0] * hr + p.lum[1] * hg + p.lum[2] * hb) * p.hdr_nits;
+          } else {
+            sv3[0] = fmaxf(sr, fmaxf(sg, sb)) * p.sdr_nits;
+            hv3[0] = fmaxf(hr, fmaxf(hg, hb)) * p.hdr_nits;
+          }
+#pragma unroll
+          for (int c = 0; c < NCH; c++) {
+            if (ONEPASS) {  // encodeGain gainmapmath.cpp:758-771 (gamma 1: powf(x, 1) == x)
+              float gain = 1.0f;
+              if (sv3[c] > 0.0f) gain = hv3[c] / sv3[c];
+              if (gain < p.min_boost) gain = p.min_boost;
+              if (gain > p.max_boost) gain = p.max_boost;
+              const float gn = (float)((log2_core(gain, sm.log2tab) - (double)p.log2_min) / (double)(p.log2_max - p.log2_min));
+              const unsigned code = (unsigned)__float2int_rz(gn * 255.0f) & 0xff;
+              const int bi = i * NCH + c;
+              bout[bi >> 2] |= code << (8 * (bi & 3));
+            } else {        // computeGain :773-782
+              float g = (float)log2_core((hv3[c] + 1e-7f) / (sv3[c] + 1e-7f), sm.log2tab);
+              if (sv3[c] < 2.f / 255.0f) g = fminf(g, 2.3f);
+              gout[i * NCH + c] = g;
+              mn[c] = fminf(mn[c], g);
+              mx[c] = fmaxf(mx[c], g);
+            }
+          }
+        }
+        const int yy = y + r;
+        if (ONEPASS) {
+          uint8_t* d = p.dst + ((size_t)yy * p.dst_stride + x) * NCH;
+          if (NCH == 3) { ((unsigned*)d)[0] = bout[0]; ((unsigned*)d)[1] = bout[1]; ((unsigned*)d)[2] = bout[2]; }
+          else *(unsigned*)d = bout[0];
+        } else {
+          float4* d = (float4*)(p.gains + ((size_t)yy * p.map_w + x) * NCH);
+          if (NCH == 3) {
+            d[0] = make_float4(gout[0], gout[1], gout[2], gout[3]);
+            d[1] = make_float4(gout[4], gout[5], gout[6], gout[7]);
+            d[2] = make_float4(gout[8], gout[9], gout[10], gout[11]);
+          } else {
+            d[0] = make_float4(gout[0], gout[1], gout[2], gout[3]);
+          }
+        }
+      }
+    }
+  }
+  if (!ONEPASS) {
+    // same order-independent reduction as k_gainmap_pass1
+    __shared__ unsigned s_mn[3][8], s_mx[3][8];
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      unsigned a = __float_as_uint(mn[c]), b = __float_as_uint(mx[c]);
+      a = (a & 0x80000000u) ? ~a : (a | 0x80000000u);
+      b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+      for (int o = 16; o; o >>= 1) {
+        a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+      }
+      if (lane == 0) { s_mn[c][warp] = a; s_mx[c][warp] = b; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int nw = nt >> 5;
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        unsigned a = lane < nw ? s_mn[c][lane] : 0xffffffffu, b = lane < nw ? s_mx[c][lane] : 0u;
+        for (int o = 4; o; o >>= 1) {
+          a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+          b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+        }
+        if (lane == 0) { atomicMin(p.minmax + c, a); atomicMax(p.minmax + 3 + c, b); }
+      }
+    }
+  }
+}
+
+// host: table of the log2 kernel, uploaded once per device
+int log2_table_dev(const double** out) {
+  static std::mutex mu;
+  static thread_local int cached_dev = -1;
+  static thread_local const double* cached = nullptr;
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (cached && cached_dev == dev) { *out = cached; return E_OK; }
+  std::lock_guard<std::mutex> lk(mu);
+  static double* per_dev[64] = {nullptr};
+  if (dev < 64 && per_dev[dev]) { cached = per_dev[dev]; cached_dev = dev; *out = cached; return E_OK; }
+  double host[256];
+  for (int i = 0; i < 128; i++) {
+    const unsigned lo = kLogOff + ((unsigned)i << 16), hi = lo + (1u << 16);
+    float flo, fhi;
+    memcpy(&flo, &lo, 4);
+    memcpy(&fhi, &hi, 4);
+    long double c = ((long double)flo + (long double)fhi) / 2;
+    if (flo <= 1.0f && fhi >= 1.0f) c = 1.0L;       // the two sub-intervals that touch 1.0
+    const double invc = (double)(1.0L / c);
+    host[i] = invc;
+    host[128 + i] = (invc == 1.0) ? 0.0 : (double)(-log2l((long double)invc));  // log2 of the c actually used
+  }
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof host));
+  CUDA_TRY(cudaMemcpy(d, host, sizeof host, cudaMemcpyHostToDevice));
+  if (dev < 64) per_dev[dev] = d;
+  cached = d;
+  cached_dev = dev;
+  *out = d;
+  return E_OK;
+}
+
+template <bool ONEPASS, int NCH, int GAMUT>
+cudaError_t launch_range(const GainmapGenParams& p, const double* tab, dim3 g, dim3 b, size_t sm, cudaStream_t s) {
+  if (p.hdr.full_range) k_gainmap_fast<ONEPASS, NCH, GAMUT, false><<<g, b, sm, s>>>(p, tab);
+  else k_gainmap_fast<ONEPASS, NCH, GAMUT, true><<<g, b, sm, s>>>(p, tab);
+  return cudaGetLastError();
+}
+template <bool ONEPASS, int NCH>
+cudaError_t launch_g(const GainmapGenParams& p, const double* tab, dim3 g, dim3 b, size_t sm, cudaStream_t s) {
+  const int gm = p.gamut_identity ? 0 : (p.gamut_on_hdr ? 2 : 1);
+  if (gm == 0) return launch_range<ONEPASS, NCH, 0>(p, tab, g, b, sm, s);
+  if (gm == 1) return launch_range<ONEPASS, NCH, 1>(p, tab, g, b, sm, s);
+  return launch_range<ONEPASS, NCH, 2>(p, tab, g, b, sm, s);
+}
+
+}  // namespace
+
+bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass) {
+  if (p.hdr.fmt != F_P010 || p.sdr.fmt != F_YUV420 || p.scale != 1) return false;
+  if (p.hdr_ct != CT_HLG && p.hdr_ct != CT_PQ) return false;
+  if ((p.map_w & 3) || (p.map_h & 1) || p.map_w != p.hdr.w || p.map_h != p.hdr.h) return false;
+  if ((p.hdr.stride[0] & 3) || (p.hdr.stride[1] & 3) || (p.sdr.stride[0] & 3) || (p.sdr.stride[1] & 1) || (p.sdr.stride[2] & 1)) return false;
+  if (((size_t)p.hdr.p[0] & 7) || ((size_t)p.hdr.p[1] & 7) || ((size_t)p.sdr.p[0] & 3) || ((size_t)p.sdr.p[1] & 1) || ((size_t)p.sdr.p[2] & 1)) return false;
+  if (onepass) {
+    if (p.gamma != 1.0f) return false;
+    if (((size_t)p.dst & 3) || ((p.dst_stride * p.nch) & 3)) return false;
+  } else if ((size_t)p.gains & 15) {
+    return false;
+  }
+  return true;
+}
+
+namespace {
+__global__ void k_log2_probe(const float* __restrict__ in, float* __restrict__ out, int n, const double* __restrict__ tab_g) {
+  __shared__ double tab[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = tab_g[i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)log2_core(in[i], tab);
+}
+}  // namespace
+
+// diagnostic: out[i] = float(log2(double(in[i]))) as the gain-map kernels evaluate it (device buffers)
+cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream_t s) {
+  const double* tab = nullptr;
+  if (log2_table_dev(&tab) != E_OK) return cudaErrorUnknown;
+  k_log2_probe<<<(n + 255) / 256, 256, 0, s>>>(d_in, d_out, n, tab);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, cudaStream_t s) {
+  const double* tab = nullptr;
+  if (log2_table_dev(&tab) != E_OK) return cudaErrorUnknown;
+  dim3 b(64, 4);
+  // persistent-ish grid: each CTA strides over tile rows so the 42 KB of tables are staged once
+  const int rows_per_cta = b.y * 2;
+  int gy = (p.map_h + rows_per_cta - 1) / rows_per_cta;
+  const int gx = (p.map_w / 4 + b.x - 1) / b.x;
+  const int want = (148 * 5 + gx - 1) / gx;  // ~5 CTAs per SM resident
+  if (gy > want) gy = want;
+  dim3 g(gx, gy);
+  const size_t sm = sizeof(GmSmem);
+  cudaError_t e;
+  if (onepass) e = p.nch == 3 ? launch_g<true, 3>(p, tab, g, b, sm, s) : launch_g<true, 1>(p, tab, g, b, sm, s);
+  else e = p.nch == 3 ? launch_g<false, 3>(p, tab, g, b, sm, s) : launch_g<false, 1>(p, tab, g, b, sm, s);
+  return e;
+}
+
+}  // namespace uhdr_b200

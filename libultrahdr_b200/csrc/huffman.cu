@@ -20,6 +20,7 @@ void jpeg_std_codebook(int which, uint32_t out[256]);
 namespace {
 
 constexpr int kMaxWordsPerBlock = 52;  // (20 + 63*26 bits) / 32 rounded up
+constexpr int kPersistentCtas = 148 * 2;  // one wave of 1024-thread CTAs on the 148 SMs
 
 struct HuffFrame {
   const int16_t* coefs[3];
@@ -240,19 +241,28 @@ __device__ __forceinline__ unsigned ff_count(unsigned v, unsigned j, unsigned to
     if (4 * j + b < total_bytes && ((v >> (24 - 8 * b)) & 0xff) == 0xff) c++;
   return c;
 }
+// zero exactly the words the concatenation will OR into (total known on the device only)
+__global__ void __launch_bounds__(256) k_zero_stream(unsigned* __restrict__ stream, const unsigned* total_bits_ptr,
+                                                     unsigned cap_words) {
+  unsigned n = (*total_bits_ptr + 31) / 32 + 2;
+  if (n > cap_words) n = cap_words;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stream[i] = 0u;
+}
+// persistent grid: CTAs stride over the tiles actually in use
 __global__ void __launch_bounds__(kScanTile) k_ff_count(const unsigned* __restrict__ stream, const unsigned* total_bits_ptr,
                                                         unsigned* __restrict__ tile_ff, unsigned* __restrict__ nwords_out) {
   const unsigned total_bits = *total_bits_ptr;
   const unsigned total_bytes = (total_bits + 7) >> 3;
   const unsigned nwords = (total_bytes + 3) >> 2;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *nwords_out = (nwords + kScanTile - 1) / kScanTile;  // tiles in use
-  if (blockIdx.x * kScanTile >= nwords) return;
-  const unsigned j = blockIdx.x * kScanTile + threadIdx.x;
-  unsigned c = 0;
-  if (j < nwords) c = ff_count(load_padded_word(stream, j, total_bits), j, total_bytes);
-  unsigned t;
-  block_exclusive_scan(c, &t);
-  if (threadIdx.x == 0) tile_ff[blockIdx.x] = t;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *nwords_out = nwords;
+  for (unsigned tile = blockIdx.x; tile * kScanTile < nwords; tile += gridDim.x) {
+    const unsigned j = tile * kScanTile + threadIdx.x;
+    unsigned c = 0;
+    if (j < nwords) c = ff_count(load_padded_word(stream, j, total_bits), j, total_bytes);
+    unsigned t;
+    block_exclusive_scan(c, &t);
+    if (threadIdx.x == 0) tile_ff[tile] = t;
+  }
 }
 __global__ void __launch_bounds__(kScanTile) k_stuff(const unsigned* __restrict__ stream, const unsigned* total_bits_ptr,
                                                      const unsigned* __restrict__ tile_off, const unsigned* total_ff,
@@ -265,23 +275,25 @@ __global__ void __launch_bounds__(kScanTile) k_stuff(const unsigned* __restrict_
     *out_bytes = total_bytes + *total_ff;
     if (total_bytes + *total_ff > out_cap) *overflow = 1;
   }
-  if (blockIdx.x * kScanTile >= nwords) return;
   if (total_bytes + *total_ff > out_cap) return;
-  const unsigned j = blockIdx.x * kScanTile + threadIdx.x;
-  unsigned v = 0, c = 0;
-  if (j < nwords) {
-    v = load_padded_word(stream, j, total_bits);
-    c = ff_count(v, j, total_bytes);
-  }
-  const unsigned e = block_exclusive_scan(c, nullptr);
-  if (j >= nwords) return;
-  unsigned pos = 4 * j + tile_off[blockIdx.x] + e;
+  for (unsigned tile = blockIdx.x; tile * kScanTile < nwords; tile += gridDim.x) {
+    const unsigned j = tile * kScanTile + threadIdx.x;
+    unsigned v = 0, c = 0;
+    if (j < nwords) {
+      v = load_padded_word(stream, j, total_bits);
+      c = ff_count(v, j, total_bytes);
+    }
+    const unsigned e = block_exclusive_scan(c, nullptr);
+    if (j < nwords) {
+      unsigned pos = 4 * j + tile_off[tile] + e;
 #pragma unroll
-  for (int b = 0; b < 4; b++) {
-    if (4 * j + b >= total_bytes) break;
-    const uint8_t byte = (uint8_t)((v >> (24 - 8 * b)) & 0xff);
-    out[pos++] = byte;
-    if (byte == 0xff) out[pos++] = 0;
+      for (int b = 0; b < 4; b++) {
+        if (4 * j + b >= total_bytes) break;
+        const uint8_t byte = (uint8_t)((v >> (24 - 8 * b)) & 0xff);
+        out[pos++] = byte;
+        if (byte == 0xff) out[pos++] = 0;
+      }
+    }
   }
 }
 
@@ -351,8 +363,7 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   job->scan_capacity = cap;
   cudaStream_t st = ws.stream();
   CUDA_TRY(cudaMemsetAsync(ctl, 0, 64, st));
-  CUDA_TRY(cudaMemsetAsync(stream, 0, cap + 64, st));
-  CUDA_TRY(cudaMemsetAsync(tile_ff, 0, (size_t)ntiles_words * 4 + 64, st));
+
   ws.t_begin("huff_blocks");
   k_huff_blocks<<<(unsigned)((nblocks + 127) / 128), 128, 0, st>>>(f, books, scratch, bits);
   ws.t_end();
@@ -362,12 +373,13 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   k_scan_apply<<<ntiles_blocks, kScanTile, 0, st>>>(bits, (unsigned)nblocks, nullptr, part, offs);
   ws.t_end();
   ws.t_begin("huff_concat");
+  k_zero_stream<<<kPersistentCtas, 256, 0, st>>>(stream, ctl + 0, cap_words);
   k_huff_concat<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(scratch, bits, offs, (unsigned)nblocks, stream, cap_words, ctl + 4);
   ws.t_end();
   ws.t_begin("huff_stuff");
-  k_ff_count<<<ntiles_words, kScanTile, 0, st>>>(stream, ctl + 0, tile_ff, ctl + 1);
-  k_scan_partials<<<1, kScanTile, 0, st>>>(tile_ff, ntiles_words, ntiles_words * kScanTile, nullptr, ctl + 2);
-  k_stuff<<<ntiles_words, kScanTile, 0, st>>>(stream, ctl + 0, tile_ff, ctl + 2, job->d_scan, (unsigned)cap, ctl + 3, ctl + 4);
+  k_ff_count<<<kPersistentCtas, kScanTile, 0, st>>>(stream, ctl + 0, tile_ff, ctl + 1);
+  k_scan_partials<<<1, kScanTile, 0, st>>>(tile_ff, ntiles_words, 0, ctl + 1, ctl + 2);
+  k_stuff<<<kPersistentCtas, kScanTile, 0, st>>>(stream, ctl + 0, tile_ff, ctl + 2, job->d_scan, (unsigned)cap, ctl + 3, ctl + 4);
   ws.t_end();
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(job->h_scan_bytes, ctl, 32, cudaMemcpyDeviceToHost, st));

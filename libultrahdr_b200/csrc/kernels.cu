@@ -784,8 +784,14 @@ template <bool ZIGZAG>
 __global__ void __launch_bounds__(128) k_fdct_quant(const DctPlaneParams p) {
   const int bx = blockIdx.x * blockDim.x + threadIdx.x;
   const int by = blockIdx.y;
-  __shared__ uint16_t sq[64];
-  if (threadIdx.x < 64) sq[threadIdx.x] = p.q[threadIdx.x];
+  // divisor 8*Q and its reciprocal: floor(a / d) == umulhi(a, ceil(2^32 / d)) exactly while
+  // a * d < 2^32 (here a < 2^17 after the 8x-scaled islow DCT of 8-bit samples, d <= 2040)
+  __shared__ unsigned sd[64], sm[64];
+  if (threadIdx.x < 64) {
+    const unsigned d = (unsigned)p.q[threadIdx.x] << 3;
+    sd[threadIdx.x] = d;
+    sm[threadIdx.x] = (unsigned)((0x100000000ull + d - 1) / d);
+  }
   __syncthreads();
   if (bx >= p.wblocks) return;
   int v[64];
@@ -843,10 +849,10 @@ __global__ void __launch_bounds__(128) k_fdct_quant(const DctPlaneParams p) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int src = ZIGZAG ? zig(i + k) : i + k;
-      const int d = (int)sq[src] << 3;
-      int t = v[src];
-      const int a = abs(t) + (d >> 1);
-      int qv = a >= d ? a / d : 0;
+      const unsigned d = sd[src];
+      const int t = v[src];
+      const unsigned a = (unsigned)abs(t) + (d >> 1);
+      int qv = (int)__umulhi(a, sm[src]);
       qv = t < 0 ? -qv : qv;
       if (k & 1) w[k >> 1] |= ((unsigned)qv & 0xffff) << 16;
       else w[k >> 1] = (unsigned)qv & 0xffff;

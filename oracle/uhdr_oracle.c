@@ -853,3 +853,9 @@ int uo_convert_yuv(uo_image_t* im, int src, int dst) {
   }
   return 6;
 }
+
+/* reference expression of computeGain's logarithm (gainmapmath.cpp:774): double log2 of a float,
+ * narrowed to float -- vector form for the device log2 probe test */
+void uo_log2_of_float(const float* in, float* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = (float)log2((double)in[i]);
+}

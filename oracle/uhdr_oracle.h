@@ -56,6 +56,7 @@ int uo_affine_map_gain(float g, float mn, float mx, float gamma);
 int uo_encode_gain(float y_sdr, float y_hdr, const uo_metadata_t* md, float l2min, float l2max,
                    int idx);
 unsigned uo_float_to_half(float f);
+void uo_log2_of_float(const float* in, float* out, size_t n);
 
 int uo_generate_gainmap(const uo_image_t* sdr, const uo_image_t* hdr, const uo_gm_config_t* cfg,
                         uo_metadata_t* md_out, uo_image_t* gainmap_out /* tight, caller mem */);

@@ -226,3 +226,23 @@ def test_apply_8k(gpu, checker):
     a = gpu.apply(sdr, gi, md, A.CT_LINEAR)
     b = checker.apply(sdr, gi, md, A.CT_LINEAR)
     assert (a == b).all(), int((a != b).sum())
+
+
+def test_device_log2_equals_libm(gpu, oracle_libs):
+    """computeGain's `float(log2(double(q)))`: the fast gain-map kernels evaluate it with their own
+    table + polynomial in fp64.  It must give the float glibc gives, on a dense sample of the
+    quotient range incl. the neighbourhood of 1 and exact powers of two."""
+    import ctypes as C
+    o = oracle_libs.Oracle().lib
+    rs = np.random.RandomState(11)
+    parts = [np.exp(rs.uniform(np.log(1e-10), np.log(1e12), 6_000_000)),
+             1.0 + rs.uniform(-3e-3, 3e-3, 1_000_000), 1.0 + rs.uniform(-1e-6, 1e-6, 200_000),
+             2.0 ** np.arange(-30, 40), np.nextafter(np.float32(1), np.float32(0)) * np.ones(1),
+             np.array([1.0, 0.69921875, 1.3984375, 0.70710678, 1.41421356])]
+    x = np.ascontiguousarray(np.concatenate(parts).astype(np.float32))
+    want = np.zeros_like(x)
+    got = np.zeros_like(x)
+    o.uo_log2_of_float(x.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), C.c_size_t(x.size))
+    assert gpu.lib.uhdr_b200_probe_log2(x.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), x.size) == 0
+    bad = got.view(np.uint32) != want.view(np.uint32)
+    assert bad.sum() == 0, (int(bad.sum()), x[bad][:5], got[bad][:5], want[bad][:5])
