@@ -75,6 +75,8 @@ UHDR_EXTERN int uhdr_b200_enc_rearm(uhdr_codec_private_t* enc);
 /* diagnostic: out[i] = float(log2(double(in[i]))) exactly as the gain-map kernels evaluate computeGain's
  * log2 (gainmapmath.cpp:773-782); host pointers. */
 UHDR_EXTERN int uhdr_b200_probe_log2(const float* in, float* out, int n);
+/* diagnostic: out[i] = powf(in[i], y) as the device evaluates the reference's float std::pow sites */
+UHDR_EXTERN int uhdr_b200_probe_powf(const float* in, float y, float* out, int n);
 
 /* LUT blob (OETF / inverse-OETF tables): build on the host with the reference's libm
  * expressions, or install a blob that was broadcast from rank 0 (NCCL) into device memory. */

@@ -12,6 +12,7 @@
 //   * floatToHalf: values are clamped to [0, 10000/203] first, so the normal-number branch is
 //     (bits + 0x1000) >> 13 - (112 << 10); the denormal branch is kept for tiny values
 #include "kernels.cuh"
+#include "powf_glibc.cuh"
 #include "tables.h"
 
 namespace uhdr_b200 {
@@ -214,10 +215,10 @@ __global__ void __launch_bounds__(kBlockX* kBlockY) k_apply_fast(const ApplyPara
         hb = hb < 0.0f ? 0.0f : (hb > 1.0f ? 1.0f : hb);
         const float* t = p.luts + (OUT == 2 ? kLutHlgOetf : kLutPqOetf);
         if (OUT == 2) {
-          const double ex = (double)(1.0f / 1.2f);
-          hr = (float)pow((double)hr, ex);
-          hg = (float)pow((double)hg, ex);
-          hb = (float)pow((double)hb, ex);
+          const float ex = 1.0f / 1.2f;
+          hr = powf_glibc(hr, ex);
+          hg = powf_glibc(hg, ex);
+          hb = powf_glibc(hb, ex);
         }
         float e[3] = {hr, hg, hb};
         unsigned px = 0x3u << 30;

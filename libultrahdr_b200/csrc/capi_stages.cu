@@ -57,6 +57,18 @@ UHDR_API int uhdr_b200_probe_log2(const float* in, float* out, int n) {
   return ws->sync();
 }
 
+UHDR_API int uhdr_b200_probe_powf(const float* in, float y, float* out, int n) {
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  float* d_in = (float*)ws->dalloc((size_t)n * 4);
+  float* d_out = (float*)ws->dalloc((size_t)n * 4);
+  if (!d_in || !d_out) return E_MEM;
+  CUDA_TRY(cudaMemcpyAsync(d_in, in, (size_t)n * 4, cudaMemcpyHostToDevice, ws->stream()));
+  CUDA_TRY(launch_powf_probe(d_in, y, d_out, n, ws->stream()));
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ws->stream()));
+  return ws->sync();
+}
+
 UHDR_API int uhdr_b200_generate_gainmap(const uhdr_raw_image_t* sdr, const uhdr_raw_image_t* hdr,
                                         const uhdr_b200_gm_config_t* cfg,
                                         uhdr_gainmap_metadata_t* md_out,

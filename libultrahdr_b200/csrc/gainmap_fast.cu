@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "kernels.cuh"
+#include "powf_glibc.cuh"
 #include "runtime.h"
 #include "tables.h"
 
@@ -282,6 +283,10 @@ bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass) {
 }
 
 namespace {
+__global__ void k_powf_probe(const float* __restrict__ in, float y, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = powf_glibc(in[i], y);
+}
 __global__ void k_log2_probe(const float* __restrict__ in, float* __restrict__ out, int n, const double* __restrict__ tab_g) {
   __shared__ double tab[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = tab_g[i];
@@ -296,6 +301,11 @@ cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream
   const double* tab = nullptr;
   if (log2_table_dev(&tab) != E_OK) return cudaErrorUnknown;
   k_log2_probe<<<(n + 255) / 256, 256, 0, s>>>(d_in, d_out, n, tab);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_powf_probe(const float* d_in, float y, float* d_out, int n, cudaStream_t s) {
+  k_powf_probe<<<(n + 255) / 256, 256, 0, s>>>(d_in, y, d_out, n);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@
 
 #include <atomic>
 
+#include "powf_glibc.cuh"
 #include "tables.h"
 
 namespace uhdr_b200 {
@@ -366,8 +367,7 @@ __device__ __forceinline__ unsigned encode_gain(const GainmapGenParams& p, float
   if (gain < p.min_boost) gain = p.min_boost;
   if (gain > p.max_boost) gain = p.max_boost;
   float gn = (float)((log2((double)gain) - (double)p.log2_min) / (double)(p.log2_max - p.log2_min));
-  // powf(x, 1.0f) == x in glibc; for gamma != 1 evaluate in double and narrow
-  float gg = p.gamma == 1.0f ? gn : (float)pow((double)gn, (double)p.gamma);
+  float gg = p.gamma == 1.0f ? gn : powf_glibc(gn, p.gamma);  // powf(x, 1.0f) == x
   return (unsigned)__float2int_rz(gg * 255.0f) & 0xff;
 }
 
@@ -513,12 +513,12 @@ __device__ __forceinline__ void apply_one(const ApplyParams& p, int x, int y, C3
     h.r = clamp01(h.r); h.g = clamp01(h.g); h.b = clamp01(h.b);
     const float* t;
     if (p.out_ct == CT_HLG) {
-      // hlgInverseOotfApprox: float std::pow(x, 1/1.2f), argument is continuous -> evaluated in
-      // double and narrowed (DESIGN.md "powf parity")
-      const double ex = (double)(1.0f / 1.2f);
-      h.r = (float)pow((double)h.r, ex);
-      h.g = (float)pow((double)h.g, ex);
-      h.b = (float)pow((double)h.b, ex);
+      // hlgInverseOotfApprox: float std::pow(x, 1/1.2f) on a continuous argument: glibc's powf,
+      // operation for operation (powf_glibc.cuh)
+      const float ex = 1.0f / 1.2f;
+      h.r = powf_glibc(h.r, ex);
+      h.g = powf_glibc(h.g, ex);
+      h.b = powf_glibc(h.b, ex);
       t = p.luts + kLutHlgOetf;
     } else {
       t = p.luts + kLutPqOetf;
@@ -571,8 +571,8 @@ __global__ void __launch_bounds__(256) k_apply_gainmap(const ApplyParams p) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float srgb_oetf_dev(float e) {  // gainmapmath.cpp:139-148
   if (e <= 0.0031308f) return 12.92f * e;
-  // float std::pow with a continuous argument: evaluated in double and narrowed
-  return (1.0f + 0.055f) * (float)pow((double)e, (double)(1.0f / 2.4f)) - 0.055f;
+  // float std::pow with a continuous argument: glibc's powf, operation for operation
+  return (1.0f + 0.055f) * powf_glibc(e, 1.0f / 2.4f) - 0.055f;
 }
 __device__ __forceinline__ unsigned scale_to_8bit(float v) {  // :1979-1983 std::round
   int i = __float2int_rz(roundf(v * 255.0f));

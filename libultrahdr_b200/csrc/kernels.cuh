@@ -135,6 +135,7 @@ cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaSt
 bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass);
 cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, cudaStream_t s);
 cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream_t s);
+cudaError_t launch_powf_probe(const float* d_in, float y, float* d_out, int n, cudaStream_t s);
 cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s);
 cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s);
 cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s);

@@ -859,3 +859,9 @@ int uo_convert_yuv(uo_image_t* im, int src, int dst) {
 void uo_log2_of_float(const float* in, float* out, size_t n) {
   for (size_t i = 0; i < n; i++) out[i] = (float)log2((double)in[i]);
 }
+
+/* float std::pow as the reference calls it (gainmapmath.cpp:147,294,304): vector form for the
+ * device powf probe test */
+void uo_powf_vec(const float* in, float y, float* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = powf(in[i], y);
+}

@@ -57,6 +57,7 @@ int uo_encode_gain(float y_sdr, float y_hdr, const uo_metadata_t* md, float l2mi
                    int idx);
 unsigned uo_float_to_half(float f);
 void uo_log2_of_float(const float* in, float* out, size_t n);
+void uo_powf_vec(const float* in, float y, float* out, size_t n);
 
 int uo_generate_gainmap(const uo_image_t* sdr, const uo_image_t* hdr, const uo_gm_config_t* cfg,
                         uo_metadata_t* md_out, uo_image_t* gainmap_out /* tight, caller mem */);
