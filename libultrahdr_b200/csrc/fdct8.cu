@@ -1,0 +1,185 @@
+// Forward block stage, second generation: 8 lanes per 8x8 block instead of one thread per block.
+//   pass 1: lane (b, r) loads row r of block b (8 bytes; RGB: 24 bytes + jccolor.c conversion),
+//           runs the 1-D islow DCT on it in registers and parks the row in a warp-private,
+//           bank-padded shared-memory tile
+//   pass 2: lane (b, c) reads column c, runs the 1-D DCT, quantises with the exact reciprocal
+//           (floor(a/d) == umulhi(a, ceil(2^32/d)) while a*d < 2^32), scatters the 8 coefficients
+//           to their (zigzag) positions in the tile
+//   store : lane (b, j) writes 16 bytes; a warp writes 4 blocks = 512 contiguous bytes
+// A warp owns 4 horizontally adjacent blocks, a CTA 32; all planes of an image go in ONE launch
+// (grid.z), the three components of an RGB888 gain map are produced from one read of the pixels.
+// Arithmetic is the same integer arithmetic as k_fdct_quant (kernels.cu) / libjpeg-turbo's
+// jfdctint.c + jcdctmgr.c: bit-exact.
+#include "kernels.cuh"
+
+namespace uhdr_b200 {
+
+namespace {
+
+#define C_BITS 13
+#define P1_BITS 2
+#define DESC(x, n) (((x) + (1 << ((n)-1))) >> (n))
+
+template <int PASS>
+__device__ __forceinline__ void dct1d(int d[8]) {
+  const int tmp0 = d[0] + d[7], tmp7 = d[0] - d[7], tmp1 = d[1] + d[6], tmp6 = d[1] - d[6];
+  const int tmp2 = d[2] + d[5], tmp5 = d[2] - d[5], tmp3 = d[3] + d[4], tmp4 = d[3] - d[4];
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  constexpr int sh = PASS == 0 ? C_BITS - P1_BITS : C_BITS + P1_BITS;
+  if (PASS == 0) {
+    d[0] = (tmp10 + tmp11) << P1_BITS;
+    d[4] = (tmp10 - tmp11) << P1_BITS;
+  } else {
+    d[0] = DESC(tmp10 + tmp11, P1_BITS);
+    d[4] = DESC(tmp10 - tmp11, P1_BITS);
+  }
+  int z1 = (tmp12 + tmp13) * 4433;
+  d[2] = DESC(z1 + tmp13 * 6270, sh);
+  d[6] = DESC(z1 + tmp12 * (-15137), sh);
+  z1 = tmp4 + tmp7;
+  int z2 = tmp5 + tmp6, z3 = tmp4 + tmp6, z4 = tmp5 + tmp7;
+  const int z5 = (z3 + z4) * 9633;
+  const int t4 = tmp4 * 2446, t5 = tmp5 * 16819, t6 = tmp6 * 25172, t7 = tmp7 * 12299;
+  z1 *= -7373;
+  z2 *= -20995;
+  z3 = z3 * (-16069) + z5;
+  z4 = z4 * (-3196) + z5;
+  d[7] = DESC(t4 + z1 + z3, sh);
+  d[5] = DESC(t5 + z2 + z4, sh);
+  d[3] = DESC(t6 + z2 + z3, sh);
+  d[1] = DESC(t7 + z1 + z4, sh);
+}
+
+// natural index -> zigzag position
+__device__ const uint8_t kUnzigTab[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                                          41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                                          46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+__device__ __forceinline__ int unzig_rt(int n) { return kUnzigTab[n]; }
+
+constexpr int kTileStride = 72;  // ints per block tile: 64 + 8 padding (4 blocks of a warp on distinct banks)
+
+template <bool ZIGZAG>
+__device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int lane_r, const unsigned* sdiv,
+                                            const unsigned* smag, const uint8_t* sunzig, int16_t* gout_block_base) {
+  // pass 1 on this lane's row, park it
+  dct1d<0>(d);
+  int* t = tile + lane_b * kTileStride;
+  *(int4*)(t + lane_r * 8) = make_int4(d[0], d[1], d[2], d[3]);
+  *(int4*)(t + lane_r * 8 + 4) = make_int4(d[4], d[5], d[6], d[7]);
+  __syncwarp();
+  // pass 2 on column c = lane_r
+  const int c = lane_r;
+#pragma unroll
+  for (int k = 0; k < 8; k++) d[k] = t[k * 8 + c];
+  dct1d<1>(d);
+  __syncwarp();
+  // quantise; element k of this column is natural index k*8 + c
+  int16_t* t16 = reinterpret_cast<int16_t*>(t);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int n = k * 8 + c;
+    const unsigned dv = sdiv[n];
+    const unsigned a = (unsigned)abs(d[k]) + (dv >> 1);
+    int q = (int)__umulhi(a, smag[n]);
+    q = d[k] < 0 ? -q : q;
+    const int pos = ZIGZAG ? (int)sunzig[n] : n;
+    t16[pos] = (int16_t)q;
+  }
+  __syncwarp();
+  // 16 bytes per lane: coefficients [8*lane_r, 8*lane_r + 8) of block lane_b
+  if (gout_block_base) *(uint4*)(gout_block_base + lane_r * 8) = *(const uint4*)(t16 + lane_r * 8);
+  __syncwarp();
+}
+
+template <bool ZIGZAG>
+__global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
+  __shared__ unsigned sdiv[2][64], smag[2][64];
+  __shared__ int tiles[8][4 * kTileStride];
+  __shared__ uint8_t sunzig[64];
+  if (threadIdx.x >= 128 && threadIdx.x < 192) sunzig[threadIdx.x - 128] = (uint8_t)unzig_rt(threadIdx.x - 128);
+  if (threadIdx.x < 128) {
+    const int t = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const unsigned d = (unsigned)P.q[t][i] << 3;
+    sdiv[t][i] = d;
+    smag[t][i] = (unsigned)((0x100000000ull + d - 1) / d);
+  }
+  __syncthreads();
+  const Fdct8Plane& pl = P.plane[blockIdx.z];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane_b = lane >> 3, lane_r = lane & 7;
+  const int by = blockIdx.y;
+  if (by >= pl.hblocks) return;
+  const int bx = blockIdx.x * 32 + warp * 4 + lane_b;
+  const bool live = bx < pl.wblocks;
+  const int bxc = live ? bx : pl.wblocks - 1;  // dead lanes compute on a valid block, store nothing
+  int* tile = tiles[warp];
+  int d[8];
+  if (!pl.rgb) {
+    int y = by * 8 + lane_r;
+    if (y >= pl.h) {  // rows past the plane: the encoder helper's pad row (jpegencoderhelper.cpp:254-296)
+#pragma unroll
+      for (int k = 0; k < 8; k++) d[k] = pl.fill - 128;
+    } else {
+      const uint2 v = __ldg((const uint2*)(pl.src + (size_t)y * pl.stride + bxc * 8));
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        d[k] = (int)((v.x >> (8 * k)) & 0xff) - 128;
+        d[4 + k] = (int)((v.y >> (8 * k)) & 0xff) - 128;
+      }
+    }
+    int16_t* out = live ? pl.coefs[0] + ((size_t)by * pl.wblocks + bx) * 64 : nullptr;
+    block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, out);
+  } else {
+    // RGB888: libjpeg's scanline path replicates the last column / row (jcsample.c, jcprepct.c)
+    const int y = min(by * 8 + lane_r, pl.h - 1);
+    const uint8_t* row = pl.src + (size_t)y * pl.stride * 3;
+    int r[8], g[8], b[8];
+    if (bxc * 8 + 8 <= pl.w) {
+      const uint2* p = (const uint2*)(row + (size_t)bxc * 24);
+      const uint2 a = __ldg(p), bb = __ldg(p + 1), cc = __ldg(p + 2);
+      const unsigned w[6] = {a.x, a.y, bb.x, bb.y, cc.x, cc.y};
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int o = 3 * k;
+        r[k] = (w[o >> 2] >> (8 * (o & 3))) & 0xff;
+        g[k] = (w[(o + 1) >> 2] >> (8 * ((o + 1) & 3))) & 0xff;
+        b[k] = (w[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 0xff;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint8_t* px = row + (size_t)min(bxc * 8 + k, pl.w - 1) * 3;
+        r[k] = __ldg(px); g[k] = __ldg(px + 1); b[k] = __ldg(px + 2);
+      }
+    }
+#pragma unroll
+    for (int comp = 0; comp < 3; comp++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {  // jccolor.c rgb_ycc_convert, SCALEBITS 16
+        int v;
+        if (comp == 0) v = (19595 * r[k] + 38470 * g[k] + 7471 * b[k] + 32768) >> 16;
+        else if (comp == 1) v = (-11059 * r[k] - 21709 * g[k] + 32768 * b[k] + (128 << 16) + 32767) >> 16;
+        else v = (32768 * r[k] - 27439 * g[k] - 5329 * b[k] + (128 << 16) + 32767) >> 16;
+        d[k] = v - 128;
+      }
+      int16_t* out = live ? pl.coefs[comp] + ((size_t)by * pl.wblocks + bx) * 64 : nullptr;
+      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[comp]], smag[pl.tq[comp]], sunzig, out);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_fdct8(const Fdct8Params& P, cudaStream_t s) {
+  int maxw = 0, maxh = 0;
+  for (int i = 0; i < P.nplanes; i++) {
+    maxw = P.plane[i].wblocks > maxw ? P.plane[i].wblocks : maxw;
+    maxh = P.plane[i].hblocks > maxh ? P.plane[i].hblocks : maxh;
+  }
+  dim3 g((maxw + 31) / 32, maxh, P.nplanes), b(256);
+  if (P.zigzag) k_fdct8<true><<<g, b, 0, s>>>(P);
+  else k_fdct8<false><<<g, b, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace uhdr_b200

@@ -11,42 +11,53 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
   if (rc) return rc;
   const JpegFrame& f = job->frame;
   job->zigzag = zigzag;
+  Fdct8Params P;
+  memset(&P, 0, sizeof P);
+  P.zigzag = zigzag ? 1 : 0;
+  memcpy(P.q[0], f.qt[0], sizeof P.q[0]);
+  memcpy(P.q[1], f.qt[1], sizeof P.q[1]);
   for (int c = 0; c < f.ncomp; c++) {
-    const JpegComp& k = f.comp[c];
     job->d_coefs[c] = (int16_t*)ws.dalloc(f.blocks(c) * 128);
     if (!job->d_coefs[c]) return E_MEM;
-    DctPlaneParams p;
-    memset(&p, 0, sizeof p);
-    p.wblocks = k.wblocks;
-    p.hblocks = k.hblocks;
-    p.coefs = job->d_coefs[c];
-    p.zigzag_out = zigzag ? 1 : 0;
-    memcpy(p.q, f.qt[k.tq], sizeof p.q);
-    if (img.v.fmt == F_RGB888) {
-      // jpeg_write_scanlines path: jccolor.c conversion, edges replicated (jcsample.c/jcprepct.c)
-      p.src = (const uint8_t*)img.v.p[0];
-      p.src_stride = img.v.stride[0];
-      p.w = img.v.w;
-      p.h = img.v.h;
-      p.pad_mode = 1;
-      p.rgb_comp = c;
-    } else {
-      // raw_data_in path (jpegencoderhelper.cpp:246-309): whole blocks are read from the plane
-      // (device strides are >= wblocks*8 and the bytes past the width are defined, see
-      // alloc_dev_image / upload); rows past the plane height come from the helper's pad row:
-      // 0 for luma, 128 for chroma.
+  }
+  if (img.v.fmt == F_RGB888) {
+    // jpeg_write_scanlines path: jccolor.c conversion, edges replicated (jcsample.c/jcprepct.c);
+    // the three components come out of one pass over the pixels
+    Fdct8Plane& pl = P.plane[0];
+    P.nplanes = 1;
+    pl.src = (const uint8_t*)img.v.p[0];
+    pl.stride = img.v.stride[0];
+    pl.w = img.v.w;
+    pl.h = img.v.h;
+    pl.wblocks = f.comp[0].wblocks;
+    pl.hblocks = f.comp[0].hblocks;
+    pl.rgb = 1;
+    for (int c = 0; c < 3; c++) { pl.tq[c] = f.comp[c].tq; pl.coefs[c] = job->d_coefs[c]; }
+  } else {
+    // raw_data_in path (jpegencoderhelper.cpp:246-309): whole blocks are read from the plane
+    // (device strides are >= wblocks*8 and the bytes past the width are defined, see
+    // alloc_dev_image / upload); rows past the plane height come from the helper's pad row:
+    // 0 for luma, 128 for chroma.
+    P.nplanes = f.ncomp;
+    for (int c = 0; c < f.ncomp; c++) {
+      const JpegComp& k = f.comp[c];
       if (img.v.stride[c] < k.wblocks * 8)
         return fail(E_ERROR, "internal: device plane stride %d < padded width %d", img.v.stride[c], k.wblocks * 8);
-      p.src = (const uint8_t*)img.v.p[c];
-      p.src_stride = img.v.stride[c];
-      p.w = k.wblocks * 8;
-      p.h = k.height;
-      p.pad_mode = 0;
-      p.fill = c == 0 ? 0 : 128;
-      p.rgb_comp = -1;
+      if (((size_t)img.v.p[c] & 7) || (img.v.stride[c] & 7))
+        return fail(E_ERROR, "internal: device plane %d not 8-byte aligned", c);
+      Fdct8Plane& pl = P.plane[c];
+      pl.src = (const uint8_t*)img.v.p[c];
+      pl.stride = img.v.stride[c];
+      pl.w = k.wblocks * 8;
+      pl.h = k.height;
+      pl.wblocks = k.wblocks;
+      pl.hblocks = k.hblocks;
+      pl.fill = c == 0 ? 0 : 128;
+      pl.tq[0] = k.tq;
+      pl.coefs[0] = job->d_coefs[c];
     }
-    TIMED(ws, "fdct_quant", launch_fdct_quant(p, ws.stream()));
   }
+  TIMED(ws, "fdct_quant", launch_fdct8(P, ws.stream()));
   return E_OK;
 }
 

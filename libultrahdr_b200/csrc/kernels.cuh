@@ -106,6 +106,21 @@ struct DctPlaneParams {             // forward: samples -> coefficients
   int16_t* coefs;                   // [hblocks*wblocks][64]
 };
 
+struct Fdct8Plane {                 // one launch covers every plane of an image (fdct8.cu)
+  const uint8_t* src;
+  int stride;                       // bytes per row for planes, pixels per row for RGB888
+  int w, h;                         // RGB: real size (edges replicated); plane: rows (>= h read `fill`)
+  int wblocks, hblocks;
+  int fill, rgb;
+  int tq[3];
+  int16_t* coefs[3];                // plane: [0]; RGB888: Y, Cb, Cr
+};
+struct Fdct8Params {
+  Fdct8Plane plane[3];
+  int nplanes, zigzag;
+  uint16_t q[2][64];
+};
+
 struct IdctPlaneParams {
   const int16_t* coefs;
   uint16_t q[64];
@@ -139,6 +154,7 @@ cudaError_t launch_powf_probe(const float* d_in, float y, float* d_out, int n, c
 cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s);
 cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s);
 cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s);
+cudaError_t launch_fdct8(const Fdct8Params& p, cudaStream_t s);
 cudaError_t launch_idct_dequant(const IdctPlaneParams& p, cudaStream_t s);
 cudaError_t launch_ycc_to_rgba(const YccToRgbaParams& p, cudaStream_t s);
 
