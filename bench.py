@@ -176,16 +176,28 @@ def kernel_report(lib, reset=True):
     return out
 
 
-# algorithmic bytes per launch (DESIGN.md "Kernels"), per full-resolution pixel, for the API-1
-# default configuration (P010 + YUV420 in, RGB888 map at scale 1)
+# algorithmic (compulsory) bytes per launch, per full-resolution pixel of a 4K API-1 frame with the
+# default settings (P010 + YUV420 in, RGB888 gain map at scale 1); derivations in DESIGN.md section 3
 ALG_BYTES_PER_PX = {
-    "gainmap_pass1": 4.5 + 12.0,   # read P010 3 + YUV420 1.5, write 3 float gains
-    "gainmap_affine": 12.0 + 3.0,  # read gains, write RGB888
+    "gainmap_pass1": 4.5 + 12.0,        # read P010 3 + YUV420 1.5, write 3 float gains
+    "gainmap_affine": 12.0 + 3.0,       # read gains, write RGB888
     "gainmap_onepass": 4.5 + 3.0,
-    "yuv_convert": 3.0,            # in place 1.5 read + 1.5 written
+    "yuv_convert": 3.0,                 # in place: 1.5 read + 1.5 written
     "tonemap": 4.5,
-    "apply_gainmap": 13.5,         # YUV420 1.5 + RGBA8888 map 4 read, RGBA-F16 8 written
+    "apply_gainmap": 13.5,              # YUV420 1.5 + RGBA8888 map 4 read, RGBA-F16 8 written
+    "fdct_quant": (4.5 + 9.0) / 2,      # avg of the two launches: 4:2:0 image 1.5 in + 3 out; RGB map 3 in + 6 out
+    "huff_blocks": (3.0 + 6.0) / 2,     # coefficient read (2 B/sample); scratch/stream writes are O(stream size)
 }
+DATA_KERNELS = ("gainmap_pass1", "gainmap_affine", "fdct_quant", "huff_blocks", "yuv_convert")
+
+
+def load_traffic():
+    """dram__bytes_read+write per launch from the committed ncu capture (profiles/), if any"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 def bench_b200(args, rank, world):
@@ -261,8 +273,7 @@ def bench_b200(args, rank, world):
 
     for _ in range(args.warmup):
         resident_step()
-    lib.uhdr_b200_set_kernel_timing(1)
-    kernel_report(lib)
+    lib.uhdr_b200_set_kernel_timing(0)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -273,8 +284,21 @@ def bench_b200(args, rank, world):
     torch.cuda.synchronize()
     t_res = max_over_ranks(time.perf_counter() - t0)
     launches = lib.uhdr_b200_kernel_launches() - l0
+    lib.uhdr_b200_set_kernel_timing(1)
     barrier()
     sampler.stop_flag = True
+    kt_busy = kernel_report(lib)
+    # kernel durations for the roofline: the same frames, ONE encoder in flight, so that the CUDA
+    # events around each launch are not stretched by kernels of other streams sharing the SMs
+    for _ in range(2):
+        for i in range(F):
+            handles[i].rearm()
+            handles[i].encode()
+    kernel_report(lib)
+    for _ in range(args.steps):
+        for i in range(F):
+            handles[i].rearm()
+            handles[i].encode()
     kt = kernel_report(lib)
     lib.uhdr_b200_set_kernel_timing(0)
     value = world * F * args.steps * MPIX_4K / t_res
@@ -309,24 +333,28 @@ def bench_b200(args, rank, world):
 
     pk, pk_kind = peaks()
     hbm = pk["hbm_gbs"]
-    # dominant kernel of the timed region
-    dom = max(kt.items(), key=lambda kv: kv[1][1]) if kt else (None, (0, 0.0))
-    roof = None
-    if dom[0]:
-        name, (cnt, ms) = dom
+    traffic = load_traffic()
+    kernels = {}
+    for k, (cnt, ms) in sorted(kt.items()):
         avg_ms = ms / cnt
-        bpp = ALG_BYTES_PER_PX.get(name)
-        if name == "fdct_quant":
-            # three launches per image (components); report the average launch: 3 B/sample
-            alg = (W4K * H4K * 1.5 + W4K * H4K * 3.0) * 3.0 / 6.0
-        else:
-            alg = bpp * W4K * H4K if bpp else None
-        if alg:
-            ach = alg / (avg_ms * 1e-3) / 1e9
-            roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                    "frac": round(ach / hbm, 4), "traffic": None, "avg_launch_ms": round(avg_ms, 4),
-                    "alg_bytes_per_launch": int(alg), "peak_kind": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
-    kernels = {k: {"launches": v[0], "avg_ms": round(v[1] / v[0], 4)} for k, v in sorted(kt.items())}
+        e = {"launches_per_frame": round(cnt / (F * args.steps), 2), "avg_ms": round(avg_ms, 4)}
+        bpp = ALG_BYTES_PER_PX.get(k)
+        if bpp:
+            ach = bpp * W4K * H4K / (avg_ms * 1e-3) / 1e9
+            e.update({"alg_bytes_per_launch": int(bpp * W4K * H4K), "achieved_gbs": round(ach, 1), "frac_of_hbm": round(ach / hbm, 4)})
+        kernels[k] = e
+    # dominant kernel = largest share of the single-stream step among the data-moving kernels
+    cand = [(kt[k][1], k) for k in DATA_KERNELS if k in kt]
+    roof = None
+    if cand:
+        name = max(cand)[1]
+        e = kernels[name]
+        roof = {"kernel": name, "bound": "hbm", "achieved": e["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": e["frac_of_hbm"], "traffic": traffic.get(name), "avg_launch_ms": e["avg_ms"],
+                "alg_bytes_per_launch": e["alg_bytes_per_launch"],
+                "share_of_step": round(kt[name][1] / sum(v[1] for v in kt.values()), 3),
+                "peak_kind": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "how": "CUDA events around every launch on its stream, %d steps with one encoder in flight" % args.steps}
 
     extra = extra_measurements(lib, api, hbm)
 
@@ -419,6 +447,34 @@ def extra_measurements(lib, api, hbm):
         out["api0_encode_4k"] = {"mpix_s_resident_1slot": round(MPIX_4K / dt, 1), "ms_per_frame": round(dt * 1e3, 3),
                                  "kernels_avg_ms": {k: round(v[1] / v[0], 4) for k, v in kt.items()}}
         lib.uhdr_b200_set_kernel_timing(0)
+        # config 3 end to end: uhdr_decode of a 7680x4320 JPEG/R (multichannel map, scale 1) to RGBA half
+        # float, host buffers both ways (stream in, 265 MB of pixels out); entropy decoding is host code
+        p8, y8 = make_frame(W8K, H8K, 7)
+        h8, s8, _k8 = frame_descs(p8, y8, W8K, H8K)
+        data = api.encode(h8, s8)
+
+        def timed_decode(L, n):
+            buf = np.frombuffer(data, np.uint8).copy()
+            ci = A.CompressedImage(buf.ctypes.data, len(data), len(data), -1, -1, -1)
+            ts = []
+            for _ in range(n):
+                dec = C.c_void_p(L.uhdr_create_decoder())
+                t0 = time.perf_counter()
+                assert L.uhdr_dec_set_image(dec, C.byref(ci)).error_code == 0
+                e = L.uhdr_decode(dec)
+                assert e.error_code == 0, e.detail
+                assert L.uhdr_get_decoded_image(dec).contents.w == W8K
+                ts.append(time.perf_counter() - t0)
+                L.uhdr_release_decoder(dec)
+            return min(ts)
+        dt = timed_decode(lib, 4)
+        out["decode_8k_e2e"] = {"ms": round(dt * 1e3, 2), "mpix_s": round(W8K * H8K / 1e6 / dt, 1), "stream_bytes": len(data),
+                                "note": "uhdr_decode through the C ABI, best of 4; Huffman decode on one host thread per JPEG"}
+        if T.have_ref():
+            rapi, rlib = load_api(T.REF_SO)
+            dtr = timed_decode(rlib, 1)
+            out["decode_8k_e2e"]["cpu_reference_ms"] = round(dtr * 1e3, 1)
+            out["decode_8k_e2e"]["cpu_reference_mpix_s"] = round(W8K * H8K / 1e6 / dtr, 1)
     except Exception as e:  # noqa: BLE001
         out["error"] = repr(e)
     return out
