@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         ok &= p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-lcudart", "-lpthread"])
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-lcudart", "-lpthread"])
     return OUT
 
 

@@ -27,42 +27,68 @@ namespace {
 struct Log2Tab { double invc[128], logc[128]; };
 constexpr unsigned kLogOff = 0x3f330000u;
 
-__device__ __forceinline__ double log2_core(float q, const double* __restrict__ tab /* smem: invc[128], logc[128] */) {
+// polynomial of log2(1+r)/r, highest degree first; in the constant bank so that every DFMA takes its
+// coefficient as a c[][] operand instead of materialising it with two moves
+__constant__ double kLog2Poly[8] = {
+    -0.18033688011112042,  // -1/(8 ln2)
+    0.20609929155556619,   //  1/(7 ln2)
+    -0.24044917348149390,  // -1/(6 ln2)
+    0.28853900817779268,   //  1/(5 ln2)
+    -0.36067376022224085,  // -1/(4 ln2)
+    0.48089834696298783,   //  1/(3 ln2)
+    -0.72134752044448170,  // -1/(2 ln2)
+    1.4426950408889634};   //  1/ln2
+
+__device__ __forceinline__ double log2_core(float q, const double2* __restrict__ tab /* smem: {invc, logc}[128] */) {
   const unsigned ix = __float_as_uint(q);
   const unsigned tmp = ix - kLogOff;
   const int i = (tmp >> 16) & 127;
   const int k = (int)tmp >> 23;
-  const float m = __uint_as_float(ix - (tmp & 0xff800000u));
-  const double r = fma((double)m, tab[i], -1.0);
+  const unsigned im = ix - (tmp & 0xff800000u);  // bits of m (a normal float in [OFF, 2*OFF))
+  // exact widenings done with integer ops (the conversion unit is the busiest pipe of this kernel):
+  // m: re-bias the exponent, shift the mantissa;  k: 2^52 + 2^31 + k minus the same constant
+  const double md = __hiloint2double((int)((im >> 3) + 0x38000000u), (int)(im << 29));
+  const double kd = __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)k)) - 4503601774854144.0;
+  const double2 t = tab[i];
+  const double r = fma(md, t.x, -1.0);
   // log2(1+r) = r * P(r), P = sum_{j>=0} (-1)^j r^j / ((j+1) ln2)
-  double p = -0.18033688011112042;            // -1/(8 ln2)
-  p = fma(p, r, 0.20609929155556619);         //  1/(7 ln2)
-  p = fma(p, r, -0.24044917348149390);        // -1/(6 ln2)
-  p = fma(p, r, 0.28853900817779268);         //  1/(5 ln2)
-  p = fma(p, r, -0.36067376022224085);        // -1/(4 ln2)
-  p = fma(p, r, 0.48089834696298783);         //  1/(3 ln2)
-  p = fma(p, r, -0.72134752044448170);        // -1/(2 ln2)
-  p = fma(p, r, 1.4426950408889634);          //  1/ln2
-  return fma(p, r, (double)k + tab[128 + i]);
+  double p = kLog2Poly[0];
+#pragma unroll
+  for (int j = 1; j < 8; j++) p = fma(p, r, kLog2Poly[j]);
+  return fma(p, r, kd + t.y);
+}
+
+// a / b for positive normal operands whose quotient is far from the float range limits: the
+// compiler's own division sequence (reciprocal estimate, one Newton step, residual correction)
+// without its out-of-range check and slow-path call.  Rounds like IEEE division in that domain.
+__device__ __forceinline__ float div_pos(float a, float b) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  const float e = __fmaf_rn(-b, r, 1.0f);
+  r = __fmaf_rn(r, e, r);
+  float q = __fmul_rn(a, r);
+  const float rem = __fmaf_rn(-b, q, a);
+  return __fmaf_rn(r, rem, q);
 }
 
 // ---- shared memory ------------------------------------------------------------------------------
 struct GmSmem {
-  double log2tab[256];
+  double2 log2tab[128];  // {invc, logc}
   float srgb2[2048];   // srgb2[j] = srgbInvLUT[(j+1)>>1]
   float hdr2[8192];    // hdr2[j]  = hdrInvLUT[(j+1)>>1], 4096-entry source table
 };
 __device__ __forceinline__ float fetch2(const float* t, float x, float scale8) {  // x in [0,1]
-  const int off = __float2int_rz(x * scale8) & ~3;
+  // trunc(x*scale8) without the conversion unit: adding 2^23 toward zero leaves it in the mantissa
+  const int off = __float_as_int(__fadd_rz(x * scale8, 8388608.0f)) & 0x7ffffc;
   return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(t) + off);
 }
 
 template <bool ONEPASS, int NCH, int GAMUT /*0 none, 1 on sdr, 2 on hdr*/, bool LIMITED>
-__global__ void __launch_bounds__(256) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g) {
-  extern __shared__ double smem_d[];
+__global__ void __launch_bounds__(256, 3) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g) {
+  extern __shared__ double2 smem_d[];
   GmSmem& sm = *reinterpret_cast<GmSmem*>(smem_d);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
-  for (int i = tid; i < 256; i += nt) sm.log2tab[i] = log2tab_g[i];
+  for (int i = tid; i < 128; i += nt) sm.log2tab[i] = make_double2(log2tab_g[i], log2tab_g[128 + i]);
   for (int i = tid; i < 2048; i += nt) sm.srgb2[i] = __ldg(p.luts + kLutSrgbInv + min((i + 1) >> 1, 1023));
   const float* hsrc = p.luts + (p.hdr_ct == CT_HLG ? kLutHlgInvOotf : kLutPqInv);
   for (int i = tid; i < 8192; i += nt) sm.hdr2[i] = __ldg(hsrc + min((i + 1) >> 1, 4095));
@@ -153,7 +179,7 @@ __global__ void __launch_bounds__(256) k_gainmap_fast(const GainmapGenParams p, 
           for (int c = 0; c < NCH; c++) {
             if (ONEPASS) {  // encodeGain gainmapmath.cpp:758-771 (gamma 1: powf(x, 1) == x)
               float gain = 1.0f;
-              if (sv3[c] > 0.0f) gain = hv3[c] / sv3[c];
+              if (sv3[c] > 0.0f) gain = div_pos(hv3[c], sv3[c]);
               if (gain < p.min_boost) gain = p.min_boost;
               if (gain > p.max_boost) gain = p.max_boost;
               const float gn = (float)((log2_core(gain, sm.log2tab) - (double)p.log2_min) / (double)(p.log2_max - p.log2_min));
@@ -161,7 +187,7 @@ __global__ void __launch_bounds__(256) k_gainmap_fast(const GainmapGenParams p, 
               const int bi = i * NCH + c;
               bout[bi >> 2] |= code << (8 * (bi & 3));
             } else {        // computeGain :773-782
-              float g = (float)log2_core((hv3[c] + 1e-7f) / (sv3[c] + 1e-7f), sm.log2tab);
+              float g = (float)log2_core(div_pos(hv3[c] + 1e-7f, sv3[c] + 1e-7f), sm.log2tab);
               if (sv3[c] < 2.f / 255.0f) g = fminf(g, 2.3f);
               gout[i * NCH + c] = g;
               mn[c] = fminf(mn[c], g);
@@ -218,6 +244,44 @@ __global__ void __launch_bounds__(256) k_gainmap_fast(const GainmapGenParams p, 
   }
 }
 
+// ---- pass 2 (jpegr.cpp:988-1013, affineMapGain gainmapmath.cpp:784-789), gamma 1, tight rows ------
+// The gains and the map are walked as flat arrays, one float4 -> one packed u32 per step.  The
+// grid has a multiple of 3 threads, so with three channels every thread keeps the same channel
+// phase for its whole walk and holds (min, range, refined 1/range) per element in registers.
+template <int NCH>
+__global__ void __launch_bounds__(192) k_affine_fast(const AffineParams p, const long long n4) {
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  float mn[4], d[4], rc[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = NCH == 3 ? (int)((t0 * 4 + j) % 3) : 0;
+    mn[j] = p.minmax_f[c];
+    d[j] = p.minmax_f[3 + c] - mn[j];
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d[j]));
+    rc[j] = __fmaf_rn(r, __fmaf_rn(-d[j], r, 1.0f), r);
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(p.gains);
+  unsigned* o = reinterpret_cast<unsigned*>(p.dst);
+#pragma unroll 4
+  for (long long f = t0; f < n4; f += nthr) {
+    const float4 g = __ldcs(g4 + f);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+    unsigned w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float a = gv[j] - mn[j];
+      float q = __fmul_rn(a, rc[j]);           // a / d[j], same steps as div_pos
+      q = __fmaf_rn(rc[j], __fmaf_rn(-d[j], q, a), q);
+      float t = q * 255.0f + 0.5f;
+      t = fminf(fmaxf(t, 0.0f), 255.0f);
+      w |= (__float_as_uint(__fadd_rz(t, 8388608.0f)) & 0xffu) << (8 * j);
+    }
+    o[f] = w;
+  }
+}
+
 // host: table of the log2 kernel, uploaded once per device
 int log2_table_dev(const double** out) {
   static std::mutex mu;
@@ -267,6 +331,21 @@ cudaError_t launch_g(const GainmapGenParams& p, const double* tab, dim3 g, dim3 
 
 }  // namespace
 
+bool affine_fast_eligible(const AffineParams& p) {
+  if (p.gamma != 1.0f || (p.nch != 1 && p.nch != 3) || p.dst_stride != p.map_w) return false;
+  if (((size_t)p.map_w * p.map_h * p.nch) & 3) return false;
+  return !(((size_t)p.gains & 15) || ((size_t)p.dst & 3));
+}
+cudaError_t launch_affine_fast(const AffineParams& p, cudaStream_t s) {
+  const long long n4 = (long long)p.map_w * p.map_h * p.nch / 4;
+  long long ctas = (n4 + 192 * 4 - 1) / (192 * 4);
+  if (ctas > 148 * 10) ctas = 148 * 10;
+  if (ctas < 1) ctas = 1;
+  if (p.nch == 3) k_affine_fast<3><<<(unsigned)ctas, 192, 0, s>>>(p, n4);
+  else k_affine_fast<1><<<(unsigned)ctas, 192, 0, s>>>(p, n4);
+  return cudaGetLastError();
+}
+
 bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass) {
   if (p.hdr.fmt != F_P010 || p.sdr.fmt != F_YUV420 || p.scale != 1) return false;
   if (p.hdr_ct != CT_HLG && p.hdr_ct != CT_PQ) return false;
@@ -288,8 +367,8 @@ __global__ void k_powf_probe(const float* __restrict__ in, float y, float* __res
   if (i < n) out[i] = powf_glibc(in[i], y);
 }
 __global__ void k_log2_probe(const float* __restrict__ in, float* __restrict__ out, int n, const double* __restrict__ tab_g) {
-  __shared__ double tab[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = tab_g[i];
+  __shared__ double2 tab[128];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) tab[i] = make_double2(tab_g[i], tab_g[128 + i]);
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)log2_core(in[i], tab);

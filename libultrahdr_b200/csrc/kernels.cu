@@ -994,6 +994,10 @@ cudaError_t launch_gainmap_finalize(const GainmapFinalizeParams& p, cudaStream_t
   return cudaGetLastError();
 }
 cudaError_t launch_gainmap_affine(const AffineParams& p, cudaStream_t s) {
+  if (affine_fast_eligible(p)) {
+    COUNT_LAUNCH();
+    return launch_affine_fast(p, s);
+  }
   const int row_bytes = p.map_w * p.nch;
   dim3 b(256, 1);
   dim3 g((row_bytes / 4 + 1 + 255) / 256, p.map_h);

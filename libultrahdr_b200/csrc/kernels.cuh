@@ -147,6 +147,8 @@ cudaError_t launch_apply_gainmap(const ApplyParams& p, cudaStream_t s);
 bool apply_fast_eligible(const ApplyParams& p);
 cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaStream_t s);
 // fast path (gainmap_fast.cu): P010 + YUV420, scale 1
+bool affine_fast_eligible(const AffineParams& p);
+cudaError_t launch_affine_fast(const AffineParams& p, cudaStream_t s);
 bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass);
 cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, cudaStream_t s);
 cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream_t s);
