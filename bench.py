@@ -386,48 +386,58 @@ def bench_b200(args, rank, world):
         dist.destroy_process_group()
 
 
+def apply_8k(lib, hbm, iters=6):
+    """applyGainMap kernel at 7680x4320 (config 3 geometry), CUDA-event time per launch"""
+    import uhdr_testlib as T
+    out = {}
+    gpu = T.Gpu()
+    # applyGainMap at 8K: RGBA8888 map, scale 1 (13.5 B/px).  Two contents: "natural" (smooth +
+    # texture, like the encode frames) and uniform noise (worst case for the table gathers)
+    md = A.GainmapMetadata()
+    for i, (mx, mn) in enumerate(((65.1, 4.9e-5), (845.9, 2.7e-3), (1283.8, 4.9e-5))):
+        md.max_content_boost[i], md.min_content_boost[i], md.gamma[i] = mx, mn, 1.0
+        md.offset_sdr[i] = md.offset_hdr[i] = 1e-7
+    md.hdr_capacity_min, md.hdr_capacity_max, md.use_base_cg = 1.0, 4.926108, 0
+    lib.uhdr_b200_set_kernel_timing(1)
+    for content in ("natural", "noise"):
+        if content == "noise":
+            sb = T.make_yuv420(W8K, H8K, "noise")
+            gm = np.random.RandomState(7).randint(0, 256, (H8K, W8K, 4)).astype(np.uint8)
+        else:
+            _p, sb = make_frame(W8K, H8K, 5)
+            yy, xx = np.mgrid[0:H8K, 0:W8K].astype(np.float32)
+            g0 = 128 + 90 * np.sin(xx / 301.0) * np.cos(yy / 257.0) + np.random.RandomState(3).randn(H8K, W8K) * 2
+            gm = np.stack([g0, g0 * 0.9 + 10, g0 * 0.8 + 20, np.full_like(g0, 255)], -1).clip(0, 255).astype(np.uint8)
+            del yy, xx, g0, _p
+        sdr, k2 = A.yuv420_image(sb, W8K, H8K, A.CG_BT709)
+        gi = T.gm_image(gm, A.CG_BT2100)
+        for _ in range(3):  # warm-up: module load, arena growth, clocks
+            gpu.apply(sdr, gi, md, A.CT_LINEAR)
+        kernel_report(lib)
+        for _ in range(iters):
+            gpu.apply(sdr, gi, md, A.CT_LINEAR)
+        kt = kernel_report(lib)
+        if "apply_gainmap" in kt:
+            cnt, ms = kt["apply_gainmap"]
+            avg = ms / cnt
+            alg = 13.5 * W8K * H8K
+            out["apply_gainmap_8k_" + content] = {
+                "avg_launch_ms": round(avg, 4), "mpix_s": round(W8K * H8K / 1e6 / (avg * 1e-3), 1),
+                "roofline": {"bound": "hbm", "achieved": round(alg / (avg * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
+                             "frac": round(alg / (avg * 1e-3) / 1e9 / hbm, 4), "alg_bytes_per_launch": int(alg)}}
+        del sb, gm
+    lib.uhdr_b200_set_kernel_timing(0)
+    return out
+
+
 def extra_measurements(lib, api, hbm):
     """config 3 (8K decode -> RGBA half float) and config 2 (4K API-0), device timings of the
     kernels named by the north star; small step counts, not the headline."""
     import uhdr_testlib as T
     out = {}
     try:
-        gpu = T.Gpu()
-        # applyGainMap at 8K: RGBA8888 map, scale 1 (13.5 B/px).  Two contents: "natural" (smooth +
-        # texture, like the encode frames) and uniform noise (worst case for the table gathers)
-        md = A.GainmapMetadata()
-        for i, (mx, mn) in enumerate(((65.1, 4.9e-5), (845.9, 2.7e-3), (1283.8, 4.9e-5))):
-            md.max_content_boost[i], md.min_content_boost[i], md.gamma[i] = mx, mn, 1.0
-            md.offset_sdr[i] = md.offset_hdr[i] = 1e-7
-        md.hdr_capacity_min, md.hdr_capacity_max, md.use_base_cg = 1.0, 4.926108, 0
+        out.update(apply_8k(lib, hbm))
         lib.uhdr_b200_set_kernel_timing(1)
-        for content in ("natural", "noise"):
-            if content == "noise":
-                sb = T.make_yuv420(W8K, H8K, "noise")
-                gm = np.random.RandomState(7).randint(0, 256, (H8K, W8K, 4)).astype(np.uint8)
-            else:
-                _p, sb = make_frame(W8K, H8K, 5)
-                yy, xx = np.mgrid[0:H8K, 0:W8K].astype(np.float32)
-                g0 = 128 + 90 * np.sin(xx / 301.0) * np.cos(yy / 257.0) + np.random.RandomState(3).randn(H8K, W8K) * 2
-                gm = np.stack([g0, g0 * 0.9 + 10, g0 * 0.8 + 20, np.full_like(g0, 255)], -1).clip(0, 255).astype(np.uint8)
-                del yy, xx, g0, _p
-            sdr, k2 = A.yuv420_image(sb, W8K, H8K, A.CG_BT709)
-            gi = T.gm_image(gm, A.CG_BT2100)
-            for _ in range(3):  # warm-up: module load, arena growth, clocks
-                gpu.apply(sdr, gi, md, A.CT_LINEAR)
-            kernel_report(lib)
-            for _ in range(6):
-                gpu.apply(sdr, gi, md, A.CT_LINEAR)
-            kt = kernel_report(lib)
-            if "apply_gainmap" in kt:
-                cnt, ms = kt["apply_gainmap"]
-                avg = ms / cnt
-                alg = 13.5 * W8K * H8K
-                out["apply_gainmap_8k_" + content] = {
-                    "avg_launch_ms": round(avg, 4), "mpix_s": round(W8K * H8K / 1e6 / (avg * 1e-3), 1),
-                    "roofline": {"bound": "hbm", "achieved": round(alg / (avg * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
-                                 "frac": round(alg / (avg * 1e-3) / 1e9 / hbm, 4), "alg_bytes_per_launch": int(alg)}}
-            del sb, gm
         # API-0 4K through the C API (resident inputs)
         p010, _ = make_frame(W4K, H4K, 99)
         hdr, _k = A.p010_image(p010, W4K, H4K, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)

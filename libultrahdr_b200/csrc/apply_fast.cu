@@ -37,6 +37,13 @@ __device__ __forceinline__ void pack_half4(float r, float g, float b, unsigned& 
   hi = *reinterpret_cast<const unsigned*>(&ba);
 }
 
+// kMaxH = reference floatToHalf(10000/203) = 0x5228; the alpha half 0x3C00 passes through both bounds
+__device__ __forceinline__ void pack_half4_clamped(float r, float g, float b, unsigned& lo, unsigned& hi) {
+  pack_half4(r, g, b, lo, hi);
+  lo = __vmins2(__vmaxs2(lo, 0u), 0x52285228u);
+  hi = __vmins2(__vmaxs2(hi, 0u), 0x52285228u);
+}
+
 // Shared-memory tables, byte-offset addressed.
 //   srgb2[j] = srgbInvOetfLUT[(j + 1) >> 1], j = floor(2 * x * 1023): the reference index
 //   int32(double(x*1023) + 0.5) equals (floor(2v) + 1) >> 1, and floor(4a) & ~3 == 4 * floor(a),
@@ -239,6 +246,231 @@ __global__ void __launch_bounds__(kBlockX* kBlockY) k_apply_fast(const ApplyPara
   }
 }
 
+// ---- scale 1, linear half-float output: the 8K decode configuration ----------------------------
+// Persistent grid (tables staged once per CTA, no wave tail) and packed-pair arithmetic: sm_100's
+// two-wide fp32 instructions (FMUL2 / FFMA2) work on the two horizontally adjacent pixels that
+// share a chroma sample, halving the issue slots of every multiply and add while each lane still
+// rounds exactly like the scalar instruction.  Only fused-multiply-add *forms* are written
+// (a*b + -0, a*1 + c, b*-1 + a): they equal the plain product / sum / difference bit for bit.
+// The -0 of the product form arrives as a kernel argument: with a literal the assembler reduces
+// the form to a multiply and then contracts it into a following add even though both carry .rn
+// (observed with ptxas 12.9), which would round once where the reference rounds twice.
+struct V2 { unsigned long long v; };
+__device__ __forceinline__ V2 v2(float a, float b) { V2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ V2 bc(float a) { return v2(a, a); }
+__device__ __forceinline__ void un(V2 a, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); }
+__device__ __forceinline__ void un(V2 a, unsigned& x, unsigned& y) { asm("mov.b64 {%0, %1}, %2;" : "=r"(x), "=r"(y) : "l"(a.v)); }
+__device__ __forceinline__ V2 vmul(V2 a, V2 b, unsigned long long nz) { V2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(nz)); return r; }
+constexpr unsigned long long kNegZero2 = 0x8000000080000000ULL;
+__device__ __forceinline__ V2 vadd(V2 a, V2 b) { V2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(0x3f8000003f800000ULL), "l"(b.v)); return r; }
+__device__ __forceinline__ V2 vsub(V2 a, V2 b) { V2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(b.v), "l"(0xbf800000bf800000ULL), "l"(a.v)); return r; }
+// trunc() of two non-negative values < 2^23, left in the mantissas (add 2^23 toward zero)
+__device__ __forceinline__ V2 vtrunc_bits(V2 a) { V2 r; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(0x3f8000003f800000ULL), "l"(0x4b0000004b000000ULL)); return r; }
+
+struct Lin1Smem {
+  float srgb2[2048];
+  float gain[768];
+};
+__device__ __forceinline__ float lds_off(const float* base, unsigned byte_off) {
+  return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + byte_off);
+}
+
+template <int BPP>
+struct TileIn {   // what one thread reads for its 4x2 pixels
+  unsigned yw[2], uu, vv;
+  uint4 m4[2];
+  unsigned m3[2][3];
+  int x, y;
+};
+
+template <int BPP, int GAMUT>
+__global__ void __launch_bounds__(kBlockX* kBlockY, 4) k_apply_lin1(const ApplyParams p, const float* __restrict__ gain_u8, const int tiles_x,
+                                                                 const int ntiles, const int wide_store, const unsigned long long nz,
+                                                                 unsigned* __restrict__ sched) {
+  __shared__ Lin1Smem sm;
+  __shared__ int s_tile[4];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  for (int i = tid; i < 2048; i += nt) sm.srgb2[i] = __ldg(p.luts + kLutSrgbInv + ((i + 1) >> 1 > 1023 ? 1023 : (i + 1) >> 1));
+  for (int i = tid; i < 768; i += nt) sm.gain[i] = __ldg(gain_u8 + i);
+  // tiles are handed out through a counter (zeroed by the caller with the table upload): the CTAs
+  // of the single resident wave then finish together instead of leaving SMs idle behind the
+  // slowest static share.  The next ticket is fetched while the current tile is being processed.
+  int tick = (int)blockIdx.x;   // static striding when no counter is given
+  auto next_ticket = [&]() -> int {
+    if (sched) return (int)atomicAdd(sched, 1u);
+    const int t = tick;
+    tick += (int)gridDim.x;
+    return t;
+  };
+  if (tid == 0) {
+    s_tile[0] = next_ticket();
+    s_tile[1] = next_ticket();
+  }
+  __syncthreads();
+  const uint8_t* __restrict__ Y = (const uint8_t*)p.sdr.p[0];
+  const V2 k255 = bc(1 / 255.0f), k8184 = bc(8184.0f);
+  const int o1 = BPP == 1 ? 0 : 1, o2 = BPP == 1 ? 0 : 2;
+  const V2 osr = bc(p.off_sdr[0]), osg = bc(p.off_sdr[o1]), osb = bc(p.off_sdr[o2]);
+  const V2 ohr = bc(p.off_hdr[0]), ohg = bc(p.off_hdr[o1]), ohb = bc(p.off_hdr[o2]);
+  auto load_tile = [&](int t, TileIn<BPP>& in) -> bool {
+    if (t >= ntiles) return false;
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int x = (tx * kBlockX + threadIdx.x) * 4;
+    const int y = ty * (kBlockY * 2) + threadIdx.y * 2;
+    if (x >= p.sdr.w || y >= p.sdr.h) return false;
+    in.x = x;
+    in.y = y;
+    in.yw[0] = __ldg((const unsigned*)(Y + (size_t)y * p.sdr.stride[0] + x));
+    in.yw[1] = __ldg((const unsigned*)(Y + (size_t)(y + 1) * p.sdr.stride[0] + x));
+    in.uu = __ldg((const uint16_t*)((const uint8_t*)p.sdr.p[1] + (size_t)(y >> 1) * p.sdr.stride[1] + (x >> 1)));
+    in.vv = __ldg((const uint16_t*)((const uint8_t*)p.sdr.p[2] + (size_t)(y >> 1) * p.sdr.stride[2] + (x >> 1)));
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const uint8_t* mrow = p.map + ((size_t)(y + r) * p.map_stride + x) * BPP;
+      if (BPP == 4) in.m4[r] = __ldg((const uint4*)mrow);
+      else if (BPP == 3) { in.m3[r][0] = __ldg((const unsigned*)mrow); in.m3[r][1] = __ldg((const unsigned*)mrow + 1); in.m3[r][2] = __ldg((const unsigned*)mrow + 2); }
+      else in.m3[r][0] = __ldg((const unsigned*)mrow);
+    }
+    return true;
+  };
+  auto compute_tile = [&](const TileIn<BPP>& in) {
+    const int x = in.x, y = in.y;
+    const unsigned* yw = in.yw;
+    const unsigned uu = in.uu, vv = in.vv;
+    const uint4* m4 = in.m4;
+    const unsigned (*m3)[3] = in.m3;
+    // chroma terms of p3YuvToRgb, shared by the 2x2 pixels under each chroma sample
+    float crv[2], gcbu[2], gcrv[2], cbu[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const float u = (float)((int)((uu >> (8 * k)) & 0xff) - 128) * (1 / 255.0f);
+      const float v = (float)((int)((vv >> (8 * k)) & 0xff) - 128) * (1 / 255.0f);
+      crv[k] = p.y2r[0] * v;
+      cbu[k] = p.y2r[1] * u;
+      gcbu[k] = p.y2r[2] * u;
+      gcrv[k] = p.y2r[3] * v;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      unsigned out[8];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {  // pixel pair (2k, 2k+1)
+        const V2 yf = vmul(v2((float)((yw[r] >> (16 * k)) & 0xff), (float)((yw[r] >> (16 * k + 8)) & 0xff)), k255, nz);
+        float y0, y1, t0, t1;
+        un(yf, y0, y1);
+        un(vsub(yf, bc(gcbu[k])), t0, t1);
+        // p3YuvToRgb with clampPixelFloat (saturate == clamp for the finite values that occur)
+        const V2 rg = v2(__saturatef(y0 + crv[k]), __saturatef(y1 + crv[k]));
+        const V2 gg = v2(__saturatef(t0 - gcrv[k]), __saturatef(t1 - gcrv[k]));
+        const V2 bg = v2(__saturatef(y0 + cbu[k]), __saturatef(y1 + cbu[k]));
+        unsigned ir0, ir1, ig0, ig1, ib0, ib1;
+        un(vtrunc_bits(vmul(rg, k8184, nz)), ir0, ir1);
+        un(vtrunc_bits(vmul(gg, k8184, nz)), ig0, ig1);
+        un(vtrunc_bits(vmul(bg, k8184, nz)), ib0, ib1);
+        V2 lr = v2(lds_off(sm.srgb2, ir0 & 0x1ffc), lds_off(sm.srgb2, ir1 & 0x1ffc));
+        V2 lg = v2(lds_off(sm.srgb2, ig0 & 0x1ffc), lds_off(sm.srgb2, ig1 & 0x1ffc));
+        V2 lb = v2(lds_off(sm.srgb2, ib0 & 0x1ffc), lds_off(sm.srgb2, ib1 & 0x1ffc));
+        if (GAMUT == 1) {
+          const V2 a = vadd(vadd(vmul(bc(p.gamut[0]), lr, nz), vmul(bc(p.gamut[1]), lg, nz)), vmul(bc(p.gamut[2]), lb, nz));
+          const V2 b = vadd(vadd(vmul(bc(p.gamut[3]), lr, nz), vmul(bc(p.gamut[4]), lg, nz)), vmul(bc(p.gamut[5]), lb, nz));
+          const V2 c = vadd(vadd(vmul(bc(p.gamut[6]), lr, nz), vmul(bc(p.gamut[7]), lg, nz)), vmul(bc(p.gamut[8]), lb, nz));
+          lr = a; lg = b; lb = c;
+        }
+        // gain factors: byte c of each pixel -> its 256-float table
+        unsigned q[2][3];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int i = 2 * k + e;
+          if (BPP == 4) {
+            const unsigned w = i == 0 ? m4[r].x : i == 1 ? m4[r].y : i == 2 ? m4[r].z : m4[r].w;
+            q[e][0] = (w << 2) & 0x3FCu; q[e][1] = (w >> 6) & 0x3FCu; q[e][2] = (w >> 14) & 0x3FCu;
+          } else if (BPP == 3) {
+            const unsigned long long lo = m3[r][0] | ((unsigned long long)m3[r][1] << 32);
+            const unsigned hi = m3[r][2];
+            auto byte_at = [&](int n) -> unsigned { return n < 8 ? (unsigned)((lo >> (8 * n)) & 0xff) : ((hi >> (8 * (n - 8))) & 0xff); };
+            q[e][0] = byte_at(3 * i) << 2; q[e][1] = byte_at(3 * i + 1) << 2; q[e][2] = byte_at(3 * i + 2) << 2;
+          } else {
+            q[e][0] = q[e][1] = q[e][2] = ((m3[r][0] >> (8 * i)) & 0xff) << 2;
+          }
+        }
+        const V2 fr = v2(lds_off(sm.gain, q[0][0]), lds_off(sm.gain, q[1][0]));
+        const V2 fg = BPP == 1 ? fr : v2(lds_off(sm.gain + 256, q[0][1]), lds_off(sm.gain + 256, q[1][1]));
+        const V2 fb = BPP == 1 ? fr : v2(lds_off(sm.gain + 512, q[0][2]), lds_off(sm.gain + 512, q[1][2]));
+        V2 hr = vsub(vmul(vadd(lr, osr), fr, nz), ohr);
+        V2 hg = vsub(vmul(vadd(lg, osg), fg, nz), ohg);
+        V2 hb = vsub(vmul(vadd(lb, osb), fb, nz), ohb);
+        if (GAMUT == 2) {
+          const V2 a = vadd(vadd(vmul(bc(p.gamut[0]), hr, nz), vmul(bc(p.gamut[1]), hg, nz)), vmul(bc(p.gamut[2]), hb, nz));
+          const V2 b = vadd(vadd(vmul(bc(p.gamut[3]), hr, nz), vmul(bc(p.gamut[4]), hg, nz)), vmul(bc(p.gamut[5]), hb, nz));
+          const V2 c = vadd(vadd(vmul(bc(p.gamut[6]), hr, nz), vmul(bc(p.gamut[7]), hg, nz)), vmul(bc(p.gamut[8]), hb, nz));
+          hr = a; hg = b; hb = c;
+        }
+        // clampPixelFloatLinear then floatToHalf, in the other order: the conversion is monotonic, so
+        // clamping the half bit patterns (as signed 16-bit integers: negative halves are negative,
+        // non-negative ones order like their bits) to [0, half(10000/203)] gives the same result with
+        // two packed integer min/max per pixel.  Negative inputs only ever clamp to 0, so forcing
+        // their last mantissa bit as well is harmless.
+        float r0, r1, g0, g1, b0, b1;
+        un(hr, r0, r1); un(hg, g0, g1); un(hb, b0, b1);
+        pack_half4_clamped(r0, g0, b0, out[4 * k], out[4 * k + 1]);
+        pack_half4_clamped(r1, g1, b1, out[4 * k + 2], out[4 * k + 3]);
+      }
+      uint2* d = (uint2*)p.dst + (size_t)(y + r) * p.dst_stride + x;
+      if (wide_store) {
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d), "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]),
+                     "r"(out[4]), "r"(out[5]), "r"(out[6]), "r"(out[7])
+                     : "memory");
+      } else {
+        ((uint4*)d)[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        ((uint4*)d)[1] = make_uint4(out[4], out[5], out[6], out[7]);
+      }
+    }
+  };
+  {
+    // software pipeline: the loads of the next tile are in flight while this one is computed
+    TileIn<BPP> cur;
+    int t = s_tile[0];
+    bool cv = load_tile(t, cur);
+#pragma unroll 1
+    for (int it = 0; t < ntiles; it++) {
+      const int tn = s_tile[(it + 1) & 3];
+      if (tid == 0) s_tile[(it + 2) & 3] = next_ticket();
+      TileIn<BPP> nx;
+      const bool nv = load_tile(tn, nx);
+      if (cv) compute_tile(cur);
+      cur = nx;
+      cv = nv;
+      t = tn;
+      __syncthreads();
+    }
+  }
+}
+
+template <int BPP>
+cudaError_t launch_lin1(const ApplyParams& p, const float* gain_u8, unsigned* sched, cudaStream_t s) {
+  const int tiles_x = (p.sdr.w / 4 + kBlockX - 1) / kBlockX, tiles_y = (p.sdr.h + kBlockY * 2 - 1) / (kBlockY * 2);
+  const int ntiles = tiles_x * tiles_y;
+  const int wide = (((size_t)p.dst & 31) == 0 && (p.dst_stride & 3) == 0) ? 1 : 0;
+  dim3 block(kBlockX, kBlockY);
+  const int g = p.gamut_identity ? 0 : (p.gamut_on_sdr ? 1 : 2);
+  // persistent grid = exactly the CTAs that are co-resident (a partial second wave would double the time)
+  static int resident[3] = {0, 0, 0};
+  if (!resident[g]) {
+    int per_sm = 0, dev = 0, sms = 0;
+    const void* fn = g == 0 ? (const void*)k_apply_lin1<BPP, 0> : g == 1 ? (const void*)k_apply_lin1<BPP, 1> : (const void*)k_apply_lin1<BPP, 2>;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlockX * kBlockY, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    resident[g] = per_sm * (sms > 0 ? sms : 148);
+  }
+  int ctas = resident[g];
+  if (ctas > ntiles) ctas = ntiles;
+  if (g == 0) k_apply_lin1<BPP, 0><<<ctas, block, 0, s>>>(p, gain_u8, tiles_x, ntiles, wide, kNegZero2, sched);
+  else if (g == 1) k_apply_lin1<BPP, 1><<<ctas, block, 0, s>>>(p, gain_u8, tiles_x, ntiles, wide, kNegZero2, sched);
+  else k_apply_lin1<BPP, 2><<<ctas, block, 0, s>>>(p, gain_u8, tiles_x, ntiles, wide, kNegZero2, sched);
+  return cudaGetLastError();
+}
+
 template <int BPP, bool S1, int G>
 cudaError_t launch_out(const ApplyParams& p, const float* gain_u8, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
   if (p.out_ct == CT_LINEAR) k_apply_fast<BPP, S1, G, 0><<<grid, block, smem, s>>>(p, gain_u8);
@@ -273,11 +505,18 @@ bool apply_fast_eligible(const ApplyParams& p) {
   return true;
 }
 
-// gain_u8: device pointer to the 3x256 composed table (scale 1 only)
+// gain_u8: device pointer to the 3x256 composed table (scale 1 only) followed by 4 zeroed words
+// (tile counter of the persistent kernel)
 cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaStream_t s) {
   dim3 block(kBlockX, kBlockY);
   dim3 grid((p.sdr.w / 4 + kBlockX - 1) / kBlockX, (p.sdr.h + kBlockY * kRowsPerThread - 1) / (kBlockY * kRowsPerThread));
   const bool s1 = p.scale_int == 1;
+  if (s1 && p.out_ct == CT_LINEAR) {
+    unsigned* sched = reinterpret_cast<unsigned*>(const_cast<float*>(gain_u8) + 768);  // zeroed with the upload
+    if (p.map_bpp == 4) return launch_lin1<4>(p, gain_u8, sched, s);
+    if (p.map_bpp == 3) return launch_lin1<3>(p, gain_u8, sched, s);
+    return launch_lin1<1>(p, gain_u8, sched, s);
+  }
   const size_t smem = sizeof(FastSmem) + (s1 ? 0 : sizeof(float) * 16 * p.scale_int * p.scale_int);
   if (p.map_bpp == 4) return s1 ? launch_gamut<4, true>(p, gain_u8, grid, block, smem, s) : launch_gamut<4, false>(p, gain_u8, grid, block, smem, s);
   if (p.map_bpp == 3) return s1 ? launch_gamut<3, true>(p, gain_u8, grid, block, smem, s) : launch_gamut<3, false>(p, gain_u8, grid, block, smem, s);

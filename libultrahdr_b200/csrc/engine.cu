@@ -301,9 +301,11 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
   static_assert(sizeof(GainmapMetadata) == sizeof(uhdr_gainmap_metadata_t), "layout");
   memcpy(&m, &md, sizeof m);
   const size_t idw_floats = integer && p.scale_int > 1 ? (size_t)16 * p.scale_int * p.scale_int : 0;
-  float* h_tab = (float*)ws.halloc(sizeof(float) * (3 * 1024 + idw_floats + 768));
-  float* d_tab = (float*)ws.dalloc(sizeof(float) * (3 * 1024 + idw_floats + 768));
+  const size_t tab_floats = 3 * 1024 + idw_floats + 768 + 4;  // + zeroed tile-counter words
+  float* h_tab = (float*)ws.halloc(sizeof(float) * tab_floats);
+  float* d_tab = (float*)ws.dalloc(sizeof(float) * tab_floats);
   if (!h_tab || !d_tab) return E_MEM;
+  memset(h_tab + tab_floats - 4, 0, 4 * sizeof(float));
   build_gain_lut(m, weight, h_tab);
   {  // scale-1 shortcut table: gain-map byte -> gain factor.  mapUintToFloat (b / 255.0f), IDW
      // weights {1,0,0,0} and GainLUT::getGainFactor's index (gamma 1) composed on the host
@@ -321,7 +323,7 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
     build_idw_tables(p.scale_int, idw);
     memcpy(h_tab + 3 * 1024, idw.data(), sizeof(float) * idw_floats);
   }
-  CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, sizeof(float) * (3 * 1024 + idw_floats + 768), cudaMemcpyHostToDevice, ws.stream()));
+  CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, sizeof(float) * tab_floats, cudaMemcpyHostToDevice, ws.stream()));
   p.gain_lut = d_tab;
   p.idw = d_tab + 3 * 1024;
   const bool single = metadata_single_channel(m);

@@ -16,11 +16,17 @@ import bench  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 gpu = T.Gpu()
-if what in ("apply", "all"):
+if what in ("apply", "apply_nat", "all"):
     W, H = 7680, 4320
-    sb = T.make_yuv420(W, H, "noise")
+    if what == "apply_nat":   # the bench's "natural" content: smooth + texture
+        _p, sb = bench.make_frame(W, H, 5)
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        g0 = 128 + 90 * np.sin(xx / 301.0) * np.cos(yy / 257.0) + np.random.RandomState(3).randn(H, W) * 2
+        gm = np.stack([g0, g0 * 0.9 + 10, g0 * 0.8 + 20, np.full_like(g0, 255)], -1).clip(0, 255).astype(np.uint8)
+    else:
+        sb = T.make_yuv420(W, H, "noise")
+        gm = np.random.RandomState(7).randint(0, 256, (H, W, 4)).astype(np.uint8)
     sdr, k2 = A.yuv420_image(sb, W, H, A.CG_BT709)
-    gm = np.random.RandomState(7).randint(0, 256, (H, W, 4)).astype(np.uint8)
     md = A.GainmapMetadata()
     for i, (mx, mn) in enumerate(((65.1, 4.9e-5), (845.9, 2.7e-3), (1283.8, 4.9e-5))):
         md.max_content_boost[i], md.min_content_boost[i], md.gamma[i] = mx, mn, 1.0
