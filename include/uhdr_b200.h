@@ -72,6 +72,13 @@ UHDR_EXTERN int uhdr_b200_jpeg_decode(const void* data, size_t size, int mode, u
 UHDR_EXTERN void uhdr_b200_set_kernel_timing(int on);
 UHDR_EXTERN int uhdr_b200_kernel_timing_report(char* buf, size_t cap, int reset);
 UHDR_EXTERN int uhdr_b200_enc_rearm(uhdr_codec_private_t* enc);
+/* Where JpegDecoderHelper's entropy decoding (libjpeg-turbo jdhuff.c behind jpegdecoderhelper.cpp:397-411)
+ * runs: 0 = automatic (device for scans of 64 KiB and more), 1 = host, 2 = device whenever the stream
+ * allows it.  Process-wide; returns the previous setting.  Results are identical either way. */
+UHDR_EXTERN int uhdr_b200_set_entropy_decoder(int mode);
+/* out[0] = scans entropy-decoded on the device so far, out[1] = scans the device decoder handed back to
+ * the host decoder, out[2] = relaxation rounds the last device decode needed */
+UHDR_EXTERN void uhdr_b200_entropy_decoder_stats(unsigned long long out[3]);
 /* diagnostic: out[i] = float(log2(double(in[i]))) exactly as the gain-map kernels evaluate computeGain's
  * log2 (gainmapmath.cpp:773-782); host pointers. */
 UHDR_EXTERN int uhdr_b200_probe_log2(const float* in, float* out, int n);

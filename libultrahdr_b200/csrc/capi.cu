@@ -456,7 +456,9 @@ UHDR_API uhdr_error_info_t uhdr_decode(uhdr_codec_private_t* dec) {
   if (h->init_rc) { h->status = err((uhdr_codec_err_t)h->init_rc, "%s", h->init_err.c_str()); return h->status; }
   const int w = h->info.width, ht = h->info.height;
   const size_t bpp = h->out_fmt == UHDR_IMG_FMT_64bppRGBAHalfFloat ? 8 : 4;
-  h->decoded.resize((size_t)w * ht * bpp);
+  // the pixel buffers come from the codec's pinned arena (allocated inside decode()): a zero-filled
+  // pageable vector of w*h*8 bytes would cost more than the whole decode
+  (void)bpp;
   memset(&h->decoded_desc, 0, sizeof h->decoded_desc);
   h->decoded_desc.fmt = (uhdr_img_fmt_t)h->out_fmt;
   h->decoded_desc.cg = UHDR_CG_UNSPECIFIED;
@@ -464,16 +466,10 @@ UHDR_API uhdr_error_info_t uhdr_decode(uhdr_codec_private_t* dec) {
   h->decoded_desc.range = UHDR_CR_UNSPECIFIED;
   h->decoded_desc.w = w;
   h->decoded_desc.h = ht;
-  h->decoded_desc.planes[0] = h->decoded.data();
+  h->decoded_desc.planes[0] = nullptr;
   h->decoded_desc.stride[0] = w;
-  JpegHeader gh;
-  size_t po, pl, go, gl;
-  split_jpegr(h->stream.data(), h->stream.size(), &po, &pl, &go, &gl);
-  jpeg_read_header(h->stream.data() + go, gl, &gh);
-  const int gch = gh.frame.ncomp == 1 ? 1 : 4;
-  h->gainmap.resize((size_t)h->info.gm_width * h->info.gm_height * gch);
   memset(&h->gainmap_desc, 0, sizeof h->gainmap_desc);
-  h->gainmap_desc.planes[0] = h->gainmap.data();
+  h->gainmap_desc.planes[0] = nullptr;
   h->gainmap_desc.stride[0] = h->info.gm_width;
   int rc = h->codec.decode(h->stream.data(), h->stream.size(), h->out_ct, h->out_fmt, h->max_boost, &h->decoded_desc,
                            &h->gainmap_desc, nullptr);
@@ -511,6 +507,12 @@ UHDR_API uhdr_error_info_t uhdr_add_effect_resize(uhdr_codec_private_t* c, int, 
 
 // ---- measurement hooks (include/uhdr_b200.h) -------------------------------------------------------
 UHDR_API void uhdr_b200_set_kernel_timing(int on) { set_kernel_timing(on != 0); }
+UHDR_API void uhdr_b200_entropy_decoder_stats(unsigned long long out[3]) { jpeg_entropy_decoder_stats(out); }
+UHDR_API int uhdr_b200_set_entropy_decoder(int mode) {
+  const int prev = jpeg_get_entropy_decoder();
+  jpeg_set_entropy_decoder(mode);
+  return prev;
+}
 UHDR_API int uhdr_b200_kernel_timing_report(char* buf, size_t cap, int reset) {
   const std::string r = kernel_timing_report(reset != 0);
   if (r.size() + 1 > cap) return -(int)r.size();

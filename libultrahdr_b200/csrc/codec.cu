@@ -169,13 +169,6 @@ int JpegRCodec::decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevI
   if (h->adobe_transform == 0 && f.ncomp == 3)
     return fail(E_UNSUPPORTED, "RGB (Adobe transform 0) JPEG input is not supported by the B200 decoder");
   if (mode == 1 && f.ncomp == 1) return fail(E_ERROR, "expected input color space to be JCS_YCbCr or JCS_RGB but got %d", 1);
-  int16_t* h_coefs[3] = {nullptr, nullptr, nullptr};
-  for (int c = 0; c < f.ncomp; c++) {
-    h_coefs[c] = (int16_t*)ws_.halloc(f.blocks(c) * 128);
-    if (!h_coefs[c]) return E_MEM;
-  }
-  rc = jpeg_host_decode_coefs(data, size, *h, h_coefs);
-  if (rc) return rc;
   memset(out, 0, sizeof *out);
   out->cg = out->ct = -1;
   out->range = UHDR_CR_FULL_RANGE;
@@ -189,8 +182,29 @@ int JpegRCodec::decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevI
     planes[c] = (uint8_t*)ws_.dalloc((size_t)strides[c] * f.comp[c].hblocks * 8);
     if (!planes[c]) return E_MEM;
   }
-  rc = jpeg_inverse_dev(ws_, *h, h_coefs, planes, strides);
-  if (rc) return rc;
+  // entropy decoding: on the device (huffdec.cu) for anything sizeable, else -- or when the device
+  // decoder declines the stream -- on the host
+  const int dec_mode = jpeg_get_entropy_decoder();
+  bool on_device = dec_mode == 2 || (dec_mode == 0 && size - h->scan_offset >= (64u << 10));
+  if (on_device) {
+    int16_t* d_coefs[3] = {nullptr, nullptr, nullptr};
+    rc = jpeg_entropy_decode_dev(ws_, data, size, *h, d_coefs);
+    if (rc == kHuffDecFallback) on_device = false;
+    else if (rc) return rc;
+    else rc = jpeg_idct_dev(ws_, *h, d_coefs, planes, strides);
+    if (on_device && rc) return rc;
+  }
+  if (!on_device) {
+    int16_t* h_coefs[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < f.ncomp; c++) {
+      h_coefs[c] = (int16_t*)ws_.halloc(f.blocks(c) * 128);
+      if (!h_coefs[c]) return E_MEM;
+    }
+    rc = jpeg_host_decode_coefs(data, size, *h, h_coefs);
+    if (rc) return rc;
+    rc = jpeg_inverse_dev(ws_, *h, h_coefs, planes, strides);
+    if (rc) return rc;
+  }
   if (mode == 1) {
     if (f.max_h != 1 || f.max_v != 1)
       return fail(E_UNSUPPORTED, "RGB output of chroma-subsampled JPEG (libjpeg fancy upsampling) is outside the B200 hot path");
@@ -278,10 +292,15 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   rc = iso_decode_metadata(blob.data() + 28, blob.size() - 28, &md);
   if (rc) return rc;
   if (md_out) *md_out = md;
-  if (gainmap_out && gainmap_out->planes[0]) {
+  if (gainmap_out) {
     gainmap_out->fmt = (uhdr_img_fmt_t)map.v.fmt;
     gainmap_out->w = map.v.w;
     gainmap_out->h = map.v.h;
+    if (!gainmap_out->planes[0]) {  // handle-owned result: pinned memory of this codec, valid until its next decode
+      gainmap_out->stride[0] = map.v.w;
+      gainmap_out->planes[0] = ws_.halloc((size_t)map.v.w * map.v.h * (map.v.fmt == F_Y400 ? 1 : 4));
+      if (!gainmap_out->planes[0]) return E_MEM;
+    }
     gainmap_out->cg = UHDR_CG_UNSPECIFIED;
     gainmap_out->ct = UHDR_CT_UNSPECIFIED;
     gainmap_out->range = UHDR_CR_FULL_RANGE;
@@ -296,6 +315,11 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   dest->cg = (uhdr_color_gamut_t)dst.cg;
   dest->ct = (uhdr_color_transfer_t)out_ct;
   dest->range = UHDR_CR_FULL_RANGE;
+  if (!dest->planes[0]) {  // handle-owned result (see above)
+    dest->stride[0] = sdr.v.w;
+    dest->planes[0] = ws_.halloc((size_t)sdr.v.w * sdr.v.h * (dest->fmt == UHDR_IMG_FMT_64bppRGBAHalfFloat ? 8 : 4));
+    if (!dest->planes[0]) return E_MEM;
+  }
   rc = download_image(ws_, dst, dest);
   if (rc) return rc;
   return ws_.sync();

@@ -92,6 +92,19 @@ int jpeg_host_decode_coefs(const uint8_t* data, size_t size, const JpegHeader& h
 // Enqueue H2D of coefficients + dequant/IDCT into device planes (stride = wblocks*8).
 int jpeg_inverse_dev(Workspace& ws, const JpegHeader& h, int16_t* const h_coefs[3],
                      uint8_t* d_planes[3], int plane_stride[3]);
+// Same, coefficients already on the device.
+int jpeg_idct_dev(Workspace& ws, const JpegHeader& h, int16_t* const d_coefs[3], uint8_t* d_planes[3], int plane_stride[3]);
+// Entropy decoding on the device (huffdec.cu): fills d_coefs[c] (allocated from the workspace) with
+// [block][64] natural-order coefficients.  Returns kHuffDecFallback when the stream is outside what
+// the parallel decoder handles (restart markers, no fixed point, inconsistent data): the caller then
+// runs jpeg_host_decode_coefs, which also produces the reference's error texts.
+constexpr int kHuffDecFallback = -1000;
+int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, const JpegHeader& h, int16_t* d_coefs[3]);
+// 0 = automatic (device for scans of at least 64 KiB), 1 = host, 2 = device whenever possible
+// [0] scans decoded on the device, [1] scans handed back to the host decoder, [2] relaxation rounds of the last one
+void jpeg_entropy_decoder_stats(unsigned long long out[3]);
+void jpeg_set_entropy_decoder(int mode);
+int jpeg_get_entropy_decoder();
 
 const char* jpeg_gainmap_comment();
 

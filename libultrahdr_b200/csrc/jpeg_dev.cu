@@ -1,4 +1,5 @@
 // Device orchestration of the JPEG block stage (see jpeg.h).
+#include <atomic>
 #include <cmath>
 #include <cstring>
 
@@ -71,17 +72,13 @@ int jpeg_fetch_coefs(Workspace& ws, JpegEncodeJob* job) {
   return E_OK;
 }
 
-int jpeg_inverse_dev(Workspace& ws, const JpegHeader& h, int16_t* const h_coefs[3], uint8_t* d_planes[3],
-                     int plane_stride[3]) {
+int jpeg_idct_dev(Workspace& ws, const JpegHeader& h, int16_t* const d_coefs[3], uint8_t* d_planes[3], int plane_stride[3]) {
   const JpegFrame& f = h.frame;
   for (int c = 0; c < f.ncomp; c++) {
     const JpegComp& k = f.comp[c];
-    int16_t* d = (int16_t*)ws.dalloc(f.blocks(c) * 128);
-    if (!d) return E_MEM;
-    CUDA_TRY(cudaMemcpyAsync(d, h_coefs[c], f.blocks(c) * 128, cudaMemcpyHostToDevice, ws.stream()));
     IdctPlaneParams p;
     memset(&p, 0, sizeof p);
-    p.coefs = d;
+    p.coefs = d_coefs[c];
     memcpy(p.q, f.qt[k.tq], sizeof p.q);
     p.wblocks = k.wblocks;
     p.hblocks = k.hblocks;
@@ -93,5 +90,23 @@ int jpeg_inverse_dev(Workspace& ws, const JpegHeader& h, int16_t* const h_coefs[
   }
   return E_OK;
 }
+
+int jpeg_inverse_dev(Workspace& ws, const JpegHeader& h, int16_t* const h_coefs[3], uint8_t* d_planes[3],
+                     int plane_stride[3]) {
+  const JpegFrame& f = h.frame;
+  int16_t* d_coefs[3] = {nullptr, nullptr, nullptr};
+  for (int c = 0; c < f.ncomp; c++) {
+    d_coefs[c] = (int16_t*)ws.dalloc(f.blocks(c) * 128);
+    if (!d_coefs[c]) return E_MEM;
+    CUDA_TRY(cudaMemcpyAsync(d_coefs[c], h_coefs[c], f.blocks(c) * 128, cudaMemcpyHostToDevice, ws.stream()));
+  }
+  return jpeg_idct_dev(ws, h, d_coefs, d_planes, plane_stride);
+}
+
+namespace {
+std::atomic<int> g_entropy_decoder{0};
+}
+void jpeg_set_entropy_decoder(int mode) { g_entropy_decoder.store(mode < 0 || mode > 2 ? 0 : mode); }
+int jpeg_get_entropy_decoder() { return g_entropy_decoder.load(); }
 
 }  // namespace uhdr_b200

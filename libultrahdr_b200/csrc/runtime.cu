@@ -80,8 +80,44 @@ int read_back_luts(float* host_out) {
 }
 
 // ---- arenas -------------------------------------------------------------------------------------
+// Blocks of released arenas are parked in a process-wide cache instead of going back to the driver:
+// the reference's usage pattern is create handle / run / release per image, and pinning a few
+// hundred MB of host memory (or cudaMalloc of as much HBM) costs far more than the decode itself.
+namespace {
+struct ParkedBlock { char* base; size_t size; int device; };
+std::mutex g_park_mu;
+std::vector<ParkedBlock> g_parked[2];              // [0] device memory, [1] pinned host memory
+size_t g_parked_bytes[2] = {0, 0};
+constexpr size_t kParkCap[2] = {(size_t)24 << 30, (size_t)8 << 30};
+
+char* take_parked(bool pinned, int device, size_t bytes, size_t* got) {
+  std::lock_guard<std::mutex> lk(g_park_mu);
+  auto& v = g_parked[pinned ? 1 : 0];
+  int best = -1;
+  for (int i = 0; i < (int)v.size(); i++) {
+    if (v[i].size < bytes || (!pinned && v[i].device != device)) continue;
+    if (best < 0 || v[i].size < v[best].size) best = i;
+  }
+  if (best < 0 || v[best].size > 4 * bytes + ((size_t)64 << 20)) return nullptr;  // do not burn a huge block on a small need
+  char* base = v[best].base;
+  *got = v[best].size;
+  g_parked_bytes[pinned ? 1 : 0] -= v[best].size;
+  v.erase(v.begin() + best);
+  return base;
+}
+bool park(bool pinned, int device, char* base, size_t size) {
+  std::lock_guard<std::mutex> lk(g_park_mu);
+  const int k = pinned ? 1 : 0;
+  if (g_parked_bytes[k] + size > kParkCap[k]) return false;
+  g_parked[k].push_back({base, size, device});
+  g_parked_bytes[k] += size;
+  return true;
+}
+}  // namespace
+
 Arena::~Arena() {
   for (auto& b : blocks_) {
+    if (park(pinned_, device_, b.base, b.size)) continue;
     if (pinned_) cudaFreeHost(b.base);
     else cudaFree(b.base);
   }
@@ -98,13 +134,16 @@ void* Arena::alloc(size_t bytes, size_t align) {
   const size_t min_block = pinned_ ? (size_t)32 << 20 : (size_t)64 << 20;
   size_t sz = bytes > min_block ? bytes : min_block;
   sz = (sz + 4095) / 4096 * 4096;
-  char* base = nullptr;
-  cudaError_t e = pinned_ ? cudaHostAlloc((void**)&base, sz, cudaHostAllocDefault)
-                          : cudaMalloc((void**)&base, sz);
-  if (e != cudaSuccess) {
-    fail(E_MEM, "%s of %zu bytes failed: %s", pinned_ ? "cudaHostAlloc" : "cudaMalloc", sz,
-         cudaGetErrorString(e));
-    return nullptr;
+  if (device_ < 0) cudaGetDevice(&device_);
+  char* base = take_parked(pinned_, device_, sz, &sz);
+  if (!base) {
+    cudaError_t e = pinned_ ? cudaHostAlloc((void**)&base, sz, cudaHostAllocPortable)
+                            : cudaMalloc((void**)&base, sz);
+    if (e != cudaSuccess) {
+      fail(E_MEM, "%s of %zu bytes failed: %s", pinned_ ? "cudaHostAlloc" : "cudaMalloc", sz,
+           cudaGetErrorString(e));
+      return nullptr;
+    }
   }
   blocks_.push_back({base, sz, bytes, 0});
   return base;

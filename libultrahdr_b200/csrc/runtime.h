@@ -62,6 +62,7 @@ class Arena {
   struct Block { char* base; size_t size, used, floor; };
   std::vector<Block> blocks_;
   bool pinned_;
+  int device_ = -1;  // device the blocks belong to (set at the first allocation)
 };
 
 class Workspace {
