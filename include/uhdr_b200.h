@@ -66,7 +66,7 @@ UHDR_EXTERN int uhdr_b200_jpeg_decode(const void* data, size_t size, int mode, u
                                       size_t cap);
 
 /* Measurement hooks.  Kernel timing brackets every kernel launch with CUDA events on the
- * launching stream and accumulates per-kernel totals ("name count total_ms" lines).
+ * launching stream and accumulates per-kernel totals ("name count total_ms min_ms max_ms" lines).
  * uhdr_b200_enc_rearm() makes a finished encoder handle runnable again while keeping the inputs
  * it uploaded at uhdr_enc_set_raw_image() time resident in HBM (streaming re-encode). */
 UHDR_EXTERN void uhdr_b200_set_kernel_timing(int on);

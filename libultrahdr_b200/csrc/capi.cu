@@ -421,8 +421,11 @@ UHDR_API uhdr_error_info_t uhdr_dec_probe(uhdr_codec_private_t* dec) {
     auto blk = [](std::vector<uint8_t>& v, uhdr_mem_block_t* b) { b->data = v.data(); b->data_sz = b->capacity = v.size(); };
     blk(h->info.exif, &h->exif_blk);
     blk(h->info.icc, &h->icc_blk);
-    blk(h->info.base_jpeg, &h->base_blk);
-    blk(h->info.gainmap_jpeg, &h->gm_blk);
+    // the compressed base / gain-map images are views into the handle's copy of the stream
+    h->base_blk.data = h->stream.data() + h->info.base_off;
+    h->base_blk.data_sz = h->base_blk.capacity = h->info.base_len;
+    h->gm_blk.data = h->stream.data() + h->info.gainmap_off;
+    h->gm_blk.data_sz = h->gm_blk.capacity = h->info.gainmap_len;
   }
   return h->probe_status;
 }
@@ -471,6 +474,7 @@ UHDR_API uhdr_error_info_t uhdr_decode(uhdr_codec_private_t* dec) {
   memset(&h->gainmap_desc, 0, sizeof h->gainmap_desc);
   h->gainmap_desc.planes[0] = nullptr;
   h->gainmap_desc.stride[0] = h->info.gm_width;
+  h->codec.set_lazy_gainmap(true);  // the map leaves HBM only if uhdr_get_decoded_gainmap_image() is called
   int rc = h->codec.decode(h->stream.data(), h->stream.size(), h->out_ct, h->out_fmt, h->max_boost, &h->decoded_desc,
                            &h->gainmap_desc, nullptr);
   h->status = from_rc(rc);
@@ -484,6 +488,10 @@ UHDR_API uhdr_raw_image_t* uhdr_get_decoded_image(uhdr_codec_private_t* dec) {
 UHDR_API uhdr_raw_image_t* uhdr_get_decoded_gainmap_image(uhdr_codec_private_t* dec) {
   Decoder* h = as<Decoder>(dec);
   if (!h || !h->sailed || h->status.error_code != UHDR_CODEC_OK) return nullptr;
+  if (!h->gainmap_desc.planes[0]) {
+    h->bind();
+    if (h->codec.fetch_gainmap(&h->gainmap_desc) != E_OK) return nullptr;
+  }
   return &h->gainmap_desc;
 }
 UHDR_API void uhdr_reset_decoder(uhdr_codec_private_t* dec) {

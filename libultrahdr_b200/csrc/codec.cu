@@ -251,8 +251,8 @@ int JpegRCodec::probe(const uint8_t* data, size_t size, DecodedInfo* info) {
   info->height = ph.frame.height;
   info->gm_width = gh.frame.width;
   info->gm_height = gh.frame.height;
-  info->base_jpeg.assign(data + po, data + po + pl);
-  info->gainmap_jpeg.assign(data + go, data + go + gl);
+  info->base_off = po; info->base_len = pl;
+  info->gainmap_off = go; info->gainmap_len = gl;
   grab_marker(data + po, ph, 0xE1, "Exif\0\0", 6, &info->exif);
   grab_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12, &info->icc);
   std::vector<uint8_t> iso;
@@ -292,20 +292,27 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   rc = iso_decode_metadata(blob.data() + 28, blob.size() - 28, &md);
   if (rc) return rc;
   if (md_out) *md_out = md;
+  map_pending_ = false;
   if (gainmap_out) {
     gainmap_out->fmt = (uhdr_img_fmt_t)map.v.fmt;
     gainmap_out->w = map.v.w;
     gainmap_out->h = map.v.h;
-    if (!gainmap_out->planes[0]) {  // handle-owned result: pinned memory of this codec, valid until its next decode
-      gainmap_out->stride[0] = map.v.w;
-      gainmap_out->planes[0] = ws_.halloc((size_t)map.v.w * map.v.h * (map.v.fmt == F_Y400 ? 1 : 4));
-      if (!gainmap_out->planes[0]) return E_MEM;
-    }
     gainmap_out->cg = UHDR_CG_UNSPECIFIED;
     gainmap_out->ct = UHDR_CT_UNSPECIFIED;
     gainmap_out->range = UHDR_CR_FULL_RANGE;
-    rc = download_image(ws_, map, gainmap_out);
-    if (rc) return rc;
+    if (!gainmap_out->planes[0] && lazy_gainmap_) {
+      gainmap_out->stride[0] = map.v.w;
+      last_map_ = map;
+      map_pending_ = true;
+    } else {
+      if (!gainmap_out->planes[0]) {  // handle-owned result: pinned memory of this codec, valid until its next decode
+        gainmap_out->stride[0] = map.v.w;
+        gainmap_out->planes[0] = ws_.halloc((size_t)map.v.w * map.v.h * (map.v.fmt == F_Y400 ? 1 : 4));
+        if (!gainmap_out->planes[0]) return E_MEM;
+      }
+      rc = download_image(ws_, map, gainmap_out);
+      if (rc) return rc;
+    }
   }
   DevImage dst;
   rc = alloc_dev_image(ws_, dest->fmt, sdr.v.w, sdr.v.h, 64, &dst);
@@ -322,6 +329,16 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   }
   rc = download_image(ws_, dst, dest);
   if (rc) return rc;
+  return ws_.sync();
+}
+
+int JpegRCodec::fetch_gainmap(uhdr_raw_image_t* gainmap_out) {
+  if (!map_pending_) return E_OK;
+  gainmap_out->planes[0] = ws_.halloc((size_t)last_map_.v.w * last_map_.v.h * (last_map_.v.fmt == F_Y400 ? 1 : 4));
+  if (!gainmap_out->planes[0]) return E_MEM;
+  int rc = download_image(ws_, last_map_, gainmap_out);
+  if (rc) return rc;
+  map_pending_ = false;
   return ws_.sync();
 }
 

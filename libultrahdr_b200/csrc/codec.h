@@ -13,7 +13,8 @@ namespace uhdr_b200 {
 
 struct DecodedInfo {
   int width = 0, height = 0, gm_width = 0, gm_height = 0;
-  std::vector<uint8_t> exif, icc, base_jpeg, gainmap_jpeg;
+  std::vector<uint8_t> exif, icc;
+  size_t base_off = 0, base_len = 0, gainmap_off = 0, gainmap_len = 0;  // the two JPEGs inside the probed stream
   uhdr_gainmap_metadata_t metadata{};
   bool has_metadata = false;
 };
@@ -39,11 +40,19 @@ class JpegRCodec {
   int decode(const uint8_t* data, size_t size, int out_ct, int out_fmt, float max_display_boost,
              uhdr_raw_image_t* dest, uhdr_raw_image_t* gainmap_out, uhdr_gainmap_metadata_t* md_out);
 
+  // With gainmap_out->planes[0] == nullptr and lazy_gainmap set, decode() only fills the descriptor's
+  // geometry and keeps the map in HBM; fetch_gainmap() copies it out when somebody asks for it
+  // (uhdr_get_decoded_gainmap_image).  Valid until the next decode() on this codec.
+  void set_lazy_gainmap(bool on) { lazy_gainmap_ = on; }
+  int fetch_gainmap(uhdr_raw_image_t* gainmap_out);
+
   // JpegDecoderHelper::decompressImage equivalent producing a device image
   int decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* hdr);
 
  private:
   Workspace ws_;
+  bool lazy_gainmap_ = false, map_pending_ = false;
+  DevImage last_map_{};
 };
 
 bool gpu_entropy_available();

@@ -448,15 +448,18 @@ int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, con
   const unsigned grid = (nseq + 127) / 128;
   ws.t_begin("huffdec_sync");
   k_hd_init<<<(nseq + 255) / 256, 256, 0, s>>>(d_out, d_used, d_cnt, nseq);
-  int rounds = 0;
+  int rounds = 0, first_quiet = 0;
   bool converged = false;
   while (!converged && rounds < kMaxRounds) {
     for (int r = 0; r < kRoundsPerBatch; r++) k_hd_sync<<<grid, 128, 0, s>>>(d_bits, d_out, d_used, d_cnt, d_flags + rounds + r, d_hs);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h_flags + rounds, d_flags + rounds, sizeof(unsigned) * kRoundsPerBatch, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    for (int r = 0; r < kRoundsPerBatch; r++)
-      if (!h_flags[rounds + r]) converged = true;
+    for (int r = 0; r < kRoundsPerBatch && !converged; r++)
+      if (!h_flags[rounds + r]) {
+        converged = true;
+        first_quiet = rounds + r + 1;
+      }
     rounds += kRoundsPerBatch;
   }
   ws.t_end();
@@ -496,7 +499,7 @@ int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, con
   CUDA_TRY(cudaStreamSynchronize(s));
   if (h_flags[1] || h_flags[0] < hf.total_blocks) return declined();  // let the host decoder produce the diagnosis
   g_hd_done.fetch_add(1);
-  g_hd_rounds.store((unsigned long long)rounds);
+  g_hd_rounds.store((unsigned long long)first_quiet);
   return E_OK;
 }
 

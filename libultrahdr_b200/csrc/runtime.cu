@@ -183,7 +183,8 @@ int Workspace::sync() {
 // ---- kernel timing ------------------------------------------------------------------------------
 static std::atomic<bool> g_timing{false};
 static std::mutex g_timing_mu;
-static std::map<std::string, std::pair<unsigned long long, double>> g_timing_acc;
+struct TimingAcc { unsigned long long n = 0; double total = 0, mn = 1e30, mx = 0; };
+static std::map<std::string, TimingAcc> g_timing_acc;
 void set_kernel_timing(bool on) { g_timing = on; }
 bool kernel_timing_enabled() { return g_timing; }
 std::string kernel_timing_report(bool reset) {
@@ -191,7 +192,7 @@ std::string kernel_timing_report(bool reset) {
   std::string out;
   char line[256];
   for (auto& kv : g_timing_acc) {
-    snprintf(line, sizeof line, "%s %llu %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    snprintf(line, sizeof line, "%s %llu %.6f %.6f %.6f\n", kv.first.c_str(), kv.second.n, kv.second.total, kv.second.mn, kv.second.mx);
     out += line;
   }
   if (reset) g_timing_acc.clear();
@@ -223,8 +224,10 @@ void Workspace::t_collect() {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
       auto& acc = g_timing_acc[s.name];
-      acc.first++;
-      acc.second += ms;
+      acc.n++;
+      acc.total += ms;
+      if (ms < acc.mn) acc.mn = ms;
+      if (ms > acc.mx) acc.mx = ms;
     }
     ev_pool_.push_back(s.a);
     ev_pool_.push_back(s.b);
