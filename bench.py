@@ -186,9 +186,9 @@ ALG_BYTES_PER_PX = {
     "tonemap": 4.5,
     "apply_gainmap": 13.5,              # YUV420 1.5 + RGBA8888 map 4 read, RGBA-F16 8 written
     "fdct_quant": (4.5 + 9.0) / 2,      # avg of the two launches: 4:2:0 image 1.5 in + 3 out; RGB map 3 in + 6 out
-    "huff_blocks": (3.0 + 6.0) / 2,     # coefficient read (2 B/sample); scratch/stream writes are O(stream size)
+    "huff_encode": (3.0 + 6.0) / 2,     # coefficient read (2 B/sample); stream writes are O(stream size)
 }
-DATA_KERNELS = ("gainmap_pass1", "gainmap_affine", "fdct_quant", "huff_blocks", "yuv_convert")
+DATA_KERNELS = ("gainmap_pass1", "gainmap_affine", "fdct_quant", "huff_encode", "yuv_convert")
 
 
 def load_traffic():

@@ -15,6 +15,7 @@
 #include <cuda_fp16.h>
 
 #include "kernels.cuh"
+#include "packed_f32.cuh"
 #include "powf_glibc.cuh"
 #include "tables.h"
 
@@ -255,18 +256,6 @@ __global__ void __launch_bounds__(kBlockX* kBlockY) k_apply_fast(const ApplyPara
 // The -0 of the product form arrives as a kernel argument: with a literal the assembler reduces
 // the form to a multiply and then contracts it into a following add even though both carry .rn
 // (observed with ptxas 12.9), which would round once where the reference rounds twice.
-struct V2 { unsigned long long v; };
-__device__ __forceinline__ V2 v2(float a, float b) { V2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ V2 bc(float a) { return v2(a, a); }
-__device__ __forceinline__ void un(V2 a, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); }
-__device__ __forceinline__ void un(V2 a, unsigned& x, unsigned& y) { asm("mov.b64 {%0, %1}, %2;" : "=r"(x), "=r"(y) : "l"(a.v)); }
-__device__ __forceinline__ V2 vmul(V2 a, V2 b, unsigned long long nz) { V2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(nz)); return r; }
-constexpr unsigned long long kNegZero2 = 0x8000000080000000ULL;
-__device__ __forceinline__ V2 vadd(V2 a, V2 b) { V2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(0x3f8000003f800000ULL), "l"(b.v)); return r; }
-__device__ __forceinline__ V2 vsub(V2 a, V2 b) { V2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(b.v), "l"(0xbf800000bf800000ULL), "l"(a.v)); return r; }
-// trunc() of two non-negative values < 2^23, left in the mantissas (add 2^23 toward zero)
-__device__ __forceinline__ V2 vtrunc_bits(V2 a) { V2 r; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(0x3f8000003f800000ULL), "l"(0x4b0000004b000000ULL)); return r; }
-
 struct Lin1Smem {
   float srgb2[2048];
   float gain[768];
@@ -508,6 +497,7 @@ bool apply_fast_eligible(const ApplyParams& p) {
 // gain_u8: device pointer to the 3x256 composed table (scale 1 only) followed by 4 zeroed words
 // (tile counter of the persistent kernel)
 cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaStream_t s) {
+  count_launches(1);
   dim3 block(kBlockX, kBlockY);
   dim3 grid((p.sdr.w / 4 + kBlockX - 1) / kBlockX, (p.sdr.h + kBlockY * kRowsPerThread - 1) / (kBlockY * kRowsPerThread));
   const bool s1 = p.scale_int == 1;

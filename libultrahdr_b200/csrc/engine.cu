@@ -179,9 +179,12 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
     p.log2_min = std::log2(p.min_boost);  // float overloads: jpegr.cpp has `using namespace std`
     p.log2_max = std::log2(p.max_boost);
     p.gamma = cfg.gamma;
-    if (gainmap_fast_eligible(p, true))
-      TIMED(ws, "gainmap_onepass", launch_gainmap_fast(p, true, ws.stream()));
-    else
+    if (gainmap_fast_eligible(p, true)) {
+      unsigned* sched = (unsigned*)ws.dalloc(64);
+      if (!sched) return E_MEM;
+      CUDA_TRY(cudaMemsetAsync(sched, 0, 4, ws.stream()));
+      TIMED(ws, "gainmap_onepass", launch_gainmap_fast(p, true, sched, ws.stream()));
+    } else
       TIMED(ws, "gainmap_onepass", launch_gainmap_onepass(p, ws.stream()));
     return E_OK;
   }
@@ -192,7 +195,7 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   if (!p.gains || !p.minmax || !d_minmax_f || !job->h_minmax) return E_MEM;
   CUDA_TRY(launch_gainmap_init_minmax(p.minmax, ws.stream()));
   if (gainmap_fast_eligible(p, false))
-    TIMED(ws, "gainmap_pass1", launch_gainmap_fast(p, false, ws.stream()));
+    TIMED(ws, "gainmap_pass1", launch_gainmap_fast(p, false, p.minmax + 8, ws.stream()));  // word 8: tile tickets, zeroed by init_minmax
   else
     TIMED(ws, "gainmap_pass1", launch_gainmap_pass1(p, ws.stream()));
   GainmapFinalizeParams f;

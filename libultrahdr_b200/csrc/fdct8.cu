@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
 }  // namespace
 
 cudaError_t launch_fdct8(const Fdct8Params& P, cudaStream_t s) {
+  count_launches(1);
   int maxw = 0, maxh = 0;
   for (int i = 0; i < P.nplanes; i++) {
     maxw = P.plane[i].wblocks > maxw ? P.plane[i].wblocks : maxw;

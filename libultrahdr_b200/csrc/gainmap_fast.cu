@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "kernels.cuh"
+#include "packed_f32.cuh"
 #include "powf_glibc.cuh"
 #include "runtime.h"
 #include "tables.h"
@@ -83,24 +84,52 @@ __device__ __forceinline__ float fetch2(const float* t, float x, float scale8) {
   return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(t) + off);
 }
 
+// a / b per lane, same steps as div_pos (na = -b is formed by the caller's packed multiply by -1)
+__device__ __forceinline__ V2 div_pos2(V2 a, V2 b, unsigned long long nz) {
+  float b0, b1, r0, r1;
+  un(b, b0, b1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(b1));
+  const V2 nb = vmul(b, bc(-1.0f), nz);
+  V2 r = v2(r0, r1);
+  const V2 e = vfma(nb, r, bc(1.0f));
+  r = vfma(r, e, r);
+  const V2 q = vmul(a, r, nz);
+  const V2 rem = vfma(nb, q, a);
+  return vfma(r, rem, q);
+}
+
+__device__ __forceinline__ float fetch_off(const float* t, unsigned mant) {  // mant: mantissa bits holding trunc(x*8(N-1))
+  return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(t) + (mant & 0x7ffffc));
+}
+
 template <bool ONEPASS, int NCH, int GAMUT /*0 none, 1 on sdr, 2 on hdr*/, bool LIMITED>
-__global__ void __launch_bounds__(256, 3) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g) {
+__global__ void __launch_bounds__(256, 3) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g, const int tiles_x,
+                                                         const int ntiles, unsigned* __restrict__ sched, const unsigned long long nz) {
   extern __shared__ double2 smem_d[];
   GmSmem& sm = *reinterpret_cast<GmSmem*>(smem_d);
+  __shared__ int s_tile[2];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
   for (int i = tid; i < 128; i += nt) sm.log2tab[i] = make_double2(log2tab_g[i], log2tab_g[128 + i]);
   for (int i = tid; i < 2048; i += nt) sm.srgb2[i] = __ldg(p.luts + kLutSrgbInv + min((i + 1) >> 1, 1023));
   const float* hsrc = p.luts + (p.hdr_ct == CT_HLG ? kLutHlgInvOotf : kLutPqInv);
   for (int i = tid; i < 8192; i += nt) sm.hdr2[i] = __ldg(hsrc + min((i + 1) >> 1, 4095));
+  // persistent CTAs; 256x8-pixel tiles handed out through a ticket counter (zeroed by the caller)
+  if (tid == 0) s_tile[0] = (int)atomicAdd(sched, 1u);
   __syncthreads();
 
   float mn[3] = {127.0f, 127.0f, 127.0f}, mx[3] = {-128.0f, -128.0f, -128.0f};
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int ybase = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
-  const int ystep = gridDim.y * blockDim.y * 2;
-  if (x < p.map_w) {
+  const V2 k8184 = bc(8184.0f), k32760 = bc(32760.0f), keps = bc(1e-7f);
+  const V2 snits = bc(p.sdr_nits), hnits = bc(p.hdr_nits);
 #pragma unroll 1
-    for (int y = ybase; y < p.map_h; y += ystep) {
+  for (int it = 0;; it++) {
+    const int t = s_tile[it & 1];
+    if (t >= ntiles) break;
+    if (tid == 0) s_tile[(it + 1) & 1] = (int)atomicAdd(sched, 1u);
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int x = (tx * 64 + threadIdx.x) * 4;
+    const int y = (ty * 4 + threadIdx.y) * 2;
+    if (x < p.map_w && y < p.map_h) {
       // ---- loads: 4x2 luma of both images, 2 chroma pairs each
       const uint16_t* HY = (const uint16_t*)p.hdr.p[0];
       const uint2 hy0 = __ldg((const uint2*)(HY + (size_t)y * p.hdr.stride[0] + x));
@@ -139,59 +168,87 @@ __global__ void __launch_bounds__(256, 3) k_gainmap_fast(const GainmapGenParams 
         float gout[12];
         unsigned bout[3] = {0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int k = i >> 1;
+        for (int k = 0; k < 2; k++) {  // pixel pair (2k, 2k+1): same chroma sample, packed arithmetic
           // sdr: getYuv420Pixel -> yuvToRgb -> srgbInvOetfLUT [-> gamut] -> clipNegatives
-          const float syf = (float)((syw >> (8 * i)) & 0xff) * (1 / 255.0f);
-          float sr = fetch2(sm.srgb2, __saturatef(syf + s_crv[k]), 8184.0f);
-          float sg = fetch2(sm.srgb2, __saturatef(syf - s_gcbu[k] - s_gcrv[k]), 8184.0f);
-          float sb = fetch2(sm.srgb2, __saturatef(syf + s_cbu[k]), 8184.0f);
+          const V2 syf = vmul(v2((float)((syw >> (16 * k)) & 0xff), (float)((syw >> (16 * k + 8)) & 0xff)), bc(1 / 255.0f), nz);
+          float a0, a1, t0, t1;
+          un(syf, a0, a1);
+          un(vsub(syf, bc(s_gcbu[k])), t0, t1);
+          unsigned i0, i1, j0, j1, l0, l1;
+          un(vtrunc_bits(vmul(v2(__saturatef(a0 + s_crv[k]), __saturatef(a1 + s_crv[k])), k8184, nz)), i0, i1);
+          un(vtrunc_bits(vmul(v2(__saturatef(t0 - s_gcrv[k]), __saturatef(t1 - s_gcrv[k])), k8184, nz)), j0, j1);
+          un(vtrunc_bits(vmul(v2(__saturatef(a0 + s_cbu[k]), __saturatef(a1 + s_cbu[k])), k8184, nz)), l0, l1);
+          V2 sr = v2(fetch_off(sm.srgb2, i0), fetch_off(sm.srgb2, i1));
+          V2 sg = v2(fetch_off(sm.srgb2, j0), fetch_off(sm.srgb2, j1));
+          V2 sb = v2(fetch_off(sm.srgb2, l0), fetch_off(sm.srgb2, l1));
           // hdr: getP010Pixel -> yuvToRgb -> invOETF(+OOTF) LUT [-> gamut] -> clipNegatives
-          const unsigned hw = (i < 2) ? hyw.x : hyw.y;
-          const int y10 = (int)(((hw >> (16 * (i & 1))) & 0xffff) >> 6);
-          const float hyf = LIMITED ? (float)(y10 - 64) * (1 / 876.0f) : (float)y10 / 1023.0f;
-          float hr = fetch2(sm.hdr2, __saturatef(hyf + h_crv[k]), 32760.0f);
-          float hg = fetch2(sm.hdr2, __saturatef(hyf - h_gcbu[k] - h_gcrv[k]), 32760.0f);
-          float hb = fetch2(sm.hdr2, __saturatef(hyf + h_cbu[k]), 32760.0f);
-          if (GAMUT == 1) {
-            const float a = p.gamut[0] * sr + p.gamut[1] * sg + p.gamut[2] * sb;
-            const float b = p.gamut[3] * sr + p.gamut[4] * sg + p.gamut[5] * sb;
-            const float c = p.gamut[6] * sr + p.gamut[7] * sg + p.gamut[8] * sb;
-            sr = fmaxf(a, 0.0f); sg = fmaxf(b, 0.0f); sb = fmaxf(c, 0.0f);
-          } else if (GAMUT == 2) {
-            const float a = p.gamut[0] * hr + p.gamut[1] * hg + p.gamut[2] * hb;
-            const float b = p.gamut[3] * hr + p.gamut[4] * hg + p.gamut[5] * hb;
-            const float c = p.gamut[6] * hr + p.gamut[7] * hg + p.gamut[8] * hb;
-            hr = fmaxf(a, 0.0f); hg = fmaxf(b, 0.0f); hb = fmaxf(c, 0.0f);
+          const unsigned hw = k ? hyw.y : hyw.x;
+          const int ya = (int)((hw & 0xffff) >> 6), yb = (int)(hw >> 22);
+          V2 hyf;
+          if (LIMITED) hyf = vmul(v2((float)(ya - 64), (float)(yb - 64)), bc(1 / 876.0f), nz);
+          else hyf = v2((float)ya / 1023.0f, (float)yb / 1023.0f);
+          un(hyf, a0, a1);
+          un(vsub(hyf, bc(h_gcbu[k])), t0, t1);
+          un(vtrunc_bits(vmul(v2(__saturatef(a0 + h_crv[k]), __saturatef(a1 + h_crv[k])), k32760, nz)), i0, i1);
+          un(vtrunc_bits(vmul(v2(__saturatef(t0 - h_gcrv[k]), __saturatef(t1 - h_gcrv[k])), k32760, nz)), j0, j1);
+          un(vtrunc_bits(vmul(v2(__saturatef(a0 + h_cbu[k]), __saturatef(a1 + h_cbu[k])), k32760, nz)), l0, l1);
+          V2 hr = v2(fetch_off(sm.hdr2, i0), fetch_off(sm.hdr2, i1));
+          V2 hg = v2(fetch_off(sm.hdr2, j0), fetch_off(sm.hdr2, j1));
+          V2 hb = v2(fetch_off(sm.hdr2, l0), fetch_off(sm.hdr2, l1));
+          if (GAMUT != 0) {
+            V2& xr = GAMUT == 1 ? sr : hr;
+            V2& xg = GAMUT == 1 ? sg : hg;
+            V2& xb = GAMUT == 1 ? sb : hb;
+            const V2 a = vadd(vadd(vmul(bc(p.gamut[0]), xr, nz), vmul(bc(p.gamut[1]), xg, nz)), vmul(bc(p.gamut[2]), xb, nz));
+            const V2 b = vadd(vadd(vmul(bc(p.gamut[3]), xr, nz), vmul(bc(p.gamut[4]), xg, nz)), vmul(bc(p.gamut[5]), xb, nz));
+            const V2 c = vadd(vadd(vmul(bc(p.gamut[6]), xr, nz), vmul(bc(p.gamut[7]), xg, nz)), vmul(bc(p.gamut[8]), xb, nz));
+            float f0, f1;
+            un(a, f0, f1); xr = v2(fmaxf(f0, 0.0f), fmaxf(f1, 0.0f));
+            un(b, f0, f1); xg = v2(fmaxf(f0, 0.0f), fmaxf(f1, 0.0f));
+            un(c, f0, f1); xb = v2(fmaxf(f0, 0.0f), fmaxf(f1, 0.0f));
           }
-          float sv3[3], hv3[3];
+          V2 sv3[3], hv3[3];
           if (NCH == 3) {
-            sv3[0] = sr * p.sdr_nits; sv3[1] = sg * p.sdr_nits; sv3[2] = sb * p.sdr_nits;
-            hv3[0] = hr * p.hdr_nits; hv3[1] = hg * p.hdr_nits; hv3[2] = hb * p.hdr_nits;
+            sv3[0] = vmul(sr, snits, nz); sv3[1] = vmul(sg, snits, nz); sv3[2] = vmul(sb, snits, nz);
+            hv3[0] = vmul(hr, hnits, nz); hv3[1] = vmul(hg, hnits, nz); hv3[2] = vmul(hb, hnits, nz);
           } else if (p.use_luminance) {
-            sv3[0] = (p.lum[0] * sr + p.lum[1] * sg + p.lum[2] * sb) * p.sdr_nits;
-            hv3[0] = (p.lum[0] * hr + p.lum[1] * hg + p.lum[2] * hb) * p.hdr_nits;
+            sv3[0] = vmul(vadd(vadd(vmul(bc(p.lum[0]), sr, nz), vmul(bc(p.lum[1]), sg, nz)), vmul(bc(p.lum[2]), sb, nz)), snits, nz);
+            hv3[0] = vmul(vadd(vadd(vmul(bc(p.lum[0]), hr, nz), vmul(bc(p.lum[1]), hg, nz)), vmul(bc(p.lum[2]), hb, nz)), hnits, nz);
           } else {
-            sv3[0] = fmaxf(sr, fmaxf(sg, sb)) * p.sdr_nits;
-            hv3[0] = fmaxf(hr, fmaxf(hg, hb)) * p.hdr_nits;
+            float r0, r1, g0, g1, b0, b1;
+            un(sr, r0, r1); un(sg, g0, g1); un(sb, b0, b1);
+            sv3[0] = vmul(v2(fmaxf(r0, fmaxf(g0, b0)), fmaxf(r1, fmaxf(g1, b1))), snits, nz);
+            un(hr, r0, r1); un(hg, g0, g1); un(hb, b0, b1);
+            hv3[0] = vmul(v2(fmaxf(r0, fmaxf(g0, b0)), fmaxf(r1, fmaxf(g1, b1))), hnits, nz);
           }
 #pragma unroll
           for (int c = 0; c < NCH; c++) {
+            float s0, s1, q0, q1;
+            un(sv3[c], s0, s1);
             if (ONEPASS) {  // encodeGain gainmapmath.cpp:758-771 (gamma 1: powf(x, 1) == x)
-              float gain = 1.0f;
-              if (sv3[c] > 0.0f) gain = div_pos(hv3[c], sv3[c]);
-              if (gain < p.min_boost) gain = p.min_boost;
-              if (gain > p.max_boost) gain = p.max_boost;
-              const float gn = (float)((log2_core(gain, sm.log2tab) - (double)p.log2_min) / (double)(p.log2_max - p.log2_min));
-              const unsigned code = (unsigned)__float2int_rz(gn * 255.0f) & 0xff;
-              const int bi = i * NCH + c;
-              bout[bi >> 2] |= code << (8 * (bi & 3));
+              float h0, h1;
+              un(hv3[c], h0, h1);
+              const float hv2[2] = {h0, h1}, sv2[2] = {s0, s1};
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                float gain = 1.0f;
+                if (sv2[e] > 0.0f) gain = div_pos(hv2[e], sv2[e]);
+                if (gain < p.min_boost) gain = p.min_boost;
+                if (gain > p.max_boost) gain = p.max_boost;
+                const float gn = (float)((log2_core(gain, sm.log2tab) - (double)p.log2_min) / (double)(p.log2_max - p.log2_min));
+                const unsigned code = (unsigned)__float2int_rz(gn * 255.0f) & 0xff;
+                const int bi = (2 * k + e) * NCH + c;
+                bout[bi >> 2] |= code << (8 * (bi & 3));
+              }
             } else {        // computeGain :773-782
-              float g = (float)log2_core(div_pos(hv3[c] + 1e-7f, sv3[c] + 1e-7f), sm.log2tab);
-              if (sv3[c] < 2.f / 255.0f) g = fminf(g, 2.3f);
-              gout[i * NCH + c] = g;
-              mn[c] = fminf(mn[c], g);
-              mx[c] = fmaxf(mx[c], g);
+              un(div_pos2(vadd(hv3[c], keps), vadd(sv3[c], keps), nz), q0, q1);
+              float g0 = (float)log2_core(q0, sm.log2tab), g1 = (float)log2_core(q1, sm.log2tab);
+              if (s0 < 2.f / 255.0f) g0 = fminf(g0, 2.3f);
+              if (s1 < 2.f / 255.0f) g1 = fminf(g1, 2.3f);
+              gout[(2 * k) * NCH + c] = g0;
+              gout[(2 * k + 1) * NCH + c] = g1;
+              mn[c] = fminf(mn[c], fminf(g0, g1));
+              mx[c] = fmaxf(mx[c], fmaxf(g0, g1));
             }
           }
         }
@@ -212,6 +269,7 @@ __global__ void __launch_bounds__(256, 3) k_gainmap_fast(const GainmapGenParams 
         }
       }
     }
+    __syncthreads();
   }
   if (!ONEPASS) {
     // same order-independent reduction as k_gainmap_pass1
@@ -315,18 +373,43 @@ int log2_table_dev(const double** out) {
   return E_OK;
 }
 
-template <bool ONEPASS, int NCH, int GAMUT>
-cudaError_t launch_range(const GainmapGenParams& p, const double* tab, dim3 g, dim3 b, size_t sm, cudaStream_t s) {
-  if (p.hdr.full_range) k_gainmap_fast<ONEPASS, NCH, GAMUT, false><<<g, b, sm, s>>>(p, tab);
-  else k_gainmap_fast<ONEPASS, NCH, GAMUT, true><<<g, b, sm, s>>>(p, tab);
+struct FastLaunch {
+  const double* tab;
+  int tiles_x, ntiles;
+  unsigned* sched;
+  size_t smem;
+  cudaStream_t s;
+};
+template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED>
+cudaError_t launch_kernel(const GainmapGenParams& p, const FastLaunch& L) {
+  // persistent grid = the CTAs that are co-resident (asked once per instantiation and device)
+  static int resident[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto fn = k_gainmap_fast<ONEPASS, NCH, GAMUT, LIMITED>;
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!resident[dev]) {
+    int per_sm = 0, sms = 0;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, L.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    resident[dev] = per_sm * (sms > 0 ? sms : 148);
+  }
+  const int ctas = resident[dev] < L.ntiles ? resident[dev] : L.ntiles;
+  count_launches(1);
+  fn<<<ctas, dim3(64, 4), L.smem, L.s>>>(p, L.tab, L.tiles_x, L.ntiles, L.sched, kNegZero2);
   return cudaGetLastError();
 }
+template <bool ONEPASS, int NCH, int GAMUT>
+cudaError_t launch_range(const GainmapGenParams& p, const FastLaunch& L) {
+  return p.hdr.full_range ? launch_kernel<ONEPASS, NCH, GAMUT, false>(p, L) : launch_kernel<ONEPASS, NCH, GAMUT, true>(p, L);
+}
 template <bool ONEPASS, int NCH>
-cudaError_t launch_g(const GainmapGenParams& p, const double* tab, dim3 g, dim3 b, size_t sm, cudaStream_t s) {
+cudaError_t launch_g(const GainmapGenParams& p, const FastLaunch& L) {
   const int gm = p.gamut_identity ? 0 : (p.gamut_on_hdr ? 2 : 1);
-  if (gm == 0) return launch_range<ONEPASS, NCH, 0>(p, tab, g, b, sm, s);
-  if (gm == 1) return launch_range<ONEPASS, NCH, 1>(p, tab, g, b, sm, s);
-  return launch_range<ONEPASS, NCH, 2>(p, tab, g, b, sm, s);
+  if (gm == 0) return launch_range<ONEPASS, NCH, 0>(p, L);
+  if (gm == 1) return launch_range<ONEPASS, NCH, 1>(p, L);
+  return launch_range<ONEPASS, NCH, 2>(p, L);
 }
 
 }  // namespace
@@ -388,22 +471,17 @@ cudaError_t launch_powf_probe(const float* d_in, float y, float* d_out, int n, c
   return cudaGetLastError();
 }
 
-cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, cudaStream_t s) {
-  const double* tab = nullptr;
-  if (log2_table_dev(&tab) != E_OK) return cudaErrorUnknown;
-  dim3 b(64, 4);
-  // persistent-ish grid: each CTA strides over tile rows so the 42 KB of tables are staged once
-  const int rows_per_cta = b.y * 2;
-  int gy = (p.map_h + rows_per_cta - 1) / rows_per_cta;
-  const int gx = (p.map_w / 4 + b.x - 1) / b.x;
-  const int want = (148 * 5 + gx - 1) / gx;  // ~5 CTAs per SM resident
-  if (gy > want) gy = want;
-  dim3 g(gx, gy);
-  const size_t sm = sizeof(GmSmem);
-  cudaError_t e;
-  if (onepass) e = p.nch == 3 ? launch_g<true, 3>(p, tab, g, b, sm, s) : launch_g<true, 1>(p, tab, g, b, sm, s);
-  else e = p.nch == 3 ? launch_g<false, 3>(p, tab, g, b, sm, s) : launch_g<false, 1>(p, tab, g, b, sm, s);
-  return e;
+// sched: one zeroed device word (tile tickets of the persistent grid)
+cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, unsigned* sched, cudaStream_t s) {
+  FastLaunch L;
+  if (log2_table_dev(&L.tab) != E_OK) return cudaErrorUnknown;
+  L.tiles_x = (p.map_w / 4 + 63) / 64;
+  L.ntiles = L.tiles_x * ((p.map_h + 7) / 8);
+  L.sched = sched;
+  L.smem = sizeof(GmSmem);
+  L.s = s;
+  if (onepass) return p.nch == 3 ? launch_g<true, 3>(p, L) : launch_g<true, 1>(p, L);
+  return p.nch == 3 ? launch_g<false, 3>(p, L) : launch_g<false, 1>(p, L);
 }
 
 }  // namespace uhdr_b200

@@ -448,9 +448,11 @@ int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, con
   const unsigned grid = (nseq + 127) / 128;
   ws.t_begin("huffdec_sync");
   k_hd_init<<<(nseq + 255) / 256, 256, 0, s>>>(d_out, d_used, d_cnt, nseq);
+  count_launches(1);
   int rounds = 0, first_quiet = 0;
   bool converged = false;
   while (!converged && rounds < kMaxRounds) {
+    count_launches(kRoundsPerBatch);
     for (int r = 0; r < kRoundsPerBatch; r++) k_hd_sync<<<grid, 128, 0, s>>>(d_bits, d_out, d_used, d_cnt, d_flags + rounds + r, d_hs);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h_flags + rounds, d_flags + rounds, sizeof(unsigned) * kRoundsPerBatch, cudaMemcpyDeviceToHost, s));
@@ -472,6 +474,7 @@ int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, con
   for (int c = 0; c < f.ncomp; c++) { o.coefs[c] = d_coefs[c]; o.dcd[c] = d_dcd[c]; }
   o.err = d_total + 1;
   ws.t_begin("huffdec_write");
+  count_launches(2 + 3 * f.ncomp);
   k_hd_scan<<<1, 1024, 0, s>>>(d_cnt, d_base, nseq, d_total);
   k_hd_write<<<grid, 128, 0, s>>>(d_bits, d_out, d_base, d_hs, o);
   ws.t_end();

@@ -1,13 +1,12 @@
 // Baseline-JPEG entropy coding on the device, bit-identical to libjpeg-turbo's jchuff.c for the
 // reference's settings (default Annex-K tables, one interleaved scan, no restart markers).
 //
-//   E1  k_huff_blocks  : one thread per 8x8 block (in scan order).  DC prediction reads the
-//                        previous block of the same component; the block's code bits go to a
-//                        word-transposed scratch (word w of block s at scratch[w*nblocks+s], so a
-//                        warp's stores are contiguous) and its bit count to bits[s].
-//   E2  scan           : exclusive prefix sum of bits[] -> bit offset of every block.
-//   E3  k_huff_concat  : blocks OR their words into the MSB-first bitstream at their offsets.
-//   E4  k_ff_count / scan / k_stuff : pad the last byte with ones, insert 0x00 after every 0xFF.
+//   E1  k_huff_encode  : CTAs of 128 consecutive blocks (scan order): stage the coefficients in
+//                        shared memory, count each block's code bits, chain the bit offsets across
+//                        CTAs with a decoupled look-back, encode into a word-aligned shared-memory
+//                        image of the CTA's segment and store it; partial boundary words travel
+//                        from CTA to CTA (details at the kernel).
+//   E2  k_ff_count / scan / k_stuff : pad the last byte with ones, insert 0x00 after every 0xFF.
 // Only the final stuffed segment (a few MB at 4K) crosses PCIe.
 #include <cstring>
 
@@ -48,88 +47,6 @@ __device__ __forceinline__ void locate(const HuffFrame& f, unsigned s, int& c, u
   }
 }
 
-struct BitSink {
-  unsigned* scratch;
-  unsigned nblocks, s;
-  unsigned long long acc;
-  int fill, words;
-  unsigned total;
-  __device__ __forceinline__ void put(unsigned bits, int n) {
-    acc = (acc << n) | bits;
-    fill += n;
-    total += n;
-    if (fill >= 32) {
-      scratch[(size_t)words * nblocks + s] = (unsigned)(acc >> (fill - 32));
-      words++;
-      fill -= 32;
-    }
-  }
-  __device__ __forceinline__ void finish() {
-    if (fill > 0) scratch[(size_t)words * nblocks + s] = (unsigned)(acc << (32 - fill));
-  }
-};
-
-// coefficients are stored in zigzag order by k_fdct_quant (zigzag_out = 1)
-__global__ void __launch_bounds__(128) k_huff_blocks(const HuffFrame f, const uint32_t* __restrict__ books,
-                                                     unsigned* __restrict__ scratch, unsigned* __restrict__ bits) {
-  __shared__ uint32_t sb[4 * 256];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sb[i] = books[i];
-  __syncthreads();
-  const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= f.nblocks) return;
-  int c;
-  unsigned blk;
-  long long prev;
-  locate(f, s, c, blk, prev);
-  const int16_t* __restrict__ base = f.coefs[c];
-  const uint4* src = (const uint4*)(base + (size_t)blk * 64);
-  unsigned w[32];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const uint4 q = __ldg(src + i);
-    w[i * 4] = q.x; w[i * 4 + 1] = q.y; w[i * 4 + 2] = q.z; w[i * 4 + 3] = q.w;
-  }
-  const int pred = prev >= 0 ? (int)__ldg(base + (size_t)prev * 64) : 0;
-  const uint32_t* dcb = sb + (c == 0 ? 0 : 512);
-  const uint32_t* acb = sb + (c == 0 ? 256 : 768);
-  BitSink o{scratch, f.nblocks, s, 0ull, 0, 0, 0u};
-  {
-    const int dc = (int)(short)(w[0] & 0xffff);
-    const int diff = dc - pred;
-    const int mag = abs(diff);
-    const int nb = mag ? 32 - __clz(mag) : 0;
-    const uint32_t e = dcb[nb];
-    const unsigned low = (unsigned)(diff < 0 ? diff - 1 : diff) & ((1u << nb) - 1u);
-    o.put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
-  }
-  int run = 0;
-#pragma unroll
-  for (int k = 1; k < 64; k++) {
-    const int v = (int)(short)((w[k >> 1] >> ((k & 1) * 16)) & 0xffff);
-    if (v == 0) {
-      run++;
-    } else {
-      while (run > 15) {
-        const uint32_t z = acb[0xF0];
-        o.put(z >> 8, (int)(z & 0xff));
-        run -= 16;
-      }
-      const int mag = abs(v);
-      const int nb = 32 - __clz(mag);
-      const uint32_t e = acb[(run << 4) | nb];
-      const unsigned low = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
-      o.put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
-      run = 0;
-    }
-  }
-  if (run > 0) {
-    const uint32_t e = acb[0];
-    o.put(e >> 8, (int)(e & 0xff));
-  }
-  o.finish();
-  bits[s] = o.total;
-}
-
 // ---- exclusive scan of u32 (three-phase, tiles of 1024) -------------------------------------------
 constexpr int kScanTile = 1024;
 
@@ -161,15 +78,6 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
 }
 
 // n may come from device memory (n_ptr) so dependent stages need no host round trip
-__global__ void __launch_bounds__(kScanTile) k_scan_reduce(const unsigned* __restrict__ in, unsigned n,
-                                                           const unsigned* n_ptr, unsigned* __restrict__ partial) {
-  if (n_ptr) n = *n_ptr;
-  const unsigned i = blockIdx.x * kScanTile + threadIdx.x;
-  if (blockIdx.x * kScanTile >= n && blockIdx.x > 0) return;
-  unsigned t;
-  block_exclusive_scan(i < n ? in[i] : 0u, &t);
-  if (threadIdx.x == 0) partial[blockIdx.x] = t;
-}
 __global__ void __launch_bounds__(kScanTile) k_scan_partials(unsigned* __restrict__ partial, unsigned ntiles_max,
                                                              unsigned n, const unsigned* n_ptr, unsigned* total_out) {
   if (n_ptr) n = *n_ptr;
@@ -185,44 +93,238 @@ __global__ void __launch_bounds__(kScanTile) k_scan_partials(unsigned* __restric
   }
   if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
-__global__ void __launch_bounds__(kScanTile) k_scan_apply(const unsigned* __restrict__ in, unsigned n, const unsigned* n_ptr,
-                                                          const unsigned* __restrict__ partial, unsigned* __restrict__ out) {
-  if (n_ptr) n = *n_ptr;
-  if (blockIdx.x * kScanTile >= n) return;
-  const unsigned i = blockIdx.x * kScanTile + threadIdx.x;
-  const unsigned v = i < n ? in[i] : 0u;
-  const unsigned e = block_exclusive_scan(v, nullptr);
-  if (i < n) out[i] = partial[blockIdx.x] + e;
+// ---- E1: encode, chain the bit offsets across CTAs, write the stream ------------------------------
+// One CTA = kEncBlocks consecutive blocks of the scan, taken in ticket order so that a CTA's
+// predecessors are always already running (the cross-CTA steps below spin on them).
+//   a. the coefficient blocks are staged in shared memory with coalesced loads (stride-129 word
+//      tile: thread j then reads word r of its block at tile[r*129 + j] without bank conflicts)
+//   b. pass A: each thread builds the 64-bit non-zero mask of its block and counts its code bits
+//      (only the non-zero coefficients are visited)
+//   c. CTA-wide exclusive scan -> bit offset of each block inside the CTA's segment and the total
+//   d. decoupled look-back over per-CTA status words (aggregate / inclusive prefix) -> the
+//      segment's absolute bit offset
+//   e. pass B: the blocks are encoded again, now ORing their bits into a shared-memory image of the
+//      segment that is aligned to the 32-bit words of the output stream
+//   f. interior words are stored coalesced; the trailing partial word is handed to the successor
+//      CTA, which merges it with its own leading bits and stores the word.  No pre-zeroed stream,
+//      no scratch, no global atomics on the stream.
+constexpr int kEncBlocks = 128;
+constexpr int kTileStride = kEncBlocks + 1;
+// shared-memory image of the CTA's segment: 2048 words = 512 bits per block on average.  Heavier
+// segments (noise at high quality; the worst case is 52 words per block) are produced in several
+// windows of this size, pass B running once per window.
+constexpr unsigned kSegWords = 2048;
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
+
+struct EncSmem {
+  uint32_t books[4 * 256];
+  uint32_t tile[32 * kTileStride];
+  uint32_t seg[kSegWords];
+};
+
+template <bool EMIT>
+__device__ __forceinline__ unsigned encode_block(const uint32_t* __restrict__ tile, int j, unsigned long long mask, int dc_diff,
+                                                 const uint32_t* __restrict__ dcb, const uint32_t* __restrict__ acb, uint32_t* seg,
+                                                 unsigned bitpos, unsigned win) {
+  unsigned total = 0;
+  unsigned long long acc = 0;
+  int fill = (int)(bitpos & 31);
+  unsigned widx = bitpos >> 5;
+  auto put = [&](unsigned bits, int n) {
+    total += n;
+    if (EMIT) {
+      acc = (acc << n) | bits;
+      fill += n;
+      if (fill >= 32) {
+        if (widx - win < kSegWords) atomicOr(seg + (widx - win), (unsigned)(acc >> (fill - 32)));
+        widx++;
+        fill -= 32;
+      }
+    }
+  };
+  {
+    const int mag = abs(dc_diff);
+    const int nb = mag ? 32 - __clz(mag) : 0;
+    const uint32_t e = dcb[nb];
+    const unsigned low = (unsigned)(dc_diff < 0 ? dc_diff - 1 : dc_diff) & ((1u << nb) - 1u);
+    put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
+  }
+  int last = 0;
+  const uint32_t zrl = acb[0xF0];
+  while (mask) {
+    const int k = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    int run = k - last - 1;
+    last = k;
+    while (run > 15) {
+      put(zrl >> 8, (int)(zrl & 0xff));
+      run -= 16;
+    }
+    const uint32_t w = tile[(k >> 1) * kTileStride + j];
+    const int v = (int)(short)((w >> ((k & 1) * 16)) & 0xffff);
+    const int mag = abs(v);
+    const int nb = 32 - __clz(mag);
+    const uint32_t e = acb[(run << 4) | nb];
+    const unsigned low = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
+    put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
+  }
+  if (last != 63) {
+    const uint32_t e = acb[0];
+    put(e >> 8, (int)(e & 0xff));
+  }
+  if (EMIT && (fill & 31) && widx - win < kSegWords) atomicOr(seg + (widx - win), (unsigned)(acc << (32 - fill)));
+  return total;
 }
 
-// ---- E3: concatenate -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_huff_concat(const unsigned* __restrict__ scratch, const unsigned* __restrict__ bits,
-                                                     const unsigned* __restrict__ offs, unsigned nblocks,
-                                                     unsigned* __restrict__ stream, unsigned cap_words, unsigned* overflow) {
-  const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nblocks) return;
-  const unsigned tb = bits[s];
-  const unsigned off = offs[s];
-  const unsigned nw = (tb + 31) >> 5;
-  if (((unsigned long long)off + tb + 31) / 32 + 1 > cap_words) {
-    *overflow = 1;
-    return;
+// status[i]: look-back word of CTA i (flag | bits);  tails[i]: (1 << 32 | trailing partial word) once known
+// ctl[0] <- total bits, ctl[5] = ticket counter (zeroed by the caller together with status / tails)
+__global__ void __launch_bounds__(kEncBlocks) k_huff_encode(const HuffFrame f, const uint32_t* __restrict__ books,
+                                                            unsigned long long* status, unsigned long long* tails,
+                                                            unsigned* __restrict__ stream, unsigned cap_words, unsigned* ctl) {
+  extern __shared__ uint32_t enc_smem_raw[];
+  EncSmem& sm = *reinterpret_cast<EncSmem*>(enc_smem_raw);
+  __shared__ unsigned s_cta, s_base, s_total;
+  __shared__ const int16_t* s_src[kEncBlocks];
+  const int j = threadIdx.x;
+  if (j == 0) s_cta = atomicAdd(ctl + 5, 1u);
+  for (int i = j; i < 1024; i += kEncBlocks) sm.books[i] = books[i];
+  __syncthreads();
+  const unsigned cta = s_cta;
+  const unsigned s = cta * kEncBlocks + j;
+  const bool live = s < f.nblocks;
+  int c = 0;
+  int pred = 0;
+  if (live) {
+    unsigned blk;
+    long long prev;
+    locate(f, s, c, blk, prev);
+    s_src[j] = f.coefs[c] + (size_t)blk * 64;
+    pred = prev >= 0 ? (int)__ldg(f.coefs[c] + (size_t)prev * 64) : 0;
+  } else {
+    s_src[j] = nullptr;
   }
-  const unsigned sh = off & 31;
-  unsigned idx = off >> 5;
-  for (unsigned w = 0; w < nw; w++, idx++) {
-    const unsigned v = scratch[(size_t)w * nblocks + s];  // unused low bits of the last word are zero
-    if (sh == 0) {
-      atomicOr(stream + idx, v);
-    } else {
-      atomicOr(stream + idx, v >> sh);
-      const unsigned lo = v << (32 - sh);
-      if (lo) atomicOr(stream + idx + 1, lo);
+  __syncthreads();
+  // a. 8 lanes per block, 16 bytes each: 4 blocks = 512 contiguous bytes per warp instruction when the
+  //    blocks are neighbours in their plane
+  for (int i = j; i < kEncBlocks * 8; i += kEncBlocks) {
+    const int b = i >> 3, ch = i & 7;
+    const int16_t* src = s_src[b];
+    if (src) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + ch);
+      uint32_t* t = sm.tile + (ch * 4) * kTileStride + b;
+      t[0] = q.x; t[kTileStride] = q.y; t[2 * kTileStride] = q.z; t[3 * kTileStride] = q.w;
     }
   }
+  __syncthreads();
+  // b. non-zero mask and bit count
+  unsigned long long mask = 0;
+  int dc_diff = 0;
+  unsigned nbits = 0;
+  const uint32_t* dcb = sm.books + (c == 0 ? 0 : 512);
+  const uint32_t* acb = sm.books + (c == 0 ? 256 : 768);
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+      const uint32_t w = sm.tile[r * kTileStride + j];
+      if (w & 0xffffu) mask |= 1ull << (2 * r);
+      if (w >> 16) mask |= 2ull << (2 * r);
+    }
+    dc_diff = (int)(short)(sm.tile[j] & 0xffff) - pred;
+    mask &= ~1ull;
+    nbits = encode_block<false>(sm.tile, j, mask, dc_diff, dcb, acb, nullptr, 0, 0);
+  }
+  // c. offsets inside the CTA
+  unsigned total;
+  const unsigned off = block_exclusive_scan(nbits, &total);
+  // d. absolute offset: publish the aggregate, then look back (warp 0, 32 predecessors at a time)
+  if (j == 0) {
+    *reinterpret_cast<volatile unsigned long long*>(status + cta) = (cta == 0 ? kFlagPrefix : kFlagAgg) | total;
+    s_total = total;
+  }
+  if (j < 32 && cta > 0) {
+    unsigned base = 0;
+    long long hi = (long long)cta - 1;  // highest predecessor not yet accounted for
+    bool done = false;
+    while (!done) {
+      const long long idx = hi - j;
+      unsigned long long st = kFlagPrefix;  // before CTA 0: nothing
+      if (idx >= 0) {
+        do { st = *reinterpret_cast<volatile unsigned long long*>(status + idx); } while ((st & kFlagMask) == 0);
+      }
+      const bool is_prefix = (st & kFlagMask) == kFlagPrefix;
+      const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+      const int first_prefix = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor carrying an inclusive prefix
+      unsigned v = (j <= first_prefix && idx >= 0) ? (unsigned)(st & 0xffffffffu) : 0u;
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      base += v;
+      if (pm) done = true;
+      else hi -= 32;
+    }
+    if (j == 0) {
+      s_base = base;
+      *reinterpret_cast<volatile unsigned long long*>(status + cta) = kFlagPrefix | (unsigned long long)(base + total);
+    }
+  } else if (j == 0 && cta == 0) {
+    s_base = 0;
+  }
+  __syncthreads();
+  const unsigned base = s_base;
+  const unsigned sh = base & 31, first = base >> 5;
+  const unsigned endbit = sh + total;              // relative to word `first`
+  const unsigned nwords = (endbit + 31) >> 5;      // words of the segment image in use
+  const bool overflow = (unsigned long long)first + nwords + 1 > cap_words;
+  // e./f. segment image, one window of kSegWords words at a time; full words are stored coalesced,
+  //       the head word (index 0) and the trailing partial word (index lastw) are kept for step g
+  const unsigned tailbits = endbit & 31;
+  const unsigned lastw = endbit >> 5;              // index (relative) of the word holding the trailing partial bits
+  const bool is_last = (cta + 1) * (unsigned)kEncBlocks >= f.nblocks;
+  __shared__ unsigned s_head, s_tail;
+  for (unsigned win = 0; win < nwords; win += kSegWords) {
+    const unsigned wn = min(kSegWords, nwords - win);
+    for (unsigned i = j; i < wn; i += kEncBlocks) sm.seg[i] = 0;
+    __syncthreads();
+    if (live) encode_block<true>(sm.tile, j, mask, dc_diff, dcb, acb, sm.seg, sh + off, win);
+    __syncthreads();
+    if (!overflow)
+      for (unsigned i = j; i < wn; i += kEncBlocks) {
+        const unsigned w = win + i;
+        if (w >= 1 && w < lastw) stream[first + w] = sm.seg[i];
+      }
+    if (j == 0) {
+      if (win == 0) s_head = sm.seg[0];
+      if (lastw >= win && lastw < win + wn) s_tail = sm.seg[lastw - win];
+    }
+    __syncthreads();
+  }
+  // g. boundary words
+  if (j == 0) {
+    // a non-degenerate segment hands its trailing partial word on *before* waiting for the
+    // predecessor's: otherwise every CTA would wait for the whole chain in front of it
+    const unsigned tail = (lastw > 0 && tailbits) ? s_tail : 0u;
+    if (lastw > 0) {
+      *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | tail;
+      if (is_last && tailbits && !overflow) stream[first + lastw] = tail;
+    }
+    unsigned head = s_head;
+    if (sh > 0) {  // leading bits of word `first` belong to the predecessor
+      unsigned long long t;
+      do { t = *reinterpret_cast<volatile unsigned long long*>(tails + cta - 1); } while ((t >> 32) == 0);
+      head |= (unsigned)t;
+    }
+    if (lastw > 0) {
+      if (!overflow) stream[first] = head;
+    } else {
+      // the whole segment lies inside word `first` (only a short last CTA can be this small): the
+      // merged word is also our trailing partial word
+      if (is_last && !overflow) stream[first] = head;
+      *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | head;
+    }
+    if (overflow) ctl[4] = 1;
+    if (is_last) ctl[0] = base + total;
+  }
 }
 
-// ---- E4: byte stuffing ---------------------------------------------------------------------------
+// ---- E2: byte stuffing ---------------------------------------------------------------------------
 // logical word j of `stream` holds stream bytes 4j..4j+3, first byte in the most significant bits
 __device__ __forceinline__ unsigned load_padded_word(const unsigned* stream, unsigned j, unsigned total_bits) {
   unsigned v = stream[j];
@@ -240,13 +342,6 @@ __device__ __forceinline__ unsigned ff_count(unsigned v, unsigned j, unsigned to
   for (int b = 0; b < 4; b++)
     if (4 * j + b < total_bytes && ((v >> (24 - 8 * b)) & 0xff) == 0xff) c++;
   return c;
-}
-// zero exactly the words the concatenation will OR into (total known on the device only)
-__global__ void __launch_bounds__(256) k_zero_stream(unsigned* __restrict__ stream, const unsigned* total_bits_ptr,
-                                                     unsigned cap_words) {
-  unsigned n = (*total_bits_ptr + 31) / 32 + 2;
-  if (n > cap_words) n = cap_words;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stream[i] = 0u;
 }
 // persistent grid: CTAs stride over the tiles actually in use
 __global__ void __launch_bounds__(kScanTile) k_ff_count(const unsigned* __restrict__ stream, const unsigned* total_bits_ptr,
@@ -347,34 +442,35 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   // (ultrahdr_api.cpp:1294); a single scan can never need more than that in a valid encode
   const size_t cap = ((size_t)fr.width * fr.height * 6 + 4096 + 3) / 4 * 4;
   const unsigned cap_words = (unsigned)(cap / 4);
-  const unsigned ntiles_blocks = (unsigned)((nblocks + kScanTile - 1) / kScanTile);
   const unsigned ntiles_words = (cap_words + kScanTile - 1) / kScanTile;
-  unsigned* scratch = (unsigned*)ws.dalloc(nblocks * kMaxWordsPerBlock * sizeof(unsigned));
-  unsigned* bits = (unsigned*)ws.dalloc(nblocks * 4);
-  unsigned* offs = (unsigned*)ws.dalloc(nblocks * 4);
-  unsigned* part = (unsigned*)ws.dalloc((size_t)(ntiles_blocks > ntiles_words ? ntiles_blocks : ntiles_words) * 4 + 64);
+  const unsigned ncta = (unsigned)((nblocks + kEncBlocks - 1) / kEncBlocks);
+  // [ctl 64 B][status ncta x 8][tails ncta x 8], zeroed together
+  const size_t ctl_bytes = 64 + (size_t)ncta * 16;
+  unsigned* ctl = (unsigned*)ws.dalloc(ctl_bytes);  // [0] total_bits [1] tiles_in_use [2] total_ff [3] out_bytes [4] overflow [5] CTA tickets
   unsigned* stream = (unsigned*)ws.dalloc(cap + 64);
   unsigned* tile_ff = (unsigned*)ws.dalloc((size_t)ntiles_words * 4 + 64);
-  unsigned* ctl = (unsigned*)ws.dalloc(64);  // [0] total_bits [1] tiles_in_use [2] total_ff [3] out_bytes [4] overflow
   job->d_scan = (uint8_t*)ws.dalloc(cap + 64);
   job->h_scan_bytes = (unsigned*)ws.halloc(64);
-  if (!scratch || !bits || !offs || !part || !stream || !tile_ff || !ctl || !job->d_scan || !job->h_scan_bytes) return E_MEM;
+  if (!stream || !tile_ff || !ctl || !job->d_scan || !job->h_scan_bytes) return E_MEM;
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(ctl + 16);
+  unsigned long long* tails = status + ncta;
   job->d_scan_bytes = ctl + 3;
   job->scan_capacity = cap;
   cudaStream_t st = ws.stream();
-  CUDA_TRY(cudaMemsetAsync(ctl, 0, 64, st));
+  CUDA_TRY(cudaMemsetAsync(ctl, 0, ctl_bytes, st));
+  static bool smem_set[64] = {false};
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !smem_set[dev]) {
+      CUDA_TRY(cudaFuncSetAttribute(k_huff_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
+      smem_set[dev] = true;
+    }
+  }
 
-  ws.t_begin("huff_blocks");
-  k_huff_blocks<<<(unsigned)((nblocks + 127) / 128), 128, 0, st>>>(f, books, scratch, bits);
-  ws.t_end();
-  ws.t_begin("huff_scan");
-  k_scan_reduce<<<ntiles_blocks, kScanTile, 0, st>>>(bits, (unsigned)nblocks, nullptr, part);
-  k_scan_partials<<<1, kScanTile, 0, st>>>(part, ntiles_blocks, (unsigned)nblocks, nullptr, ctl + 0);
-  k_scan_apply<<<ntiles_blocks, kScanTile, 0, st>>>(bits, (unsigned)nblocks, nullptr, part, offs);
-  ws.t_end();
-  ws.t_begin("huff_concat");
-  k_zero_stream<<<kPersistentCtas, 256, 0, st>>>(stream, ctl + 0, cap_words);
-  k_huff_concat<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(scratch, bits, offs, (unsigned)nblocks, stream, cap_words, ctl + 4);
+  count_launches(4);
+  ws.t_begin("huff_encode");
+  k_huff_encode<<<ncta, kEncBlocks, sizeof(EncSmem), st>>>(f, books, status, tails, stream, cap_words, ctl);
   ws.t_end();
   ws.t_begin("huff_stuff");
   k_ff_count<<<kPersistentCtas, kScanTile, 0, st>>>(stream, ctl + 0, tile_ff, ctl + 1);

@@ -14,6 +14,7 @@ namespace uhdr_b200 {
 
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long launch_count() { return g_launches.load(); }
+void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 #define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 struct C3 { float r, g, b; };  // also y,u,v
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(256) k_gainmap_pass1(const GainmapGenParams p)
 __global__ void k_gainmap_init_minmax(unsigned* mm) {
   if (threadIdx.x < 3) mm[threadIdx.x] = fkey(127.0f);
   else if (threadIdx.x < 6) mm[threadIdx.x] = fkey(-128.0f);
+  else if (threadIdx.x == 8) mm[8] = 0;  // tile-ticket counter of k_gainmap_fast
 }
 
 // jpegr.cpp:969-986 on the device so pass 2 can follow without a host round trip

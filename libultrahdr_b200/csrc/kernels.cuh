@@ -150,7 +150,7 @@ cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaSt
 bool affine_fast_eligible(const AffineParams& p);
 cudaError_t launch_affine_fast(const AffineParams& p, cudaStream_t s);
 bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass);
-cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, cudaStream_t s);
+cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, unsigned* sched, cudaStream_t s);
 cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream_t s);
 cudaError_t launch_powf_probe(const float* d_in, float y, float* d_out, int n, cudaStream_t s);
 cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s);
@@ -162,5 +162,6 @@ cudaError_t launch_ycc_to_rgba(const YccToRgbaParams& p, cudaStream_t s);
 
 // number of kernel launches issued by this library since load (bench.py's gpu_launches)
 unsigned long long launch_count();
+void count_launches(unsigned n);  // launches made outside kernels.cu (fast paths, JPEG stages)
 
 }  // namespace uhdr_b200
