@@ -53,9 +53,12 @@ int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b
   if (rc) return rc;
   // base image: icc of the sdr intent's gamut is chosen before the yuv re-encoding (:260)
   const int sdr_cg = sdr.cg;
-  if (fmt_is_rgb_host(sdr.v.fmt))
-    return fail(E_UNSUPPORTED, "RGBA8888 sdr intent needs convert_raw_input_to_ycbcr (gainmapmath.cpp:1291) "
-                "which is not part of the B200 hot path yet");
+  if (fmt_is_rgb_host(sdr.v.fmt)) {  // convert_raw_input_to_ycbcr (:221-228, :263-271)
+    DevImage ycc;
+    rc = rgb_to_ycbcr_dev(ws_, sdr, &ycc);
+    if (rc) return rc;
+    sdr = ycc;
+  }
   if (sdr_in) {
     rc = convert_yuv_dev(ws_, &sdr, sdr.cg, UHDR_CG_DISPLAY_P3);  // :277
     if (rc) return rc;

@@ -414,4 +414,27 @@ int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg) {
   return E_OK;
 }
 
+int rgb_to_ycbcr_dev(Workspace& ws, const DevImage& rgb, DevImage* out) {
+  if (rgb.v.fmt != F_RGBA8888 && rgb.v.fmt != F_RGB888)
+    return fail(E_UNSUPPORTED, "convert_raw_input_to_ycbcr: unsupported packed format %d", rgb.v.fmt);
+  RgbToYccParams p;
+  memset(&p, 0, sizeof p);
+  if (!rgb2yuv_coeffs(rgb.cg, p.k)) return fail(E_ERROR, "internal error : cannot convert packed rgb of color gamut %d to yuv", rgb.cg);
+  int rc = alloc_dev_image(ws, F_YUV444, rgb.v.w, rgb.v.h, 64, out);
+  if (rc) return rc;
+  out->cg = rgb.cg;
+  out->ct = rgb.ct;
+  out->range = UHDR_CR_FULL_RANGE;
+  out->v.full_range = 1;
+  p.src = (const uint8_t*)rgb.v.p[0];
+  p.src_stride = rgb.v.stride[0];
+  p.bpp = rgb.v.fmt == F_RGBA8888 ? 4 : 3;
+  for (int i = 0; i < 3; i++) p.dst[i] = (uint8_t*)out->v.p[i];
+  p.dst_stride = out->v.stride[0];
+  p.w = rgb.v.w;
+  p.h = rgb.v.h;
+  TIMED(ws, "rgb_to_ycbcr", launch_rgb_to_ycc(p, ws.stream()));
+  return E_OK;
+}
+
 }  // namespace uhdr_b200

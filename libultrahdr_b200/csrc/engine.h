@@ -43,5 +43,7 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
                       DevImage* dst /* allocated by caller, fmt F16 / 1010102 */);
 int tonemap_dev(Workspace& ws, const DevImage& hdr, DevImage* sdr /* allocated by caller */);
 int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg);
+// convert_raw_input_to_ycbcr for RGBA8888 / RGB888 (gainmapmath.cpp:1440-1467): new YCbCr 4:4:4 device image
+int rgb_to_ycbcr_dev(Workspace& ws, const DevImage& rgb, DevImage* out);
 
 }  // namespace uhdr_b200

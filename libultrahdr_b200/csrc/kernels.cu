@@ -1020,6 +1020,37 @@ cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s) {
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
+// convert_raw_input_to_ycbcr for 8-bit RGB input (gainmapmath.cpp:1440-1467): getPixel (/255.0f), the
+// gamut's rgbToYuv, *255 + 0.5 (+128 for chroma), clip, truncate
+__global__ void __launch_bounds__(256) k_rgb_to_ycc(const RgbToYccParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= p.w) return;
+  const uint8_t* s = p.src + ((size_t)y * p.src_stride + x) * p.bpp;
+  float r, g, b;
+  if (p.bpp == 4) {
+    const unsigned v = __ldg((const unsigned*)s);
+    r = (float)(v & 0xff); g = (float)((v >> 8) & 0xff); b = (float)((v >> 16) & 0xff);
+  } else {
+    r = (float)s[0]; g = (float)s[1]; b = (float)s[2];
+  }
+  r = r / 255.0f; g = g / 255.0f; b = b / 255.0f;
+  const float yg = p.k[0] * r + p.k[1] * g + p.k[2] * b;
+  const float u = (b - yg) / p.k[3], v = (r - yg) / p.k[4];
+  float yy = yg * 255.0f + 0.5f;
+  yy = yy < 0.0f ? 0.0f : (yy > 255.0f ? 255.0f : yy);
+  float uu = u * 255.0f + 0.5f + 128.0f, vv = v * 255.0f + 0.5f + 128.0f;
+  uu = uu < 0.0f ? 0.0f : (uu > 255.0f ? 255.0f : uu);
+  vv = vv < 0.0f ? 0.0f : (vv > 255.0f ? 255.0f : vv);
+  const size_t o = (size_t)y * p.dst_stride + x;
+  p.dst[0][o] = (uint8_t)__float2int_rz(yy);
+  p.dst[1][o] = (uint8_t)__float2int_rz(uu);
+  p.dst[2][o] = (uint8_t)__float2int_rz(vv);
+}
+cudaError_t launch_rgb_to_ycc(const RgbToYccParams& p, cudaStream_t s) {
+  k_rgb_to_ycc<<<dim3((p.w + 255) / 256, p.h), 256, 0, s>>>(p);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
 cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s) {
   dim3 b(32, 8);
   const int f = p.fmt == F_YUV420 ? 2 : 1;

@@ -93,6 +93,15 @@ struct YuvConvParams {              // transformYuv420/444, gainmapmath.cpp:686-
   float m[9];
 };
 
+struct RgbToYccParams {             // convert_raw_input_to_ycbcr, gainmapmath.cpp:1440-1467 (RGBA8888 / RGB888 -> YCbCr 4:4:4)
+  const uint8_t* src;
+  int src_stride, bpp;              // pixels per row; 4 or 3 bytes per pixel
+  uint8_t* dst[3];
+  int dst_stride;
+  int w, h;
+  float k[5];                       // yr, yg, yb, cb, cr
+};
+
 struct DctPlaneParams {             // forward: samples -> coefficients
   const uint8_t* src;               // plane (or packed RGB when rgb_comp >= 0)
   int src_stride;                   // elements per row (pixels for RGB)
@@ -155,6 +164,7 @@ cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream
 cudaError_t launch_powf_probe(const float* d_in, float y, float* d_out, int n, cudaStream_t s);
 cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s);
 cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s);
+cudaError_t launch_rgb_to_ycc(const RgbToYccParams& p, cudaStream_t s);
 cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s);
 cudaError_t launch_fdct8(const Fdct8Params& p, cudaStream_t s);
 cudaError_t launch_idct_dequant(const IdctPlaneParams& p, cudaStream_t s);

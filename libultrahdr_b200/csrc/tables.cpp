@@ -177,6 +177,18 @@ bool yuv_matrix(int src, int dst, float out[9]) {
 }
 
 // gainmapmath.cpp:94,104-111,164,174-181,194,226-233: {cr, cb, gcb, gcr}
+bool rgb2yuv_coeffs(int cg, float out[5]) {
+  if (cg == 0) {
+    out[0] = kSrgbR; out[1] = kSrgbG; out[2] = kSrgbB; out[3] = f2(kSrgbB); out[4] = f2(kSrgbR);
+  } else if (cg == 1) {
+    out[0] = kP3YR; out[1] = kP3YG; out[2] = kP3YB; out[3] = kP3Cb; out[4] = kP3Cr;
+  } else if (cg == 2) {
+    out[0] = kBtR; out[1] = kBtG; out[2] = kBtB; out[3] = f2(kBtB); out[4] = f2(kBtR);
+  } else {
+    return false;
+  }
+  return true;
+}
 bool yuv2rgb_coeffs(int cg, float out[4]) {
   if (cg == 0) {
     float cb = f2(kSrgbB), cr = f2(kSrgbR);

@@ -45,6 +45,8 @@ bool gamut_matrix(int dst_cg, int src_cg, float out[9], bool* identity);
 bool yuv_matrix(int src_cg, int dst_cg, float out[9]);
 // yuv->rgb coefficients {cr, cb, gcb, gcr} of a gamut
 bool yuv2rgb_coeffs(int cg, float out[4]);
+// {yr, yg, yb, cb, cr} of srgb/p3/bt2100RgbToYuv (gainmapmath.cpp:96-99,166-169,196-199)
+bool rgb2yuv_coeffs(int cg, float out[5]);
 // luminance coefficients
 bool luminance_coeffs(int cg, float out[3]);
 float reference_display_peak_nits(int ct);

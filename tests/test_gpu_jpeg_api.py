@@ -152,3 +152,33 @@ def test_uhdr_encode_api0_file_bytes(gpu, oracle_libs, w, h, kind):
     hdr, sdr, keep = _frames(w, h, kind)
     for opts in ({}, {"multichannel": 0}, {"scale": 2}):
         assert mine.encode(hdr, None, **opts) == ref.encode(hdr, None, **opts), opts
+
+
+def _rgba_frames(w, h, hdr_kind):
+    """packed intents: RGBA1010102 (PQ / HLG) or RGBA half float (linear) HDR + RGBA8888 SDR"""
+    if hdr_kind == "f16":
+        hb = T.make_rgbaf16(w, h)
+        hdr = A.raw_image(A.FMT_RGBAF16, A.CG_BT2100, A.CT_LINEAR, A.CR_FULL, w, h, [hb], [w])
+    else:
+        hb = T.make_rgba1010102(w, h)
+        hdr = A.raw_image(A.FMT_RGBA1010102, A.CG_BT2100, A.CT_PQ if hdr_kind == "pq" else A.CT_HLG, A.CR_FULL, w, h, [hb], [w])
+    sb = T.make_rgba8888(w, h)
+    sdr = A.raw_image(A.FMT_RGBA8888, A.CG_BT709, A.CT_SRGB, A.CR_FULL, w, h, [sb], [w])
+    return hdr, sdr, (hb, sb)
+
+
+@pytest.mark.parametrize("hdr_kind", ["pq", "hlg", "f16"])
+def test_uhdr_encode_packed_intents_file_bytes(gpu, oracle_libs, hdr_kind):
+    """RGBA1010102 / RGBA half-float HDR intents and the RGBA8888 SDR intent (convert_raw_input_to_ycbcr,
+    4:4:4 base image): API-0 and API-1 files equal the reference's byte for byte."""
+    if not oracle_libs.have_ref():
+        pytest.skip("reference build not available")
+    ref = T.UhdrApi(oracle_libs.Ref().lib)
+    mine = T.UhdrApi(gpu.lib)
+    for (w, h) in ((320, 192), (648, 364)):
+        hdr, sdr, keep = _rgba_frames(w, h, hdr_kind)
+        a, b = mine.encode(hdr, None), ref.encode(hdr, None)
+        assert a == b, ("api0", hdr_kind, w, h, len(a), len(b))
+        for opts in ({}, {"scale": 2, "multichannel": 0}):
+            a, b = mine.encode(hdr, sdr, **opts), ref.encode(hdr, sdr, **opts)
+            assert a == b, ("api1", hdr_kind, w, h, opts, len(a), len(b))
