@@ -200,12 +200,42 @@ def load_traffic():
         return {}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """one process per GPU: run on (and first-touch pinned memory from) the CPU cores NVML names as
+    closest to that GPU.  Returns a short description for the config, or the reason it was skipped."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        try:
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+            except TypeError:
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return "unchanged (empty NVML cpu set)"
+        os.sched_setaffinity(0, cpus)
+        return "%d cpus near gpu %d (%d-%d)" % (len(cpus), local, cpus[0], cpus[-1])
+    except Exception as e:  # noqa: BLE001
+        return "unchanged (%s)" % type(e).__name__
+
+
 def bench_b200(args, rank, world):
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
     import torch
     import torch.distributed as dist
     import __graft_entry__ as G
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     so = os.path.join(ROOT, "libultrahdr_b200", "libuhdr_b200.so")
@@ -368,7 +398,7 @@ def bench_b200(args, rank, world):
         "ms_per_step": round(t_res / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "api1_encode_3840x2160_p010hlg_bt2100+yuv420_bt709", "frames_per_gpu_per_step": F, "host_buffers": "pinned",
-                   "encoder_slots": slots_n, "quality": 95, "gainmap": "multichannel scale 1 two-pass",
+                   "cpu_affinity": affinity, "encoder_slots": slots_n, "quality": 95, "gainmap": "multichannel scale 1 two-pass",
                    "l2_policy": "inputs larger than L2 (%d MB of frames per step, distinct per frame)" % (in_bytes >> 20),
                    "timing": "wall clock between device-wide synchronisations around exactly K steps, max over ranks; "
                              "per-kernel times from CUDA events on the launching streams"},
@@ -382,7 +412,7 @@ def bench_b200(args, rank, world):
         "extra": extra,
         "stream_bytes_per_frame": int(sum(out_bytes) / max(1, F)),
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -536,7 +566,7 @@ def bench_reference(args, rank, world):
     import uhdr_testlib as T
     T.ensure_oracle_built()
     if not T.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libuhdr_ref.so not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libuhdr_ref.so not built (needs /root/reference at build time)"})
         return
     api, lib = load_api(T.REF_SO)
     ncpu = os.cpu_count() or 1
@@ -555,14 +585,25 @@ def bench_reference(args, rank, world):
     dt = time.perf_counter() - t0
     v = per_step * args.steps * MPIX_4K / dt
     sample = "%d concurrent 4K API-1 uhdr_encode calls per step (reference uses 4 worker threads per call)" % conc
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "MPix/s encode(API-1) at 4K", "value": round(v, 2), "unit": "MPix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "api1_encode_3840x2160_p010hlg_bt2100+yuv420_bt709", "frames_per_step": per_step},
         "cpu_baseline": {"value": round(v, 2), "unit": "MPix/s", "cores": min(ncpu, conc * 4), "kind": "reference", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the one JSON line, on the process's real stdout"""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
 
 
 def main():
@@ -576,6 +617,12 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # stdout must carry exactly one JSON line: while the bench runs, file descriptor 1 points at
+    # stderr (NCCL and other libraries print banners to stdout); emit() switches it back
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         if args.steps > 3:
             args.steps = 3  # bounded sample: each step is seconds of CPU work
