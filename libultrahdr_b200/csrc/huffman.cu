@@ -110,14 +110,13 @@ __global__ void __launch_bounds__(kScanTile) k_scan_partials(unsigned* __restric
 //      no scratch, no global atomics on the stream.
 constexpr int kEncBlocks = 128;
 constexpr int kTileStride = kEncBlocks + 1;
-// shared-memory image of the CTA's segment: 2048 words = 512 bits per block on average.  Heavier
+// shared-memory image of the CTA's segment: 1024 words = 256 bits per block on average.  Heavier
 // segments (noise at high quality; the worst case is 52 words per block) are produced in several
 // windows of this size, pass B running once per window.
-constexpr unsigned kSegWords = 2048;
+constexpr unsigned kSegWords = 1024;
 constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
 
 struct EncSmem {
-  uint32_t books[4 * 256];
   uint32_t tile[32 * kTileStride];
   uint32_t seg[kSegWords];
 };
@@ -145,12 +144,12 @@ __device__ __forceinline__ unsigned encode_block(const uint32_t* __restrict__ ti
   {
     const int mag = abs(dc_diff);
     const int nb = mag ? 32 - __clz(mag) : 0;
-    const uint32_t e = dcb[nb];
+    const uint32_t e = __ldg(dcb + nb);
     const unsigned low = (unsigned)(dc_diff < 0 ? dc_diff - 1 : dc_diff) & ((1u << nb) - 1u);
     put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
   }
   int last = 0;
-  const uint32_t zrl = acb[0xF0];
+  const uint32_t zrl = __ldg(acb + 0xF0);
   while (mask) {
     const int k = __ffsll((long long)mask) - 1;
     mask &= mask - 1;
@@ -164,12 +163,12 @@ __device__ __forceinline__ unsigned encode_block(const uint32_t* __restrict__ ti
     const int v = (int)(short)((w >> ((k & 1) * 16)) & 0xffff);
     const int mag = abs(v);
     const int nb = 32 - __clz(mag);
-    const uint32_t e = acb[(run << 4) | nb];
+    const uint32_t e = __ldg(acb + ((run << 4) | nb));
     const unsigned low = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
     put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
   }
   if (last != 63) {
-    const uint32_t e = acb[0];
+    const uint32_t e = __ldg(acb);
     put(e >> 8, (int)(e & 0xff));
   }
   if (EMIT && (fill & 31) && widx - win < kSegWords) atomicOr(seg + (widx - win), (unsigned)(acc << (32 - fill)));
@@ -187,7 +186,6 @@ __global__ void __launch_bounds__(kEncBlocks) k_huff_encode(const HuffFrame f, c
   __shared__ const int16_t* s_src[kEncBlocks];
   const int j = threadIdx.x;
   if (j == 0) s_cta = atomicAdd(ctl + 5, 1u);
-  for (int i = j; i < 1024; i += kEncBlocks) sm.books[i] = books[i];
   __syncthreads();
   const unsigned cta = s_cta;
   const unsigned s = cta * kEncBlocks + j;
@@ -220,8 +218,10 @@ __global__ void __launch_bounds__(kEncBlocks) k_huff_encode(const HuffFrame f, c
   unsigned long long mask = 0;
   int dc_diff = 0;
   unsigned nbits = 0;
-  const uint32_t* dcb = sm.books + (c == 0 ? 0 : 512);
-  const uint32_t* acb = sm.books + (c == 0 ? 256 : 768);
+  // code books (4 KB, hot in L1) are read through the read-only path: keeping them out of shared
+  // memory buys two more resident CTAs per SM
+  const uint32_t* dcb = books + (c == 0 ? 0 : 512);
+  const uint32_t* acb = books + (c == 0 ? 256 : 768);
   if (live) {
 #pragma unroll
     for (int r = 0; r < 32; r++) {
