@@ -209,8 +209,10 @@ int JpegRCodec::decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevI
     if (rc) return rc;
   }
   if (mode == 1) {
-    if (f.max_h != 1 || f.max_v != 1)
-      return fail(E_UNSUPPORTED, "RGB output of chroma-subsampled JPEG (libjpeg fancy upsampling) is outside the B200 hot path");
+    const bool s444 = f.max_h == 1 && f.max_v == 1, s422 = f.max_h == 2 && f.max_v == 1, s420 = f.max_h == 2 && f.max_v == 2;
+    if (!(s444 || s422 || s420) || f.comp[0].h_samp != f.max_h || f.comp[0].v_samp != f.max_v || f.comp[1].h_samp != 1 ||
+        f.comp[1].v_samp != 1 || f.comp[2].h_samp != 1 || f.comp[2].v_samp != 1)
+      return fail(E_UNSUPPORTED, "RGB output is implemented for 4:4:4, 4:2:2 and 4:2:0 JPEG input");
     DevImage rgba;
     rc = alloc_dev_image(ws_, F_RGBA8888, f.width, f.height, 1, &rgba);
     if (rc) return rc;
@@ -219,6 +221,11 @@ int JpegRCodec::decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevI
     p.src_stride = strides[0];
     p.w = f.width;
     p.h = f.height;
+    p.hs = f.max_h;
+    p.vs = f.max_v;
+    p.c_stride = strides[1];
+    p.cw = (f.width + f.max_h - 1) / f.max_h;
+    p.ch = (f.height + f.max_v - 1) / f.max_v;
     p.dst = (uint8_t*)rgba.v.p[0];
     p.dst_stride = rgba.v.stride[0];
     TIMED(ws_, "ycc_to_rgba", launch_ycc_to_rgba(p, ws_.stream()));
@@ -275,27 +282,34 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   size_t po, pl, go, gl;
   int rc = split_jpegr(data, size, &po, &pl, &go, &gl);
   if (rc) return rc;
-  if (out_ct == UHDR_CT_SRGB)
-    return fail(E_UNSUPPORTED, "sdr (UHDR_CT_SRGB) output is a plain libjpeg decode with chroma upsampling; outside the B200 hot path");
+  const bool sdr_only = out_ct == UHDR_CT_SRGB;  // :1479-1481, :1520-1523: the base image as RGBA8888, no gain map applied
   DevImage sdr, map;
   JpegHeader ph, gh;
-  rc = decode_jpeg_dev(data + po, pl, 0, &sdr, &ph);  // DECODE_TO_YCBCR_CS :1479-1481
-  if (rc) return rc;
-  rc = decode_jpeg_dev(data + go, gl, 2, &map, &gh);  // DECODE_STREAM :1486
+  rc = decode_jpeg_dev(data + po, pl, sdr_only ? 1 : 0, &sdr, &ph);  // DECODE_TO_RGB_CS / DECODE_TO_YCBCR_CS
   if (rc) return rc;
   std::vector<uint8_t> blob;
-  grab_marker(data + go, gh, 0xE2, "ICC_PROFILE", 12, &blob);
-  map.cg = icc_read_gamut(blob.data(), blob.size());
   grab_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12, &blob);
   sdr.cg = icc_read_gamut(blob.data(), blob.size());
-  grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &blob);
-  if (blob.empty())
-    return fail(E_UNSUPPORTED, "gain map metadata in XMP form only; the B200 decoder reads ISO 21496-1 metadata");
-  uhdr_gainmap_metadata_t md;
-  rc = iso_decode_metadata(blob.data() + 28, blob.size() - 28, &md);
-  if (rc) return rc;
-  if (md_out) *md_out = md;
   map_pending_ = false;
+  uhdr_gainmap_metadata_t md{};
+  if (gainmap_out || !sdr_only) {  // :1484-1495
+    rc = decode_jpeg_dev(data + go, gl, 2, &map, &gh);  // DECODE_STREAM :1486
+    if (rc) return rc;
+    grab_marker(data + go, gh, 0xE2, "ICC_PROFILE", 12, &blob);
+    map.cg = icc_read_gamut(blob.data(), blob.size());
+  }
+  if (md_out || !sdr_only) {  // :1497-1518
+    if (!(gainmap_out || !sdr_only)) {
+      rc = jpeg_read_header(data + go, gl, &gh);
+      if (rc) return rc;
+    }
+    grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &blob);
+    if (blob.empty())
+      return fail(E_UNSUPPORTED, "gain map metadata in XMP form only; the B200 decoder reads ISO 21496-1 metadata");
+    rc = iso_decode_metadata(blob.data() + 28, blob.size() - 28, &md);
+    if (rc) return rc;
+    if (md_out) *md_out = md;
+  }
   if (gainmap_out) {
     gainmap_out->fmt = (uhdr_img_fmt_t)map.v.fmt;
     gainmap_out->w = map.v.w;
@@ -318,12 +332,20 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
     }
   }
   DevImage dst;
-  rc = alloc_dev_image(ws_, dest->fmt, sdr.v.w, sdr.v.h, 64, &dst);
-  if (rc) return rc;
-  rc = apply_gainmap_dev(ws_, sdr, map, md, out_ct, max_display_boost, &dst);
-  if (rc) return rc;
-  dest->cg = (uhdr_color_gamut_t)dst.cg;
-  dest->ct = (uhdr_color_transfer_t)out_ct;
+  if (sdr_only) {  // copy_raw_image(&sdr_intent, dest) :1520-1523
+    if (dest->fmt != UHDR_IMG_FMT_32bppRGBA8888)
+      return fail(E_INVALID_PARAM, "unsupported output pixel format and output color transfer pair");
+    dst = sdr;
+    dest->cg = (uhdr_color_gamut_t)sdr.cg;
+    dest->ct = UHDR_CT_UNSPECIFIED;
+  } else {
+    rc = alloc_dev_image(ws_, dest->fmt, sdr.v.w, sdr.v.h, 64, &dst);
+    if (rc) return rc;
+    rc = apply_gainmap_dev(ws_, sdr, map, md, out_ct, max_display_boost, &dst);
+    if (rc) return rc;
+    dest->cg = (uhdr_color_gamut_t)dst.cg;
+    dest->ct = (uhdr_color_transfer_t)out_ct;
+  }
   dest->range = UHDR_CR_FULL_RANGE;
   if (!dest->planes[0]) {  // handle-owned result (see above)
     dest->stride[0] = sdr.v.w;

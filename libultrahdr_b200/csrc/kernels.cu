@@ -957,7 +957,46 @@ __global__ void __launch_bounds__(256) k_ycc_to_rgba(const YccToRgbaParams p) {
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= p.w || y >= p.h) return;
   const size_t i = (size_t)y * p.src_stride + x;
-  const int yy = __ldg(p.y + i), xb = (int)__ldg(p.cb + i) - 128, xr = (int)__ldg(p.cr + i) - 128;
+  const int yy = __ldg(p.y + i);
+  int xb, xr;
+  if (p.hs == 1) {
+    xb = (int)__ldg(p.cb + i) - 128;
+    xr = (int)__ldg(p.cr + i) - 128;
+  } else {
+    // libjpeg-turbo jdsample.c: h2v1 / h2v2 "fancy" (triangle) upsampling, the library default; a
+    // component whose downsampled width is <= 2 is replicated instead (jinit_upsampler).  Rows above
+    // the first / below the last real row are that row itself (jdmainct.c context rows).
+    const int cx = x >> 1;
+    const uint8_t* pl[2] = {p.cb, p.cr};
+    int o[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const uint8_t* base = pl[c];
+      if (p.cw <= 2) {
+        o[c] = __ldg(base + (size_t)(y / p.vs) * p.c_stride + cx);
+      } else if (p.vs == 1) {
+        const uint8_t* in = base + (size_t)y * p.c_stride;
+        const int cur = __ldg(in + cx);
+        if (x & 1) o[c] = cx == p.cw - 1 ? cur : (cur * 3 + (int)__ldg(in + cx + 1) + 2) >> 2;
+        else o[c] = cx == 0 ? cur : (cur * 3 + (int)__ldg(in + cx - 1) + 1) >> 2;
+      } else {
+        const int r0 = y >> 1;
+        const int r1 = (y & 1) ? min(r0 + 1, p.ch - 1) : max(r0 - 1, 0);
+        const uint8_t* in0 = base + (size_t)r0 * p.c_stride;
+        const uint8_t* in1 = base + (size_t)r1 * p.c_stride;
+        const int cur = (int)__ldg(in0 + cx) * 3 + (int)__ldg(in1 + cx);
+        if (x & 1) {
+          if (cx == p.cw - 1) o[c] = (cur * 4 + 7) >> 4;
+          else o[c] = (cur * 3 + (int)__ldg(in0 + cx + 1) * 3 + (int)__ldg(in1 + cx + 1) + 7) >> 4;
+        } else {
+          if (cx == 0) o[c] = (cur * 4 + 8) >> 4;
+          else o[c] = (cur * 3 + (int)__ldg(in0 + cx - 1) * 3 + (int)__ldg(in1 + cx - 1) + 8) >> 4;
+        }
+      }
+    }
+    xb = o[0] - 128;
+    xr = o[1] - 128;
+  }
   const int r = yy + ((91881 * xr + 32768) >> 16);
   const int b = yy + ((116130 * xb + 32768) >> 16);
   const int g = yy + ((-22554 * xb + 32768 - 46802 * xr) >> 16);

@@ -142,6 +142,8 @@ struct IdctPlaneParams {
 struct YccToRgbaParams {
   const uint8_t* y; const uint8_t* cb; const uint8_t* cr;
   int src_stride, w, h;
+  int hs, vs;                       // chroma subsampling (1,1) (2,1) (2,2)
+  int c_stride, cw, ch;             // chroma plane stride and real (downsampled) size
   uint8_t* dst;                     // RGBA8888
   int dst_stride;                   // pixels
 };

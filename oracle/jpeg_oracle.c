@@ -901,3 +901,88 @@ void jo_inverse(const jo_header_t* h, int16_t* const coefs[3], uint8_t* planes[3
                       planes[c] + (size_t)by * 8 * pw + bx * 8, pw);
   }
 }
+
+/* Chroma upsampling + colour conversion for RGB output of a subsampled three-component stream:
+ * libjpeg-turbo jdsample.c h2v2_fancy_upsample / h2v1_fancy_upsample (do_fancy_upsampling is the
+ * library default and the reference does not change it, jpegdecoderhelper.cpp:344-396; components
+ * whose downsampled width is <= 2 are replicated instead, jinit_upsampler), row context
+ * as jdmainct.c provides it (the row above the first and below the last real row is that row
+ * itself), then jdcolor.c ycc_rgb_convert.  planes[] are the padded planes of jo_inverse
+ * (stride wblocks*8); rgba is width*height*4 bytes, alpha 0xFF (JCS_EXT_RGBA).
+ * Returns -1 for sampling layouts other than 4:4:4, 4:2:2 (h2v1) and 4:2:0 (h2v2). */
+int jo_planes_to_rgba(const jo_header_t* h, uint8_t* const planes[3], uint8_t* rgba) {
+  const jo_frame_t* f = &h->frame;
+  if (f->ncomp != 3) return -1;
+  const int hs = f->max_h, vs = f->max_v;
+  if (f->comp[0].h_samp != hs || f->comp[0].v_samp != vs) return -1;
+  if (f->comp[1].h_samp != 1 || f->comp[1].v_samp != 1 || f->comp[2].h_samp != 1 || f->comp[2].v_samp != 1) return -1;
+  if (!((hs == 1 && vs == 1) || (hs == 2 && vs == 1) || (hs == 2 && vs == 2))) return -1;
+  const int w = f->width, ht = f->height;
+  const int cw = (w + hs - 1) / hs, ch = (ht + vs - 1) / vs; /* downsampled_width / _height */
+  const int ypw = f->comp[0].wblocks * 8;
+  uint8_t* up[2];
+  up[0] = (uint8_t*)malloc((size_t)2 * cw + 2);
+  up[1] = (uint8_t*)malloc((size_t)2 * cw + 2);
+  if (!up[0] || !up[1]) { free(up[0]); free(up[1]); return -1; }
+  for (int y = 0; y < ht; y++) {
+    for (int c = 1; c < 3; c++) {
+      const int pw = f->comp[c].wblocks * 8;
+      uint8_t* o = up[c - 1];
+      if (hs == 1) {
+        memcpy(o, planes[c] + (size_t)y * pw, (size_t)w);
+      } else if (cw <= 2) { /* jinit_upsampler: fancy only when downsampled_width > 2, else replication */
+        const uint8_t* in = planes[c] + (size_t)(y / vs) * pw;
+        for (int x = 0; x < cw; x++) o[2 * x] = o[2 * x + 1] = in[x];
+      } else if (vs == 1) { /* h2v1 fancy */
+        const uint8_t* in = planes[c] + (size_t)y * pw;
+        if (cw == 1) { o[0] = o[1] = in[0]; }
+        else {
+          int x = 0;
+          o[0] = in[0];
+          o[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
+          for (x = 1; x < cw - 1; x++) {
+            o[2 * x] = (uint8_t)((in[x] * 3 + in[x - 1] + 1) >> 2);
+            o[2 * x + 1] = (uint8_t)((in[x] * 3 + in[x + 1] + 2) >> 2);
+          }
+          o[2 * x] = (uint8_t)((in[x] * 3 + in[x - 1] + 1) >> 2);
+          o[2 * x + 1] = in[x];
+        }
+      } else { /* h2v2 fancy: nearest input row, and the next nearest above (even y) / below (odd y) */
+        const int r0 = y >> 1;
+        int r1 = (y & 1) ? r0 + 1 : r0 - 1;
+        if (r1 < 0) r1 = 0;
+        if (r1 > ch - 1) r1 = ch - 1;
+        const uint8_t* in0 = planes[c] + (size_t)r0 * pw;
+        const uint8_t* in1 = planes[c] + (size_t)r1 * pw;
+        if (cw == 1) {
+          const int s0 = in0[0] * 3 + in1[0];
+          o[0] = (uint8_t)((s0 * 4 + 8) >> 4);
+          o[1] = (uint8_t)((s0 * 4 + 7) >> 4);
+        } else {
+          int last, cur = in0[0] * 3 + in1[0], next = in0[1] * 3 + in1[1];
+          o[0] = (uint8_t)((cur * 4 + 8) >> 4);
+          o[1] = (uint8_t)((cur * 3 + next + 7) >> 4);
+          last = cur; cur = next;
+          int x;
+          for (x = 1; x < cw - 1; x++) {
+            next = in0[x + 1] * 3 + in1[x + 1];
+            o[2 * x] = (uint8_t)((cur * 3 + last + 8) >> 4);
+            o[2 * x + 1] = (uint8_t)((cur * 3 + next + 7) >> 4);
+            last = cur; cur = next;
+          }
+          o[2 * x] = (uint8_t)((cur * 3 + last + 8) >> 4);
+          o[2 * x + 1] = (uint8_t)((cur * 4 + 7) >> 4);
+        }
+      }
+    }
+    for (int x = 0; x < w; x++) {
+      uint8_t* px = rgba + ((size_t)y * w + x) * 4;
+      jo_ycc_to_rgb(planes[0][(size_t)y * ypw + x], up[0][x], up[1][x], px, px + 1, px + 2);
+      px[3] = 0xFF;
+    }
+  }
+  free(up[0]);
+  free(up[1]);
+  return 0;
+}
+

@@ -121,6 +121,8 @@ int jo_decode_coefs(const uint8_t* data, size_t size, const jo_header_t* h, int1
 
 /* Inverse stage: coefficients -> planes of wblocks*8 x hblocks*8 samples (stride wblocks*8). */
 void jo_inverse(const jo_header_t* h, int16_t* const coefs[3], uint8_t* planes[3]);
+/* fancy chroma upsampling (jdsample.c) + YCbCr->RGB (jdcolor.c) of the planes jo_inverse produced */
+int jo_planes_to_rgba(const jo_header_t* h, uint8_t* const planes[3], uint8_t* rgba);
 
 #ifdef __cplusplus
 }

@@ -180,21 +180,14 @@ uhdr_error_info_t JpegDecoderHelper::decompressImage(const void* image, size_t l
   jo_inverse(&h, coefs, planes);
 
   if (DECODE_TO_RGB_CS == mode) {
-    if (f.ncomp != 3 || f.max_h != 1 || f.max_v != 1)
-      return err(UHDR_CODEC_UNSUPPORTED_FEATURE,
-                 "oracle shim: RGB output only for 4:4:4 three-component streams");
     mPlaneHStride[0] = f.width;
     mPlaneVStride[0] = f.height;
     for (int i = 1; i < kMaxNumComponents; i++) mPlaneHStride[i] = mPlaneVStride[i] = 0;
     mResultBuffer.resize((size_t)f.width * f.height * 4);
-    const int pw = f.comp[0].wblocks * 8;
-    for (int y = 0; y < f.height; y++)
-      for (int x = 0; x < f.width; x++) {
-        uint8_t* o = &mResultBuffer[((size_t)y * f.width + x) * 4];
-        jo_ycc_to_rgb(planes[0][(size_t)y * pw + x], planes[1][(size_t)y * pw + x],
-                      planes[2][(size_t)y * pw + x], o, o + 1, o + 2);
-        o[3] = 0xFF;
-      }
+    /* jpeg_read_scanlines with JCS_EXT_RGBA: libjpeg's default fancy upsampling + jdcolor */
+    if (f.ncomp != 3 || jo_planes_to_rgba(&h, planes, mResultBuffer.data()) != 0)
+      return err(UHDR_CODEC_UNSUPPORTED_FEATURE,
+                 "oracle shim: RGB output only for 4:4:4 / 4:2:2 / 4:2:0 three-component streams");
     mOutFormat = UHDR_IMG_FMT_32bppRGBA8888;
   } else {
     size_t size = 0;

@@ -182,3 +182,53 @@ def test_uhdr_encode_packed_intents_file_bytes(gpu, oracle_libs, hdr_kind):
         for opts in ({}, {"scale": 2, "multichannel": 0}):
             a, b = mine.encode(hdr, sdr, **opts), ref.encode(hdr, sdr, **opts)
             assert a == b, ("api1", hdr_kind, w, h, opts, len(a), len(b))
+
+
+@pytest.mark.parametrize("subsampling", [2, 1, 0])
+def test_decode_rgb_of_subsampled_streams(gpu, oracle_libs, subsampling):
+    """DECODE_TO_RGB_CS of 4:2:0 / 4:2:2 / 4:4:4 streams written by a real libjpeg-turbo (Pillow):
+    libjpeg's fancy chroma upsampling + colour conversion on the device == the CPU checker (which is
+    pinned against Pillow's own decode in test_oracle_jpeg.py)."""
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    o = oracle_libs.Oracle().lib
+    for (w, h) in ((64, 48), (318, 237), (17, 9), (2, 2), (5, 3), (640, 361)):
+        rs = np.random.RandomState(w + h)
+        rgb = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        b = io.BytesIO()
+        PIL.fromarray(rgb).save(b, "JPEG", quality=90, subsampling=subsampling)
+        data = b.getvalue()
+        hd, planes = T.oracle_decode(o, data)
+        want = np.zeros((h, w, 4), np.uint8)
+        pp = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+        assert o.jo_planes_to_rgba(C.byref(hd), pp, want.ctypes.data_as(C.c_void_p)) == 0
+        for dec_mode in (1, 2):  # host and device entropy decoder
+            prev = gpu.lib.uhdr_b200_set_entropy_decoder(dec_mode)
+            try:
+                buf = np.zeros(w * h * 4 + 65536, np.uint8)
+                out = A.raw_image(-1, -1, -1, -1, 0, 0, [buf], [0])
+                cbuf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+                rc = gpu.lib.uhdr_b200_jpeg_decode(cbuf, C.c_size_t(len(data)), 1, C.byref(out), C.c_size_t(buf.size))
+            finally:
+                gpu.lib.uhdr_b200_set_entropy_decoder(prev)
+            assert rc == 0, T.gpu_err(gpu)
+            assert out.fmt == A.FMT_RGBA8888
+            got = buf[:w * h * 4].reshape(h, w, 4)
+            assert (got == want).all(), (w, h, subsampling, dec_mode, int((got != want).sum()))
+
+
+def test_uhdr_decode_sdr_output(gpu, oracle_libs):
+    """uhdr_decode with UHDR_CT_SRGB / RGBA8888: the base image through libjpeg's RGB path, gain map and
+    metadata still available -- identical to the reference decoder."""
+    if not oracle_libs.have_ref():
+        pytest.skip("reference build not available")
+    ref = T.UhdrApi(oracle_libs.Ref().lib)
+    mine = T.UhdrApi(gpu.lib)
+    for (w, h, opts) in ((640, 368, {}), (322, 182, {"scale": 2, "multichannel": 0})):
+        hdr, sdr, keep = _frames(w, h)
+        data = ref.encode(hdr, sdr, **opts)
+        pa, ga, ma, cga = mine.decode(data, A.FMT_RGBA8888, A.CT_SRGB)
+        pb, gb, mb, cgb = ref.decode(data, A.FMT_RGBA8888, A.CT_SRGB)
+        assert T.md_equal(ma, mb) and cga == cgb
+        assert (ga == gb).all()
+        assert (pa == pb).all(), (w, h, opts, int((pa != pb).sum()))

@@ -103,3 +103,24 @@ def test_420_raw_path_roundtrip_through_pillow(olib):
     assert (np.array(im)[..., 0] == pl[0][:h, :w]).all()
     # q90 of a smooth ramp stays close to the source
     assert np.abs(pl[0][:h, :w].astype(int) - buf[:w * h].reshape(h, w)).max() <= 12
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (318, 237), (17, 9), (2, 2), (1, 7), (640, 361), (33, 64)])
+@pytest.mark.parametrize("subsampling", [2, 1, 0])  # Pillow: 2 = 4:2:0, 1 = 4:2:2, 0 = 4:4:4
+def test_rgb_output_of_subsampled_streams_matches_pillow(olib, w, h, subsampling):
+    """jo_planes_to_rgba (fancy upsampling + colour conversion as libjpeg-turbo's default decode
+    path does them) against Pillow decoding the same stream to RGB."""
+    rs = np.random.RandomState(w * 131 + h * 7 + subsampling)
+    for kind in ("noise", "smooth"):
+        rgb = rs.randint(0, 256, (h, w, 3)).astype(np.uint8) if kind == "noise" else \
+            np.stack([(np.add.outer(np.arange(h) * k, np.arange(w) * (5 - k))) % 256 for k in (1, 2, 3)], -1).astype(np.uint8)
+        b = io.BytesIO()
+        PIL.fromarray(rgb).save(b, "JPEG", quality=92, subsampling=subsampling)
+        data = b.getvalue()
+        want = np.asarray(PIL.open(io.BytesIO(data)).convert("RGB"))
+        hd, planes = T.oracle_decode(olib, data)
+        out = np.zeros((h, w, 4), np.uint8)
+        pp = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+        assert olib.jo_planes_to_rgba(C.byref(hd), pp, out.ctypes.data_as(C.c_void_p)) == 0
+        assert (out[..., 3] == 255).all()
+        assert (out[..., :3] == want).all(), (w, h, subsampling, kind, int((out[..., :3] != want).sum()))
