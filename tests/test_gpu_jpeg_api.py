@@ -232,3 +232,20 @@ def test_uhdr_decode_sdr_output(gpu, oracle_libs):
         assert T.md_equal(ma, mb) and cga == cgb
         assert (ga == gb).all()
         assert (pa == pb).all(), (w, h, opts, int((pa != pb).sum()))
+
+
+def test_uhdr_decode_444_base(gpu, oracle_libs):
+    """files written from an RGBA8888 SDR intent carry a 4:4:4 base image: decode (half float, PQ
+    1010102 and SDR outputs) == the reference decoder."""
+    if not oracle_libs.have_ref():
+        pytest.skip("reference build not available")
+    ref = T.UhdrApi(oracle_libs.Ref().lib)
+    mine = T.UhdrApi(gpu.lib)
+    hdr, sdr, keep = _rgba_frames(328, 200, "pq")
+    for opts in ({}, {"scale": 2}):
+        data = ref.encode(hdr, sdr, **opts)
+        for fmt, ct in ((A.FMT_RGBAF16, A.CT_LINEAR), (A.FMT_RGBA1010102, A.CT_PQ), (A.FMT_RGBA1010102, A.CT_HLG), (A.FMT_RGBA8888, A.CT_SRGB)):
+            pa, ga, ma, cga = mine.decode(data, fmt, ct)
+            pb, gb, mb, cgb = ref.decode(data, fmt, ct)
+            assert T.md_equal(ma, mb) and cga == cgb and (ga == gb).all()
+            assert (pa == pb).all(), (opts, fmt, ct, int((pa != pb).sum()))
