@@ -1,5 +1,9 @@
 #include "codec.h"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <cmath>
 #include <cstring>
 #include <thread>
@@ -278,6 +282,7 @@ int JpegRCodec::probe(const uint8_t* data, size_t size, DecodedInfo* info) {
 int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt, float max_display_boost,
                        uhdr_raw_image_t* dest, uhdr_raw_image_t* gainmap_out, uhdr_gainmap_metadata_t* md_out) {
   (void)out_fmt;
+  PhaseTrace tr;
   ws_.rewind();
   size_t po, pl, go, gl;
   int rc = split_jpegr(data, size, &po, &pl, &go, &gl);
@@ -287,6 +292,7 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   JpegHeader ph, gh;
   rc = decode_jpeg_dev(data + po, pl, sdr_only ? 1 : 0, &sdr, &ph);  // DECODE_TO_RGB_CS / DECODE_TO_YCBCR_CS
   if (rc) return rc;
+  tr.mark("primary jpeg enqueued");
   std::vector<uint8_t> blob;
   grab_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12, &blob);
   sdr.cg = icc_read_gamut(blob.data(), blob.size());
@@ -297,6 +303,7 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
     if (rc) return rc;
     grab_marker(data + go, gh, 0xE2, "ICC_PROFILE", 12, &blob);
     map.cg = icc_read_gamut(blob.data(), blob.size());
+    tr.mark("gainmap jpeg enqueued");
   }
   if (md_out || !sdr_only) {  // :1497-1518
     if (!(gainmap_out || !sdr_only)) {
@@ -352,9 +359,12 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
     dest->planes[0] = ws_.halloc((size_t)sdr.v.w * sdr.v.h * (dest->fmt == UHDR_IMG_FMT_64bppRGBAHalfFloat ? 8 : 4));
     if (!dest->planes[0]) return E_MEM;
   }
+  tr.mark("apply enqueued");
   rc = download_image(ws_, dst, dest);
   if (rc) return rc;
-  return ws_.sync();
+  rc = ws_.sync();
+  tr.mark("pixels on the host");
+  return rc;
 }
 
 int JpegRCodec::fetch_gainmap(uhdr_raw_image_t* gainmap_out) {

@@ -366,9 +366,12 @@ static bool scan_one(const uint8_t* d, size_t n, size_t start, size_t* end) {
     const size_t l = (d[p + 2] << 8) | d[p + 3];
     if (l < 2 || p + 2 + l > n) return false;
     p += 2 + l;
-    if (m == 0xDA) {  // entropy-coded data up to the next real marker
+    if (m == 0xDA) {  // entropy-coded data up to the next real marker (hop from 0xFF to 0xFF)
       while (p + 1 < n) {
-        if (d[p] == 0xFF && d[p + 1] != 0x00 && !(d[p + 1] >= 0xD0 && d[p + 1] <= 0xD7) && d[p + 1] != 0xFF) break;
+        const uint8_t* ff = static_cast<const uint8_t*>(memchr(d + p, 0xFF, n - 1 - p));
+        if (!ff) { p = n - 1; break; }
+        p = (size_t)(ff - d);
+        if (d[p + 1] != 0x00 && !(d[p + 1] >= 0xD0 && d[p + 1] <= 0xD7) && d[p + 1] != 0xFF) break;
         p++;
       }
     }

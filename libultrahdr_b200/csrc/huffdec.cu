@@ -401,7 +401,9 @@ int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, con
   const size_t cap = size - h.scan_offset + 16;
   uint8_t* h_bits = (uint8_t*)ws.halloc(cap);
   if (!h_bits) return E_MEM;
+  PhaseTrace tr;
   const long clean = unstuff_scan(data, size, h.scan_offset, h_bits);
+  tr.mark("  unstuff");
   if (clean < 0) return declined();
   if ((size_t)clean * 8 > 0xfffffff0u - kSeqBits) return declined();
   memset(h_bits + clean, 0, 16);
@@ -465,6 +467,7 @@ int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, con
     rounds += kRoundsPerBatch;
   }
   ws.t_end();
+  tr.mark("  relaxation rounds");
   if (!converged) return declined();
 
   // 3. block offsets, then the writing pass
@@ -500,6 +503,7 @@ int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, con
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(h_flags, d_total, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  tr.mark("  write + dc");
   if (h_flags[1] || h_flags[0] < hf.total_blocks) return declined();  // let the host decoder produce the diagnosis
   g_hd_done.fetch_add(1);
   g_hd_rounds.store((unsigned long long)first_quiet);

@@ -2,6 +2,9 @@
 // and a stream.  180 GB of HBM per GPU means we never free inside a codec call: arenas are
 // rewound, not released.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <cstddef>
@@ -45,6 +48,17 @@ std::string kernel_timing_report(bool reset);
     (ws).t_end();                    \
     CUDA_TRY(_te);                   \
   } while (0)
+
+struct PhaseTrace {  // UHDR_B200_TRACE=1: wall-clock phases of one call on stderr
+  bool on = getenv("UHDR_B200_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[uhdr_b200] %-26s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 class Arena {
  public:
