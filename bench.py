@@ -525,6 +525,23 @@ def extra_measurements(lib, api, hbm):
                                             "relaxation_rounds_last": int(st1[2])},
                         "note": "uhdr_dec_set_image + uhdr_decode + uhdr_get_decoded_image through the C ABI, best of 6; "
                                 "output 64bppRGBAHalfFloat in handle-owned pinned memory"}
+            # several decoder handles in flight (one host thread each): stream in / pixels out overlap
+            nthr, per = 4, 6
+            bar = threading.Barrier(nthr + 1)
+
+            def worker():
+                timed_decode(lib, 2)   # warm-up: arenas of this thread's handles get sized and parked
+                bar.wait()
+                timed_decode(lib, per)
+            ths = [threading.Thread(target=worker) for _ in range(nthr)]
+            for t in ths:
+                t.start()
+            bar.wait()
+            t0 = time.perf_counter()
+            for t in ths:
+                t.join()
+            dtb = time.perf_counter() - t0
+            out[key]["throughput_mpix_s_4_handles"] = round(nthr * per * w * h / 1e6 / dtb, 1)
             if T.have_ref():
                 rapi, rlib = load_api(T.REF_SO)
                 dtr, _m = timed_decode(rlib, 1)

@@ -99,17 +99,22 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
   if (threadIdx.x >= 128 && threadIdx.x < 192) sunzig[threadIdx.x - 128] = (uint8_t)unzig_rt(threadIdx.x - 128);
   if (threadIdx.x < 128) {
     const int t = threadIdx.x >> 6, i = threadIdx.x & 63;
-    const unsigned d = (unsigned)P.q[t][i] << 3;
-    sdiv[t][i] = d;
-    smag[t][i] = (unsigned)((0x100000000ull + d - 1) / d);
+    sdiv[t][i] = (unsigned)P.q[t][i] << 3;
+    smag[t][i] = P.mag[t][i];
   }
   __syncthreads();
-  const Fdct8Plane& pl = P.plane[blockIdx.z];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lane_b = lane >> 3, lane_r = lane & 7;
-  const int by = blockIdx.y;
-  if (by >= pl.hblocks) return;
-  const int bx = blockIdx.x * 32 + warp * 4 + lane_b;
+  const int total_tiles = P.tile_end[P.nplanes - 1];
+  // persistent CTAs: tiles of 32 horizontally adjacent blocks, all planes in one flat index space
+#pragma unroll 1
+  for (int tidx = blockIdx.x; tidx < total_tiles; tidx += gridDim.x) {
+  const int pi = tidx < P.tile_end[0] ? 0 : (tidx < P.tile_end[1] ? 1 : 2);
+  const Fdct8Plane& pl = P.plane[pi];
+  const int local = tidx - (pi ? P.tile_end[pi - 1] : 0);
+  const int tiles_x = (pl.wblocks + 31) >> 5;
+  const int by = local / tiles_x, tx = local - by * tiles_x;
+  const int bx = tx * 32 + warp * 4 + lane_b;
   const bool live = bx < pl.wblocks;
   const int bxc = live ? bx : pl.wblocks - 1;  // dead lanes compute on a valid block, store nothing
   int* tile = tiles[warp];
@@ -166,20 +171,36 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
       block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[comp]], smag[pl.tq[comp]], sunzig, out);
     }
   }
+  }
 }
 
 }  // namespace
 
-cudaError_t launch_fdct8(const Fdct8Params& P, cudaStream_t s) {
+cudaError_t launch_fdct8(const Fdct8Params& Pin, cudaStream_t s) {
   count_launches(1);
-  int maxw = 0, maxh = 0;
-  for (int i = 0; i < P.nplanes; i++) {
-    maxw = P.plane[i].wblocks > maxw ? P.plane[i].wblocks : maxw;
-    maxh = P.plane[i].hblocks > maxh ? P.plane[i].hblocks : maxh;
+  Fdct8Params P = Pin;
+  for (int t = 0; t < 2; t++)
+    for (int i = 0; i < 64; i++) {
+      const unsigned d = (unsigned)P.q[t][i] << 3;
+      P.mag[t][i] = d ? (unsigned)((0x100000000ull + d - 1) / d) : 0u;
+    }
+  int total = 0;
+  for (int i = 0; i < 3; i++) {
+    if (i < P.nplanes) total += ((P.plane[i].wblocks + 31) / 32) * P.plane[i].hblocks;
+    P.tile_end[i] = total;
   }
-  dim3 g((maxw + 31) / 32, maxh, P.nplanes), b(256);
-  if (P.zigzag) k_fdct8<true><<<g, b, 0, s>>>(P);
-  else k_fdct8<false><<<g, b, 0, s>>>(P);
+  if (total == 0) return cudaSuccess;
+  static int resident = 0;  // CTAs of one wave (same for both instantiations: identical resources)
+  if (!resident) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fdct8<true>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    resident = per_sm * (sms > 0 ? sms : 148);
+  }
+  const int ctas = total < resident ? total : resident;
+  if (P.zigzag) k_fdct8<true><<<ctas, 256, 0, s>>>(P);
+  else k_fdct8<false><<<ctas, 256, 0, s>>>(P);
   return cudaGetLastError();
 }
 

@@ -128,6 +128,8 @@ struct Fdct8Params {
   Fdct8Plane plane[3];
   int nplanes, zigzag;
   uint16_t q[2][64];
+  unsigned mag[2][64];              // ceil(2^32 / (8*q)), filled by launch_fdct8
+  int tile_end[3];                  // cumulative count of 32-block tiles per plane, filled by launch_fdct8
 };
 
 struct IdctPlaneParams {
