@@ -164,7 +164,11 @@ static void grab_marker(const uint8_t* d, const JpegHeader& h, uint8_t id, const
     }
 }
 
-int JpegRCodec::decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* h) {
+JpegRCodec::~JpegRCodec() {
+  if (map_ready_) cudaEventDestroy(map_ready_);
+}
+
+int JpegRCodec::decode_jpeg_dev(Workspace& ws_, const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* h) {
   if (!data) return fail(E_INVALID_PARAM, "received nullptr for compressed image data");
   if (size == 0) return fail(E_INVALID_PARAM, "received bad compressed image size %zd", size);
   int rc = jpeg_read_header(data, size, h);
@@ -290,7 +294,31 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   const bool sdr_only = out_ct == UHDR_CT_SRGB;  // :1479-1481, :1520-1523: the base image as RGBA8888, no gain map applied
   DevImage sdr, map;
   JpegHeader ph, gh;
-  rc = decode_jpeg_dev(data + po, pl, sdr_only ? 1 : 0, &sdr, &ph);  // DECODE_TO_RGB_CS / DECODE_TO_YCBCR_CS
+  const bool want_map = gainmap_out || !sdr_only;  // :1484-1495
+  // both images sizeable: the gain-map JPEG goes to a helper thread with its own stream
+  const bool overlap = want_map && pl >= (256u << 10) && gl >= (256u << 10);
+  int rc2 = E_OK;
+  std::string err2;
+  std::thread helper;
+  if (overlap) {
+    if (!ws2_) {
+      ws2_.reset(new Workspace());
+      rc = ws2_->init();
+      if (rc) { ws2_.reset(); return rc; }
+      CUDA_TRY(cudaEventCreateWithFlags(&map_ready_, cudaEventDisableTiming));
+    }
+    ws2_->rewind();
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    helper = std::thread([&, dev]() {
+      if (cudaSetDevice(dev) != cudaSuccess) { rc2 = E_ERROR; err2 = "cudaSetDevice failed in the gain-map decode thread"; return; }
+      rc2 = decode_jpeg_dev(*ws2_, data + go, gl, 2, &map, &gh);  // DECODE_STREAM :1486
+      if (rc2) err2 = last_error();
+      else if (cudaEventRecord(map_ready_, ws2_->stream()) != cudaSuccess) { rc2 = E_ERROR; err2 = "cudaEventRecord failed"; }
+    });
+  }
+  rc = decode_jpeg_dev(ws_, data + po, pl, sdr_only ? 1 : 0, &sdr, &ph);  // DECODE_TO_RGB_CS / DECODE_TO_YCBCR_CS
+  if (helper.joinable()) helper.join();
   if (rc) return rc;
   tr.mark("primary jpeg enqueued");
   std::vector<uint8_t> blob;
@@ -298,15 +326,21 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   sdr.cg = icc_read_gamut(blob.data(), blob.size());
   map_pending_ = false;
   uhdr_gainmap_metadata_t md{};
-  if (gainmap_out || !sdr_only) {  // :1484-1495
-    rc = decode_jpeg_dev(data + go, gl, 2, &map, &gh);  // DECODE_STREAM :1486
-    if (rc) return rc;
+  if (want_map) {
+    if (overlap) {
+      if (rc2) { set_last_error(err2); return rc2; }
+      CUDA_TRY(cudaStreamWaitEvent(ws_.stream(), map_ready_, 0));
+      if (kernel_timing_enabled()) ws2_->sync();
+    } else {
+      rc = decode_jpeg_dev(ws_, data + go, gl, 2, &map, &gh);  // DECODE_STREAM :1486
+      if (rc) return rc;
+    }
     grab_marker(data + go, gh, 0xE2, "ICC_PROFILE", 12, &blob);
     map.cg = icc_read_gamut(blob.data(), blob.size());
     tr.mark("gainmap jpeg enqueued");
   }
   if (md_out || !sdr_only) {  // :1497-1518
-    if (!(gainmap_out || !sdr_only)) {
+    if (!want_map) {
       rc = jpeg_read_header(data + go, gl, &gh);
       if (rc) return rc;
     }

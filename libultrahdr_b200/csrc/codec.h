@@ -47,10 +47,18 @@ class JpegRCodec {
   int fetch_gainmap(uhdr_raw_image_t* gainmap_out);
 
   // JpegDecoderHelper::decompressImage equivalent producing a device image
-  int decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* hdr);
+  int decode_jpeg_dev(const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* hdr) {
+    return decode_jpeg_dev(ws_, data, size, mode, out, hdr);
+  }
+  ~JpegRCodec();
 
  private:
+  int decode_jpeg_dev(Workspace& ws, const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* hdr);
   Workspace ws_;
+  // second stream + arenas: the gain-map JPEG of a decode is processed by a helper thread while the
+  // calling thread handles the primary image (both entropy decoders alternate host and device phases)
+  std::unique_ptr<Workspace> ws2_;
+  cudaEvent_t map_ready_ = nullptr;
   bool lazy_gainmap_ = false, map_pending_ = false;
   DevImage last_map_{};
 };

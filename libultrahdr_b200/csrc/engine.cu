@@ -67,6 +67,13 @@ int alloc_dev_image(Workspace& ws, int fmt, int w, int h, int stride_align, DevI
   return E_OK;
 }
 
+// rows that are tight on both sides go as one linear copy (one DMA descriptor instead of one per row)
+static cudaError_t copy_plane_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                                    cudaMemcpyKind kind, cudaStream_t s) {
+  if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * height, kind, s);
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
+}
+
 int upload_image(Workspace& ws, const uhdr_raw_image_t& src, DevImage* out) {
   if (src.w == 0 || src.h == 0) return fail(E_INVALID_PARAM, "image has zero dimension");
   int rc = alloc_dev_image(ws, src.fmt, src.w, src.h, 64, out);
@@ -81,9 +88,9 @@ int upload_image(Workspace& ws, const uhdr_raw_image_t& src, DevImage* out) {
     int pw, ph, esz;
     fmt_plane_geom(src.fmt, src.w, src.h, i, &pw, &ph, &esz);
     if ((int)src.stride[i] < pw) pw = src.stride[i];
-    CUDA_TRY(cudaMemcpy2DAsync((void*)out->v.p[i], (size_t)out->v.stride[i] * esz, src.planes[i],
-                               (size_t)src.stride[i] * esz, (size_t)pw * esz, ph,
-                               cudaMemcpyHostToDevice, ws.stream()));
+    CUDA_TRY(copy_plane_async((void*)out->v.p[i], (size_t)out->v.stride[i] * esz, src.planes[i],
+                              (size_t)src.stride[i] * esz, (size_t)pw * esz, ph,
+                              cudaMemcpyHostToDevice, ws.stream()));
   }
   return E_OK;
 }
@@ -94,9 +101,9 @@ int download_image(Workspace& ws, const DevImage& src, uhdr_raw_image_t* dst) {
     int pw, ph, esz;
     fmt_plane_geom(src.v.fmt, src.v.w, src.v.h, i, &pw, &ph, &esz);
     if ((int)dst->stride[i] < pw) pw = dst->stride[i];
-    CUDA_TRY(cudaMemcpy2DAsync(dst->planes[i], (size_t)dst->stride[i] * esz, src.v.p[i],
-                               (size_t)src.v.stride[i] * esz, (size_t)pw * esz, ph,
-                               cudaMemcpyDeviceToHost, ws.stream()));
+    CUDA_TRY(copy_plane_async(dst->planes[i], (size_t)dst->stride[i] * esz, src.v.p[i],
+                              (size_t)src.v.stride[i] * esz, (size_t)pw * esz, ph,
+                              cudaMemcpyDeviceToHost, ws.stream()));
   }
   return E_OK;
 }

@@ -104,7 +104,7 @@ __device__ __forceinline__ float fetch_off(const float* t, unsigned mant) {  // 
 }
 
 template <bool ONEPASS, int NCH, int GAMUT /*0 none, 1 on sdr, 2 on hdr*/, bool LIMITED>
-__global__ void __launch_bounds__(256, 3) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g, const int tiles_x,
+__global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g, const int tiles_x,
                                                          const int ntiles, unsigned* __restrict__ sched, const unsigned long long nz) {
   extern __shared__ double2 smem_d[];
   GmSmem& sm = *reinterpret_cast<GmSmem*>(smem_d);
