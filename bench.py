@@ -392,6 +392,29 @@ def bench_b200(args, rank, world):
     # ---------------- CPU baseline: the reference's own code on this box's host cores --------------
     cpu = cpu_baseline(frames[:2])
 
+    # what the link itself gives on this box: plain pinned<->device copies of 256 MB, CUDA events
+    def pcie_probe():
+        try:
+            n = 256 << 20
+            hbuf = torch.empty(n, dtype=torch.uint8).pin_memory()
+            dbuf = torch.empty(n, dtype=torch.uint8, device="cuda")
+            res = {}
+            for name, (dst, src) in (("h2d_gbs", (dbuf, hbuf)), ("d2h_gbs", (hbuf, dbuf))):
+                for _ in range(2):
+                    dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    dst.copy_(src, non_blocking=True)
+                b.record()
+                torch.cuda.synchronize()
+                res[name] = round(5 * n / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+            return res
+        except Exception as e:  # noqa: BLE001
+            return {"error": repr(e)}
+    pcie = pcie_probe() if rank == 0 else {}
+
     line = {
         "metric": "MPix/s encode(API-1) at 4K",
         "value": round(value, 1), "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -403,7 +426,9 @@ def bench_b200(args, rank, world):
                    "timing": "wall clock between device-wide synchronisations around exactly K steps, max over ranks; "
                              "per-kernel times from CUDA events on the launching streams"},
         "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": int(in_bytes),
-                "d2h_bytes_per_step": int(sum(e2e_out)), "ms_per_step": round(t_e2e / args.steps * 1e3, 3)},
+                "d2h_bytes_per_step": int(sum(e2e_out)), "ms_per_step": round(t_e2e / args.steps * 1e3, 3),
+                "h2d_achieved_gbs": round(in_bytes / (t_e2e / args.steps) / 1e9, 1), "pcie_probe": pcie,
+                "bound": "pcie h2d: 37.3 MB of raw pixels enter per 4K frame, 2.3 MB of JPEG/R leave"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": roof,
@@ -629,7 +654,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=16, help="4K frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=32, help="4K frames per GPU per step (config 4: 32 per GPU)")
     ap.add_argument("--slots", type=int, default=8, help="concurrent encoder handles (host threads) per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
