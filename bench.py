@@ -81,37 +81,56 @@ def frame_descs(p010, yuv, w, h):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML every 10 ms (what nvidia-smi's
+    clocks.sm / clocks_event_reasons.* print), falling back to nvidia-smi itself."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, nvml_handle=None):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.samples = []
+        self.h = nvml_handle
+        self.samples = []   # (sm_mhz, max_mhz, [reason flags])
         self.stop_flag = False
+
+    def _nvml(self):
+        import pynvml as N
+        sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+        mx = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+        r = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        flags = [bool(r & N.nvmlClocksThrottleReasonHwSlowdown), bool(r & N.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 bool(r & N.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & N.nvmlClocksThrottleReasonSwPowerCap)]
+        self.samples.append((int(sm), int(mx), flags))
+
+    def _smi(self):
+        o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                            "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in o.strip().split(",")]
+        if len(f) >= 6 and f[0].isdigit() and f[1].isdigit():
+            self.samples.append((int(f[0]), int(f[1]), [x.lower().startswith("active") for x in f[2:6]]))
 
     def run(self):
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in o.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
+                if self.h is not None:
+                    self._nvml()
+                    time.sleep(0.01)
+                    continue
+                self._smi()
+            except Exception:  # noqa: BLE001
+                if self.h is not None:
+                    self.h = None   # NVML query failed: use nvidia-smi from here on
+                    continue
             time.sleep(0.2)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2][i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": max(s[1] for s in self.samples),
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.h is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -200,21 +219,31 @@ def load_traffic():
         return {}
 
 
-def bind_to_gpu_numa_node(torch, local):
+def nvml_handle(torch, local):
+    """NVML handle of torch's device `local` (matched by PCI address, so CUDA_VISIBLE_DEVICES is honoured)"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            try:
+                return pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+            except TypeError:
+                return pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:  # noqa: BLE001
+            return pynvml.nvmlDeviceGetHandleByIndex(local)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def bind_to_gpu_numa_node(h, local):
     """one process per GPU: run on (and first-touch pinned memory from) the CPU cores NVML names as
     closest to that GPU.  Returns a short description for the config, or the reason it was skipped."""
     try:
         import pynvml
-        pynvml.nvmlInit()
-        pr = torch.cuda.get_device_properties(local)
-        try:
-            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-            try:
-                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
-            except TypeError:
-                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
-        except Exception:  # noqa: BLE001
-            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        if h is None:
+            return "unchanged (no NVML handle)"
         ncpu = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
@@ -235,7 +264,8 @@ def bench_b200(args, rank, world):
     import __graft_entry__ as G
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
-    affinity = bind_to_gpu_numa_node(torch, local)
+    nvh = nvml_handle(torch, local)
+    affinity = bind_to_gpu_numa_node(nvh, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     so = os.path.join(ROOT, "libultrahdr_b200", "libuhdr_b200.so")
@@ -304,7 +334,7 @@ def bench_b200(args, rank, world):
     for _ in range(args.warmup):
         resident_step()
     lib.uhdr_b200_set_kernel_timing(0)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, nvh)
     sampler.start()
     barrier()
     l0 = lib.uhdr_b200_kernel_launches()
@@ -390,8 +420,6 @@ def bench_b200(args, rank, world):
     extra = extra_measurements(lib, api, hbm)
 
     # ---------------- CPU baseline: the reference's own code on this box's host cores --------------
-    cpu = cpu_baseline(frames[:2])
-
     # what the link itself gives on this box: plain pinned<->device copies of 256 MB, CUDA events
     def pcie_probe():
         try:
@@ -414,6 +442,15 @@ def bench_b200(args, rank, world):
         except Exception as e:  # noqa: BLE001
             return {"error": repr(e)}
     pcie = pcie_probe() if rank == 0 else {}
+
+    # reference on the host: all cores of the box (the GPU arm's NUMA binding is lifted for it), one
+    # frame per concurrent call, the same concurrency rule as `--impl reference`
+    ncpu_all = os.cpu_count() or 1
+    try:
+        os.sched_setaffinity(0, range(ncpu_all))
+    except OSError:
+        pass
+    cpu = cpu_baseline(frames[:max(2, min(len(frames), ncpu_all // 4))])
 
     line = {
         "metric": "MPix/s encode(API-1) at 4K",
@@ -584,7 +621,7 @@ def cpu_baseline(frames, reps=1):
     if not T.have_ref():
         return {"value": None, "unit": "MPix/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
     api, lib = load_api(T.REF_SO)
-    ncpu = os.cpu_count() or 1
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     conc = max(1, min(len(frames), ncpu // 4))  # the reference uses min(hw,4) threads per call
     descs = [frame_descs(p, y, W4K, H4K) for (p, y) in frames]
     t0 = time.perf_counter()
