@@ -6,7 +6,8 @@
 //                        CTAs with a decoupled look-back, encode into a word-aligned shared-memory
 //                        image of the CTA's segment and store it; partial boundary words travel
 //                        from CTA to CTA (details at the kernel).
-//   E2  k_ff_count / scan / k_stuff : pad the last byte with ones, insert 0x00 after every 0xFF.
+//   E2  k_stuff_lb     : pad the last byte with ones, insert 0x00 after every 0xFF (count, look-back
+//                        over 1024-word tiles and write in one launch).
 // Only the final stuffed segment (a few MB at 4K) crosses PCIe.
 #include <cstring>
 
@@ -77,22 +78,6 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
   return r;
 }
 
-// n may come from device memory (n_ptr) so dependent stages need no host round trip
-__global__ void __launch_bounds__(kScanTile) k_scan_partials(unsigned* __restrict__ partial, unsigned ntiles_max,
-                                                             unsigned n, const unsigned* n_ptr, unsigned* total_out) {
-  if (n_ptr) n = *n_ptr;
-  const unsigned ntiles = min(ntiles_max, (n + kScanTile - 1) / kScanTile);
-  unsigned carry = 0;
-  for (unsigned base = 0; base < ntiles; base += kScanTile) {
-    const unsigned i = base + threadIdx.x;
-    const unsigned v = i < ntiles ? partial[i] : 0u;
-    unsigned t;
-    const unsigned e = block_exclusive_scan(v, &t);
-    if (i < ntiles) partial[i] = carry + e;
-    carry += t;
-  }
-  if (threadIdx.x == 0 && total_out) *total_out = carry;
-}
 // ---- E1: encode, chain the bit offsets across CTAs, write the stream ------------------------------
 // One CTA = kEncBlocks consecutive blocks of the scan, taken in ticket order so that a CTA's
 // predecessors are always already running (the cross-CTA steps below spin on them).
@@ -115,6 +100,29 @@ constexpr int kTileStride = kEncBlocks + 1;
 // windows of this size, pass B running once per window.
 constexpr unsigned kSegWords = 1024;
 constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
+
+// Decoupled look-back (one warp): sum of the values of all predecessors of `idx`.  status[i] carries a
+// 2-bit flag and a 32-bit value: kFlagAgg = the value of i alone, kFlagPrefix = the inclusive prefix up
+// to i.  Predecessors are running or finished (ticket order), so the spin loops terminate.
+__device__ __forceinline__ unsigned lookback_sum(const unsigned long long* status, unsigned idx, int lane) {
+  unsigned base = 0;
+  long long hi = (long long)idx - 1;  // highest predecessor not yet accounted for
+  for (;;) {
+    const long long k = hi - lane;
+    unsigned long long st = kFlagPrefix;  // before element 0: nothing
+    if (k >= 0) {
+      do { st = *reinterpret_cast<const volatile unsigned long long*>(status + k); } while ((st & kFlagMask) == 0);
+    }
+    const bool is_prefix = (st & kFlagMask) == kFlagPrefix;
+    const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+    const int first_prefix = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor carrying an inclusive prefix
+    unsigned v = (lane <= first_prefix && k >= 0) ? (unsigned)(st & 0xffffffffu) : 0u;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    base += v;
+    if (pm) return base;
+    hi -= 32;
+  }
+}
 
 struct EncSmem {
   uint32_t tile[32 * kTileStride];
@@ -242,24 +250,7 @@ __global__ void __launch_bounds__(kEncBlocks) k_huff_encode(const HuffFrame f, c
     s_total = total;
   }
   if (j < 32 && cta > 0) {
-    unsigned base = 0;
-    long long hi = (long long)cta - 1;  // highest predecessor not yet accounted for
-    bool done = false;
-    while (!done) {
-      const long long idx = hi - j;
-      unsigned long long st = kFlagPrefix;  // before CTA 0: nothing
-      if (idx >= 0) {
-        do { st = *reinterpret_cast<volatile unsigned long long*>(status + idx); } while ((st & kFlagMask) == 0);
-      }
-      const bool is_prefix = (st & kFlagMask) == kFlagPrefix;
-      const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-      const int first_prefix = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor carrying an inclusive prefix
-      unsigned v = (j <= first_prefix && idx >= 0) ? (unsigned)(st & 0xffffffffu) : 0u;
-      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      base += v;
-      if (pm) done = true;
-      else hi -= 32;
-    }
+    const unsigned base = lookback_sum(status, cta, j);
     if (j == 0) {
       s_base = base;
       *reinterpret_cast<volatile unsigned long long*>(status + cta) = kFlagPrefix | (unsigned long long)(base + total);
@@ -343,50 +334,58 @@ __device__ __forceinline__ unsigned ff_count(unsigned v, unsigned j, unsigned to
     if (4 * j + b < total_bytes && ((v >> (24 - 8 * b)) & 0xff) == 0xff) c++;
   return c;
 }
-// persistent grid: CTAs stride over the tiles actually in use
-__global__ void __launch_bounds__(kScanTile) k_ff_count(const unsigned* __restrict__ stream, const unsigned* total_bits_ptr,
-                                                        unsigned* __restrict__ tile_ff, unsigned* __restrict__ nwords_out) {
-  const unsigned total_bits = *total_bits_ptr;
+// count + look-back + write in one launch: persistent CTAs take 1024-word tiles in ticket order
+// ctl[0] total bits (in), ctl[3] <- stuffed bytes, ctl[4] <- overflow, ctl[6] = tile tickets (zeroed by the caller)
+__global__ void __launch_bounds__(kScanTile) k_stuff_lb(const unsigned* __restrict__ stream, unsigned* ctl, unsigned long long* status,
+                                                        uint8_t* __restrict__ out, unsigned out_cap) {
+  __shared__ unsigned s_tile, s_base;
+  const unsigned total_bits = ctl[0];
   const unsigned total_bytes = (total_bits + 7) >> 3;
   const unsigned nwords = (total_bytes + 3) >> 2;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *nwords_out = nwords;
-  for (unsigned tile = blockIdx.x; tile * kScanTile < nwords; tile += gridDim.x) {
-    const unsigned j = tile * kScanTile + threadIdx.x;
-    unsigned c = 0;
-    if (j < nwords) c = ff_count(load_padded_word(stream, j, total_bits), j, total_bytes);
-    unsigned t;
-    block_exclusive_scan(c, &t);
-    if (threadIdx.x == 0) tile_ff[tile] = t;
-  }
-}
-__global__ void __launch_bounds__(kScanTile) k_stuff(const unsigned* __restrict__ stream, const unsigned* total_bits_ptr,
-                                                     const unsigned* __restrict__ tile_off, const unsigned* total_ff,
-                                                     uint8_t* __restrict__ out, unsigned out_cap, unsigned* out_bytes,
-                                                     unsigned* overflow) {
-  const unsigned total_bits = *total_bits_ptr;
-  const unsigned total_bytes = (total_bits + 7) >> 3;
-  const unsigned nwords = (total_bytes + 3) >> 2;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *out_bytes = total_bytes + *total_ff;
-    if (total_bytes + *total_ff > out_cap) *overflow = 1;
-  }
-  if (total_bytes + *total_ff > out_cap) return;
-  for (unsigned tile = blockIdx.x; tile * kScanTile < nwords; tile += gridDim.x) {
+  const unsigned ntiles = (nwords + kScanTile - 1) / kScanTile;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(ctl + 6, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= ntiles) break;
     const unsigned j = tile * kScanTile + threadIdx.x;
     unsigned v = 0, c = 0;
     if (j < nwords) {
       v = load_padded_word(stream, j, total_bits);
       c = ff_count(v, j, total_bytes);
     }
-    const unsigned e = block_exclusive_scan(c, nullptr);
+    unsigned t;
+    const unsigned e = block_exclusive_scan(c, &t);
+    if (threadIdx.x == 0) {
+      *reinterpret_cast<volatile unsigned long long*>(status + tile) = (tile == 0 ? kFlagPrefix : kFlagAgg) | t;
+      if (tile == 0) s_base = 0;
+    }
+    if (threadIdx.x < 32 && tile > 0) {
+      const unsigned b = lookback_sum(status, tile, (int)threadIdx.x);
+      if (threadIdx.x == 0) {
+        s_base = b;
+        *reinterpret_cast<volatile unsigned long long*>(status + tile) = kFlagPrefix | (unsigned long long)(b + t);
+      }
+    }
+    __syncthreads();
+    const unsigned base = s_base;
+    if (tile == ntiles - 1 && threadIdx.x == 0) {
+      ctl[3] = total_bytes + base + t;
+      if (total_bytes + base + t > out_cap) ctl[4] = 1;
+    }
     if (j < nwords) {
-      unsigned pos = 4 * j + tile_off[tile] + e;
+      unsigned pos = 4 * j + base + e;
 #pragma unroll
       for (int b = 0; b < 4; b++) {
         if (4 * j + b >= total_bytes) break;
         const uint8_t byte = (uint8_t)((v >> (24 - 8 * b)) & 0xff);
-        out[pos++] = byte;
-        if (byte == 0xff) out[pos++] = 0;
+        if (pos < out_cap) out[pos] = byte;
+        pos++;
+        if (byte == 0xff) {
+          if (pos < out_cap) out[pos] = 0;
+          pos++;
+        }
       }
     }
   }
@@ -445,15 +444,15 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   const unsigned ntiles_words = (cap_words + kScanTile - 1) / kScanTile;
   const unsigned ncta = (unsigned)((nblocks + kEncBlocks - 1) / kEncBlocks);
   // [ctl 64 B][status ncta x 8][tails ncta x 8], zeroed together
-  const size_t ctl_bytes = 64 + (size_t)ncta * 16;
-  unsigned* ctl = (unsigned*)ws.dalloc(ctl_bytes);  // [0] total_bits [1] tiles_in_use [2] total_ff [3] out_bytes [4] overflow [5] CTA tickets
+  const size_t ctl_bytes = 64 + (size_t)ncta * 16 + (size_t)ntiles_words * 8;
+  unsigned* ctl = (unsigned*)ws.dalloc(ctl_bytes);  // [0] total_bits [3] out_bytes [4] overflow [5] encoder CTA tickets [6] stuffing tile tickets
   unsigned* stream = (unsigned*)ws.dalloc(cap + 64);
-  unsigned* tile_ff = (unsigned*)ws.dalloc((size_t)ntiles_words * 4 + 64);
   job->d_scan = (uint8_t*)ws.dalloc(cap + 64);
   job->h_scan_bytes = (unsigned*)ws.halloc(64);
-  if (!stream || !tile_ff || !ctl || !job->d_scan || !job->h_scan_bytes) return E_MEM;
+  if (!stream || !ctl || !job->d_scan || !job->h_scan_bytes) return E_MEM;
   unsigned long long* status = reinterpret_cast<unsigned long long*>(ctl + 16);
   unsigned long long* tails = status + ncta;
+  unsigned long long* stuff_status = tails + ncta;
   job->d_scan_bytes = ctl + 3;
   job->scan_capacity = cap;
   cudaStream_t st = ws.stream();
@@ -468,14 +467,12 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
     }
   }
 
-  count_launches(4);
+  count_launches(2);
   ws.t_begin("huff_encode");
   k_huff_encode<<<ncta, kEncBlocks, sizeof(EncSmem), st>>>(f, books, status, tails, stream, cap_words, ctl);
   ws.t_end();
   ws.t_begin("huff_stuff");
-  k_ff_count<<<kPersistentCtas, kScanTile, 0, st>>>(stream, ctl + 0, tile_ff, ctl + 1);
-  k_scan_partials<<<1, kScanTile, 0, st>>>(tile_ff, ntiles_words, 0, ctl + 1, ctl + 2);
-  k_stuff<<<kPersistentCtas, kScanTile, 0, st>>>(stream, ctl + 0, tile_ff, ctl + 2, job->d_scan, (unsigned)cap, ctl + 3, ctl + 4);
+  k_stuff_lb<<<kPersistentCtas, kScanTile, 0, st>>>(stream, ctl, stuff_status, job->d_scan, (unsigned)cap);
   ws.t_end();
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(job->h_scan_bytes, ctl, 32, cudaMemcpyDeviceToHost, st));
