@@ -213,7 +213,6 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   f.has_user_min = cfg.min_content_boost != FLT_MIN;
   f.log2_user_max = f.has_user_max ? std::log2(cfg.max_content_boost) : 0.0f;
   f.log2_user_min = f.has_user_min ? std::log2(cfg.min_content_boost) : 0.0f;
-  TIMED(ws, "gainmap_finalize", launch_gainmap_finalize(f, ws.stream()));
   AffineParams a;
   a.gains = p.gains;
   a.minmax_f = d_minmax_f;
@@ -223,7 +222,13 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   a.nch = p.nch;
   a.dst_stride = p.dst_stride;
   a.gamma = cfg.gamma;
-  TIMED(ws, "gainmap_affine", launch_gainmap_affine(a, ws.stream()));
+  if (affine_fast_eligible(a)) {  // clamp / hints folded into the affine pass
+    count_launches(1);
+    TIMED(ws, "gainmap_affine", launch_affine_fast(a, f, ws.stream()));
+  } else {
+    TIMED(ws, "gainmap_finalize", launch_gainmap_finalize(f, ws.stream()));
+    TIMED(ws, "gainmap_affine", launch_gainmap_affine(a, ws.stream()));
+  }
   CUDA_TRY(cudaMemcpyAsync(job->h_minmax, d_minmax_f, 6 * sizeof(float), cudaMemcpyDeviceToHost, ws.stream()));
   return E_OK;
 }

@@ -306,16 +306,37 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
 // The gains and the map are walked as flat arrays, one float4 -> one packed u32 per step.  The
 // grid has a multiple of 3 threads, so with three channels every thread keeps the same channel
 // phase for its whole walk and holds (min, range, refined 1/range) per element in registers.
+// The clamp / hint step between the passes (jpegr.cpp:969-986, k_gainmap_finalize in kernels.cu) is
+// folded in: every thread derives the final min / max of its channels from the pass-1 keys (a dozen
+// instructions), thread 0 also leaves them in minmax_f for the metadata.
+__device__ __forceinline__ void finalized_minmax(const GainmapFinalizeParams& f, int c, float& mn, float& mx) {
+  const unsigned kmn = f.minmax[c < f.nch ? c : 0], kmx = f.minmax[3 + (c < f.nch ? c : 0)];
+  mn = __uint_as_float((kmn & 0x80000000u) ? (kmn & 0x7fffffffu) : ~kmn);
+  mx = __uint_as_float((kmx & 0x80000000u) ? (kmx & 0x7fffffffu) : ~kmx);
+  mn = mn < -14.3f ? -14.3f : (mn > 15.6f ? 15.6f : mn);
+  mx = mx < -14.3f ? -14.3f : (mx > 15.6f ? 15.6f : mx);
+  if (f.has_user_max) mx = fminf(mx, f.log2_user_max);
+  if (f.has_user_min) mn = fmaxf(mn, f.log2_user_min);
+  if (fabsf(mx - mn) < 1.1920928955078125e-07f) mx += 0.1f;
+}
+
 template <int NCH>
-__global__ void __launch_bounds__(192) k_affine_fast(const AffineParams p, const long long n4) {
+__global__ void __launch_bounds__(192) k_affine_fast(const AffineParams p, const GainmapFinalizeParams fin, const long long n4) {
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthr = (long long)gridDim.x * blockDim.x;
+  if (t0 < 3) {
+    float a, b;
+    finalized_minmax(fin, (int)t0, a, b);
+    fin.minmax_f[t0] = a;
+    fin.minmax_f[3 + t0] = b;
+  }
   float mn[4], d[4], rc[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const int c = NCH == 3 ? (int)((t0 * 4 + j) % 3) : 0;
-    mn[j] = p.minmax_f[c];
-    d[j] = p.minmax_f[3 + c] - mn[j];
+    float mxj;
+    finalized_minmax(fin, c, mn[j], mxj);
+    d[j] = mxj - mn[j];
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d[j]));
     rc[j] = __fmaf_rn(r, __fmaf_rn(-d[j], r, 1.0f), r);
@@ -338,6 +359,54 @@ __global__ void __launch_bounds__(192) k_affine_fast(const AffineParams p, const
     }
     o[f] = w;
   }
+}
+
+// ---- convertYuv 4:2:0 (transformYuv420, gainmapmath.cpp:686-726), in place -----------------------
+// thread = 4x2 luma samples + their two chroma pairs (32-bit / 16-bit accesses instead of single
+// bytes), the per-pixel products and sums on packed pairs.  Same operand order as k_yuv_convert.
+__global__ void __launch_bounds__(256) k_yuv420_fast(const YuvConvParams p, const unsigned long long nz) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
+  if (x >= p.w || y >= p.h) return;
+  unsigned* py0 = reinterpret_cast<unsigned*>(p.p[0] + (size_t)y * p.stride[0] + x);
+  unsigned* py1 = reinterpret_cast<unsigned*>(p.p[0] + (size_t)(y + 1) * p.stride[0] + x);
+  uint16_t* pu = reinterpret_cast<uint16_t*>(p.p[1] + (size_t)(y >> 1) * p.stride[1] + (x >> 1));
+  uint16_t* pv = reinterpret_cast<uint16_t*>(p.p[2] + (size_t)(y >> 1) * p.stride[2] + (x >> 1));
+  const unsigned yw[2] = {*py0, *py1};
+  const unsigned uu = *pu, vv = *pv;
+  const V2 k255i = bc(1 / 255.0f), k255 = bc(255.0f), khalf = bc(0.5f);
+  const V2 m0 = bc(p.m[0]), m3 = bc(p.m[3]), m6 = bc(p.m[6]);
+  unsigned oy[2] = {0, 0}, ou = 0, ov = 0;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const float u = (float)((int)((uu >> (8 * k)) & 0xff) - 128) * (1 / 255.0f);
+    const float v = (float)((int)((vv >> (8 * k)) & 0xff) - 128) * (1 / 255.0f);
+    const V2 um1 = bc(u * p.m[1]), vm2 = bc(v * p.m[2]), um4 = bc(u * p.m[4]), vm5 = bc(v * p.m[5]);
+    const V2 um7 = bc(u * p.m[7]), vm8 = bc(v * p.m[8]);
+    float cu[4], cv[4];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const V2 yy = vmul(v2((float)((yw[r] >> (16 * k)) & 0xff), (float)((yw[r] >> (16 * k + 8)) & 0xff)), k255i, nz);
+      const V2 ny = vadd(vadd(vmul(yy, m0, nz), um1), vm2);
+      un(vadd(vadd(vmul(yy, m3, nz), um4), vm5), cu[2 * r], cu[2 * r + 1]);
+      un(vadd(vadd(vmul(yy, m6, nz), um7), vm8), cv[2 * r], cv[2 * r + 1]);
+      float t0, t1;
+      un(vadd(vmul(ny, k255, nz), khalf), t0, t1);
+      unsigned b0, b1;
+      un(vtrunc_bits(v2(fminf(fmaxf(t0, 0.0f), 255.0f), fminf(fmaxf(t1, 0.0f), 255.0f))), b0, b1);
+      oy[r] |= ((b0 & 0xff) << (16 * k)) | ((b1 & 0xff) << (16 * k + 8));
+    }
+    const float su = (((cu[0] + cu[1]) + cu[2]) + cu[3]) * 0.25f;   // / 4.0f: exact either way
+    const float sv = (((cv[0] + cv[1]) + cv[2]) + cv[3]) * 0.25f;
+    const float tu = fminf(fmaxf(su * 255.0f + 128.0f + 0.5f, 0.0f), 255.0f);
+    const float tv = fminf(fmaxf(sv * 255.0f + 128.0f + 0.5f, 0.0f), 255.0f);
+    ou |= (__float_as_uint(__fadd_rz(tu, 8388608.0f)) & 0xff) << (8 * k);
+    ov |= (__float_as_uint(__fadd_rz(tv, 8388608.0f)) & 0xff) << (8 * k);
+  }
+  *py0 = oy[0];
+  *py1 = oy[1];
+  *pu = (uint16_t)ou;
+  *pv = (uint16_t)ov;
 }
 
 // host: table of the log2 kernel, uploaded once per device
@@ -419,13 +488,24 @@ bool affine_fast_eligible(const AffineParams& p) {
   if (((size_t)p.map_w * p.map_h * p.nch) & 3) return false;
   return !(((size_t)p.gains & 15) || ((size_t)p.dst & 3));
 }
-cudaError_t launch_affine_fast(const AffineParams& p, cudaStream_t s) {
+cudaError_t launch_affine_fast(const AffineParams& p, const GainmapFinalizeParams& fin, cudaStream_t s) {
   const long long n4 = (long long)p.map_w * p.map_h * p.nch / 4;
   long long ctas = (n4 + 192 * 4 - 1) / (192 * 4);
   if (ctas > 148 * 10) ctas = 148 * 10;
   if (ctas < 1) ctas = 1;
-  if (p.nch == 3) k_affine_fast<3><<<(unsigned)ctas, 192, 0, s>>>(p, n4);
-  else k_affine_fast<1><<<(unsigned)ctas, 192, 0, s>>>(p, n4);
+  if (p.nch == 3) k_affine_fast<3><<<(unsigned)ctas, 192, 0, s>>>(p, fin, n4);
+  else k_affine_fast<1><<<(unsigned)ctas, 192, 0, s>>>(p, fin, n4);
+  return cudaGetLastError();
+}
+
+bool yuv420_fast_eligible(const YuvConvParams& p) {
+  if (p.fmt != F_YUV420 || (p.w & 3) || (p.h & 1)) return false;
+  if ((p.stride[0] & 3) || (p.stride[1] & 1) || (p.stride[2] & 1)) return false;
+  return !(((size_t)p.p[0] & 3) || ((size_t)p.p[1] & 1) || ((size_t)p.p[2] & 1));
+}
+cudaError_t launch_yuv420_fast(const YuvConvParams& p, cudaStream_t s) {
+  dim3 b(64, 4), g((p.w / 4 + 63) / 64, (p.h / 2 + 3) / 4);
+  k_yuv420_fast<<<g, b, 0, s>>>(p, kNegZero2);
   return cudaGetLastError();
 }
 

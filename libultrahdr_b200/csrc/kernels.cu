@@ -1035,10 +1035,6 @@ cudaError_t launch_gainmap_finalize(const GainmapFinalizeParams& p, cudaStream_t
   return cudaGetLastError();
 }
 cudaError_t launch_gainmap_affine(const AffineParams& p, cudaStream_t s) {
-  if (affine_fast_eligible(p)) {
-    COUNT_LAUNCH();
-    return launch_affine_fast(p, s);
-  }
   const int row_bytes = p.map_w * p.nch;
   dim3 b(256, 1);
   dim3 g((row_bytes / 4 + 1 + 255) / 256, p.map_h);
@@ -1091,6 +1087,10 @@ cudaError_t launch_rgb_to_ycc(const RgbToYccParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s) {
+  if (yuv420_fast_eligible(p)) {
+    COUNT_LAUNCH();
+    return launch_yuv420_fast(p, s);
+  }
   dim3 b(32, 8);
   const int f = p.fmt == F_YUV420 ? 2 : 1;
   k_yuv_convert<<<grid2(p.w / f, p.h / f, b), b, 0, s>>>(p);

@@ -161,13 +161,16 @@ bool apply_fast_eligible(const ApplyParams& p);
 cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaStream_t s);
 // fast path (gainmap_fast.cu): P010 + YUV420, scale 1
 bool affine_fast_eligible(const AffineParams& p);
-cudaError_t launch_affine_fast(const AffineParams& p, cudaStream_t s);
+// finalize (clamp / hints) + affine in one launch; also writes fin.minmax_f
+cudaError_t launch_affine_fast(const AffineParams& p, const GainmapFinalizeParams& fin, cudaStream_t s);
 bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass);
 cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, unsigned* sched, cudaStream_t s);
 cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream_t s);
 cudaError_t launch_powf_probe(const float* d_in, float y, float* d_out, int n, cudaStream_t s);
 cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s);
 cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s);
+bool yuv420_fast_eligible(const YuvConvParams& p);
+cudaError_t launch_yuv420_fast(const YuvConvParams& p, cudaStream_t s);
 cudaError_t launch_rgb_to_ycc(const RgbToYccParams& p, cudaStream_t s);
 cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s);
 cudaError_t launch_fdct8(const Fdct8Params& p, cudaStream_t s);
