@@ -110,3 +110,52 @@ def test_device_entropy_decoder_4k_against_reference(gpu, oracle_libs):
     assert T.md_equal(ma, mb) and cga == cgb
     assert (ga == gb).all()
     assert (pa == pb).all(), int((pa != pb).sum())
+
+
+def test_corrupted_scans_agree_with_host_decoder(gpu, oracle_libs):
+    """bytes flipped inside the entropy-coded segments: whatever the host decoder makes of the stream
+    (an error, or garbage pixels), the device decoder must make the same of it -- and never hang."""
+    api = T.UhdrApi(gpu.lib)
+    lib = gpu.lib
+    w, h = 640, 368
+    hb = T.make_p010(w, h, "smooth")
+    sb = T.make_yuv420(w, h, "smooth")
+    hdr, k1 = A.p010_image(hb, w, h, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+    sdr, k2 = A.yuv420_image(sb, w, h, A.CG_BT709)
+    good = bytearray(api.encode(hdr, sdr))
+    sos = [i for i in range(len(good) - 1) if good[i] == 0xFF and good[i + 1] == 0xDA]
+    assert len(sos) == 2
+    rs = np.random.RandomState(99)
+
+    def run(data, mode):
+        prev = lib.uhdr_b200_set_entropy_decoder(mode)
+        try:
+            dec = C.c_void_p(lib.uhdr_create_decoder())
+            buf = np.frombuffer(bytes(data), np.uint8).copy()
+            ci = A.CompressedImage(buf.ctypes.data, len(data), len(data), -1, -1, -1)
+            e = lib.uhdr_dec_set_image(dec, C.byref(ci))
+            if e.error_code == 0:
+                e = lib.uhdr_decode(dec)
+            px = None
+            if e.error_code == 0:
+                d = lib.uhdr_get_decoded_image(dec).contents
+                px = np.ctypeslib.as_array(C.cast(d.planes[0], C.POINTER(C.c_uint8)), (d.h, d.stride[0] * 8)).copy()
+            lib.uhdr_release_decoder(dec)
+            return e.error_code, px
+        finally:
+            lib.uhdr_b200_set_entropy_decoder(prev)
+
+    for t in range(24):
+        bad = bytearray(good)
+        s = sos[t % 2]
+        lo = s + 16
+        hi = (sos[1] - 64) if t % 2 == 0 else (len(bad) - 8)
+        for _ in range(1 + t % 3):
+            pos = int(rs.randint(lo, hi))
+            v = int(rs.randint(0, 255))
+            bad[pos] = v if v != 0xFF else 0x7F   # keep marker structure intact: only code bits change
+        rc_h, px_h = run(bad, 1)
+        rc_d, px_d = run(bad, 2)
+        assert rc_h == rc_d, (t, rc_h, rc_d)
+        if rc_h == 0:
+            assert (px_h == px_d).all(), t
