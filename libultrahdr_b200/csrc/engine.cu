@@ -261,9 +261,10 @@ void finish_gainmap_metadata(const GainmapJob& job, uhdr_gainmap_metadata_t* md)
 }
 
 // ------------------------------------------------------------------------------------------------
-int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
+int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map_in,
                       const uhdr_gainmap_metadata_t& md, int out_ct, float max_display_boost,
                       DevImage* dst) {
+  DevImage map = map_in;
   // validation, jpegr.cpp:1538-1614
   if (!dst || !dst->v.p[0])
     return fail(E_INVALID_PARAM, "apply gainmap method received nullptr for destination image or plane pointer");
@@ -292,9 +293,21 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
   p.gamut_identity = ident ? 1 : 0;
   {  // aspect-ratio check :1652-1671
     const float pa = (float)sdr.v.w / sdr.v.h, ga = (float)map.v.w / map.v.h;
-    if (std::fabs(pa - ga) / pa > 0.01f)
-      return fail(E_UNSUPPORTED, "gainmap aspect ratio differs from the primary image by more than 1%%; "
-                  "the bicubic gainmap resize (editorhelper.cpp:100-146) is outside the B200 hot path");
+    if (std::fabs(pa - ga) / pa > 0.01f) {  // resize_image(gainmap_img, sdr_intent->w, sdr_intent->h)
+      DevImage rs;
+      int rc = alloc_dev_image(ws, map.v.fmt, sdr.v.w, sdr.v.h, 64, &rs);
+      if (rc) return fail(E_UNSUPPORTED, "encountered error while resizing the gainmap image from %ux%u to %ux%u", map.v.w,
+                          map.v.h, sdr.v.w, sdr.v.h);
+      ResizeMapParams r;
+      r.src = (const uint8_t*)map.v.p[0];
+      r.src_w = map.v.w; r.src_h = map.v.h; r.src_stride = map.v.stride[0];
+      r.bpp = map.v.fmt == F_RGBA8888 ? 4 : (map.v.fmt == F_RGB888 ? 3 : 1);
+      r.dst = (uint8_t*)rs.v.p[0];
+      r.dst_w = sdr.v.w; r.dst_h = sdr.v.h; r.dst_stride = rs.v.stride[0];
+      TIMED(ws, "resize_gainmap", launch_resize_map(r, ws.stream()));
+      rs.cg = map.cg; rs.ct = map.ct; rs.range = map.range;
+      map = rs;
+    }
   }
   const float scale = (float)sdr.v.w / map.v.w;
   int srnd = (int)std::roundf(scale);

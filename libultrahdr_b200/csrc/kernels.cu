@@ -1081,6 +1081,42 @@ __global__ void __launch_bounds__(256) k_rgb_to_ycc(const RgbToYccParams p) {
   p.dst[1][o] = (uint8_t)__float2int_rz(uu);
   p.dst[2][o] = (uint8_t)__float2int_rz(vv);
 }
+// resize_image (editorhelper.cpp:100-146): the reference's "bicubic" is a cubic Bernstein blend of the
+// four neighbours p0 (x0,y0), p1 (x0+1,y0), p2 (x0,y0+1), p3 (x0+1,y0+1) weighted by the *horizontal*
+// fraction only, evaluated in double; pixels go through getPixel / putPixel of the map's format.
+__global__ void __launch_bounds__(256) k_resize_map(const ResizeMapParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= p.dst_w) return;
+  const double scale_x = (double)p.src_w / p.dst_w, scale_y = (double)p.src_h / p.dst_h;
+  const double ori_x = x * scale_x, ori_y = y * scale_y;
+  const int p0x = min(max((int)floor(ori_x), 0), p.src_w - 1), p0y = min(max((int)floor(ori_y), 0), p.src_h - 1);
+  const int p1x = min(max(p0x + 1, 0), p.src_w - 1), p2y = min(max(p0y + 1, 0), p.src_h - 1);
+  const double fx = ori_x - p0x;
+  const double w0 = (1 - fx) * (1 - fx) * (1 - fx), w1 = 3 * fx * (1 - fx) * (1 - fx), w2 = 3 * fx * fx * (1 - fx), w3 = fx * fx * fx;
+  const int nch = p.bpp == 1 ? 1 : 3;
+  unsigned outv[3] = {0, 0, 0};
+  for (int c = 0; c < nch; c++) {
+    auto px = [&](int xx, int yy) -> float {
+      const unsigned b = __ldg(p.src + ((size_t)yy * p.src_stride + xx) * p.bpp + c);
+      // getYuv400Pixel multiplies by (1 / 255.0f), getRgb888Pixel / getRgba8888Pixel divide by 255.0f
+      return p.bpp == 1 ? (float)b * (1 / 255.0f) : (float)b / 255.0f;
+    };
+    const double a0 = px(p0x, p0y), a1 = px(p1x, p0y), a2 = px(p0x, p2y), a3 = px(p1x, p2y);
+    float v = (float)(w0 * a0 + w1 * a1 + w2 * a2 + w3 * a3);
+    v = v * 255.0f;
+    v = v + 0.5f;
+    v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
+    outv[c] = (unsigned)__float2int_rz(v);
+  }
+  uint8_t* d = p.dst + ((size_t)y * p.dst_stride + x) * p.bpp;
+  if (p.bpp == 4) *reinterpret_cast<unsigned*>(d) = outv[0] | (outv[1] << 8) | (outv[2] << 16) | (255u << 24);
+  else for (int c = 0; c < nch; c++) d[c] = (uint8_t)outv[c];
+}
+cudaError_t launch_resize_map(const ResizeMapParams& p, cudaStream_t s) {
+  k_resize_map<<<dim3((p.dst_w + 255) / 256, p.dst_h), 256, 0, s>>>(p);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
 cudaError_t launch_rgb_to_ycc(const RgbToYccParams& p, cudaStream_t s) {
   k_rgb_to_ycc<<<dim3((p.w + 255) / 256, p.h), 256, 0, s>>>(p);
   COUNT_LAUNCH();

@@ -102,6 +102,13 @@ struct RgbToYccParams {             // convert_raw_input_to_ycbcr, gainmapmath.c
   float k[5];                       // yr, yg, yb, cb, cr
 };
 
+struct ResizeMapParams {            // resize_image, editorhelper.cpp:100-146 (gain map to the base image's size)
+  const uint8_t* src;
+  int src_w, src_h, src_stride, bpp;   // bpp 1 (Y400) / 3 (RGB888) / 4 (RGBA8888)
+  uint8_t* dst;
+  int dst_w, dst_h, dst_stride;
+};
+
 struct DctPlaneParams {             // forward: samples -> coefficients
   const uint8_t* src;               // plane (or packed RGB when rgb_comp >= 0)
   int src_stride;                   // elements per row (pixels for RGB)
@@ -172,6 +179,7 @@ cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s);
 bool yuv420_fast_eligible(const YuvConvParams& p);
 cudaError_t launch_yuv420_fast(const YuvConvParams& p, cudaStream_t s);
 cudaError_t launch_rgb_to_ycc(const RgbToYccParams& p, cudaStream_t s);
+cudaError_t launch_resize_map(const ResizeMapParams& p, cudaStream_t s);
 cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s);
 cudaError_t launch_fdct8(const Fdct8Params& p, cudaStream_t s);
 cudaError_t launch_idct_dequant(const IdctPlaneParams& p, cudaStream_t s);

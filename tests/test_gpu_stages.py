@@ -276,3 +276,30 @@ def test_device_log2_equals_libm(gpu, oracle_libs):
     assert gpu.lib.uhdr_b200_probe_log2(x.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), x.size) == 0
     bad = got.view(np.uint32) != want.view(np.uint32)
     assert bad.sum() == 0, (int(bad.sum()), x[bad][:5], got[bad][:5], want[bad][:5])
+
+
+def test_apply_resized_gainmap(gpu, oracle_libs):
+    """gain map whose aspect ratio differs from the base image by more than 1 %: applyGainMap first
+    resizes it (resize_image, editorhelper.cpp:100-146, double-precision cubic blend).  Compared with
+    the reference's own code (the C restatement does not cover this branch)."""
+    if not oracle_libs.have_ref():
+        pytest.skip("reference build not available")
+    ref = oracle_libs.Ref()
+    w, h = 256, 128
+    sb = T.make_yuv420(w, h, "noise")
+    sdr, k2 = A.yuv420_image(sb, w, h, A.CG_BT709)
+    md = A.GainmapMetadata()
+    for i, (mx, mn) in enumerate(((8.0, 0.5), (6.0, 0.7), (4.0, 1.0))):
+        md.max_content_boost[i], md.min_content_boost[i], md.gamma[i] = mx, mn, 1.0
+        md.offset_sdr[i] = md.offset_hdr[i] = 1.0 / 64
+    md.hdr_capacity_min, md.hdr_capacity_max, md.use_base_cg = 1.0, 8.0, 0
+    rs = np.random.RandomState(21)
+    for (mw, mh, ch) in ((100, 80, 4), (64, 64, 3), (77, 13, 1), (300, 100, 4)):
+        gm = rs.randint(0, 256, (mh, mw, ch)).astype(np.uint8)
+        if ch == 4:
+            gm[..., 3] = 255
+        gi = T.gm_image(np.ascontiguousarray(gm), A.CG_BT2100)
+        for ct in (A.CT_LINEAR, A.CT_PQ):
+            a = gpu.apply(sdr, gi, md, ct)
+            b = ref.apply(sdr, gi, md, ct)
+            assert (a == b).all(), (mw, mh, ch, ct, int((a != b).sum()))
