@@ -1,4 +1,4 @@
-// Forward block stage, second generation: 8 lanes per 8x8 block instead of one thread per block.
+// Forward block stage: 8 lanes per 8x8 block.
 //   pass 1: lane (b, r) loads row r of block b (8 bytes; RGB: 24 bytes + jccolor.c conversion),
 //           runs the 1-D islow DCT on it in registers and parks the row in a warp-private,
 //           bank-padded shared-memory tile
@@ -8,8 +8,7 @@
 //   store : lane (b, j) writes 16 bytes; a warp writes 4 blocks = 512 contiguous bytes
 // A warp owns 4 horizontally adjacent blocks, a CTA 32; all planes of an image go in ONE launch
 // (grid.z), the three components of an RGB888 gain map are produced from one read of the pixels.
-// Arithmetic is the same integer arithmetic as k_fdct_quant (kernels.cu) / libjpeg-turbo's
-// jfdctint.c + jcdctmgr.c: bit-exact.
+// Arithmetic is libjpeg-turbo's jccolor.c / jfdctint.c / jcdctmgr.c integer arithmetic: bit-exact.
 #include "kernels.cuh"
 
 namespace uhdr_b200 {

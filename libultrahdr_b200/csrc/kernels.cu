@@ -729,139 +729,7 @@ __global__ void __launch_bounds__(256) k_yuv_convert(const YuvConvParams p) {
 #define FX_3_072711026 25172
 #define DESCALE(x, n) (((x) + (1 << ((n)-1))) >> (n))
 
-template <int PASS>
-__device__ __forceinline__ void fdct8(int& d0, int& d1, int& d2, int& d3, int& d4, int& d5, int& d6,
-                                      int& d7) {
-  int tmp0 = d0 + d7, tmp7 = d0 - d7, tmp1 = d1 + d6, tmp6 = d1 - d6;
-  int tmp2 = d2 + d5, tmp5 = d2 - d5, tmp3 = d3 + d4, tmp4 = d3 - d4;
-  int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
-  constexpr int sh = PASS == 0 ? C_BITS - P1_BITS : C_BITS + P1_BITS;
-  if (PASS == 0) {
-    d0 = (tmp10 + tmp11) << P1_BITS;
-    d4 = (tmp10 - tmp11) << P1_BITS;
-  } else {
-    d0 = DESCALE(tmp10 + tmp11, P1_BITS);
-    d4 = DESCALE(tmp10 - tmp11, P1_BITS);
-  }
-  int z1 = (tmp12 + tmp13) * FX_0_541196100;
-  d2 = DESCALE(z1 + tmp13 * FX_0_765366865, sh);
-  d6 = DESCALE(z1 + tmp12 * (-FX_1_847759065), sh);
-  z1 = tmp4 + tmp7;
-  int z2 = tmp5 + tmp6, z3 = tmp4 + tmp6, z4 = tmp5 + tmp7;
-  int z5 = (z3 + z4) * FX_1_175875602;
-  tmp4 *= FX_0_298631336;
-  tmp5 *= FX_2_053119869;
-  tmp6 *= FX_3_072711026;
-  tmp7 *= FX_1_501321110;
-  z1 *= -FX_0_899976223;
-  z2 *= -FX_2_562915447;
-  z3 *= -FX_1_961570560;
-  z4 *= -FX_0_390180644;
-  z3 += z5;
-  z4 += z5;
-  d7 = DESCALE(tmp4 + z1 + z3, sh);
-  d5 = DESCALE(tmp5 + z2 + z4, sh);
-  d3 = DESCALE(tmp6 + z2 + z3, sh);
-  d1 = DESCALE(tmp7 + z1 + z4, sh);
-}
-
-__device__ __forceinline__ int rgb_to_ycc_comp(int comp, int r, int g, int b) {  // jccolor.c
-  constexpr int HALF = 1 << 15, OFF = 128 << 16;
-  if (comp == 0) return (19595 * r + 38470 * g + 7471 * b + HALF) >> 16;
-  if (comp == 1) return (-11059 * r - 21709 * g + 32768 * b + OFF + HALF - 1) >> 16;
-  return (32768 * r - 27439 * g - 5329 * b + OFF + HALF - 1) >> 16;
-}
-
-// zigzag position -> natural index; after full unrolling the loads fold to constants
-__device__ __forceinline__ constexpr int zig(int i) {
-  constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
-                         41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
-                         30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-  return t[i];
-}
-
-// one thread = one 8x8 block; a warp covers 32 horizontally adjacent blocks so every row load of
-// the warp is one contiguous 256-byte segment.
-template <bool ZIGZAG>
-__global__ void __launch_bounds__(128) k_fdct_quant(const DctPlaneParams p) {
-  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y;
-  // divisor 8*Q and its reciprocal: floor(a / d) == umulhi(a, ceil(2^32 / d)) exactly while
-  // a * d < 2^32 (here a < 2^17 after the 8x-scaled islow DCT of 8-bit samples, d <= 2040)
-  __shared__ unsigned sd[64], sm[64];
-  if (threadIdx.x < 64) {
-    const unsigned d = (unsigned)p.q[threadIdx.x] << 3;
-    sd[threadIdx.x] = d;
-    sm[threadIdx.x] = (unsigned)((0x100000000ull + d - 1) / d);
-  }
-  __syncthreads();
-  if (bx >= p.wblocks) return;
-  int v[64];
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    int y = by * 8 + r;
-    bool fill_row = false;
-    if (y >= p.h) {
-      if (p.pad_mode == 1) y = p.h - 1;
-      else fill_row = true;
-    }
-    if (p.rgb_comp < 0) {
-      const uint8_t* row = p.src + (size_t)y * p.src_stride + bx * 8;
-      if (fill_row) {
-#pragma unroll
-        for (int c = 0; c < 8; c++) v[r * 8 + c] = p.fill - 128;
-      } else if (bx * 8 + 8 <= p.w && ((((size_t)row) & 7) == 0)) {
-        const uint2 q = __ldg((const uint2*)row);
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          v[r * 8 + c] = (int)((q.x >> (8 * c)) & 0xff) - 128;
-          v[r * 8 + 4 + c] = (int)((q.y >> (8 * c)) & 0xff) - 128;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          int x = bx * 8 + c;
-          int s;
-          if (x < p.w) s = __ldg(row + c);
-          else s = p.pad_mode == 1 ? (int)__ldg(p.src + (size_t)y * p.src_stride + p.w - 1) : p.fill;
-          v[r * 8 + c] = s - 128;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        int x = min(bx * 8 + c, p.w - 1);  // scanline path replicates edges (jcsample.c)
-        const uint8_t* px = p.src + ((size_t)y * p.src_stride + x) * 3;
-        v[r * 8 + c] = rgb_to_ycc_comp(p.rgb_comp, __ldg(px), __ldg(px + 1), __ldg(px + 2)) - 128;
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 8; r++)
-    fdct8<0>(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5],
-             v[r * 8 + 6], v[r * 8 + 7]);
-#pragma unroll
-  for (int c = 0; c < 8; c++)
-    fdct8<1>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
-  // quantise: sign * ((|x| + d/2) / d), d = 8*Q
-  int16_t* out = p.coefs + ((size_t)by * p.wblocks + bx) * 64;
-#pragma unroll
-  for (int i = 0; i < 64; i += 8) {
-    unsigned w[4];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int src = ZIGZAG ? zig(i + k) : i + k;
-      const unsigned d = sd[src];
-      const int t = v[src];
-      const unsigned a = (unsigned)abs(t) + (d >> 1);
-      int qv = (int)__umulhi(a, sm[src]);
-      qv = t < 0 ? -qv : qv;
-      if (k & 1) w[k >> 1] |= ((unsigned)qv & 0xffff) << 16;
-      else w[k >> 1] = (unsigned)qv & 0xffff;
-    }
-    *(uint4*)(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
+// (the forward block stage lives in fdct8.cu)
 
 __device__ __forceinline__ void idct8(int d0, int d1, int d2, int d3, int d4, int d5, int d6, int d7,
                                       int o[8], int shift) {
@@ -1130,14 +998,6 @@ cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s) {
   dim3 b(32, 8);
   const int f = p.fmt == F_YUV420 ? 2 : 1;
   k_yuv_convert<<<grid2(p.w / f, p.h / f, b), b, 0, s>>>(p);
-  COUNT_LAUNCH();
-  return cudaGetLastError();
-}
-cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s) {
-  dim3 b(128, 1);
-  dim3 g((p.wblocks + 127) / 128, p.hblocks);
-  if (p.zigzag_out) k_fdct_quant<true><<<g, b, 0, s>>>(p);
-  else k_fdct_quant<false><<<g, b, 0, s>>>(p);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }

@@ -109,19 +109,6 @@ struct ResizeMapParams {            // resize_image, editorhelper.cpp:100-146 (g
   int dst_w, dst_h, dst_stride;
 };
 
-struct DctPlaneParams {             // forward: samples -> coefficients
-  const uint8_t* src;               // plane (or packed RGB when rgb_comp >= 0)
-  int src_stride;                   // elements per row (pixels for RGB)
-  int w, h;                         // real plane size
-  int wblocks, hblocks;
-  int pad_mode;                     // 0: rows >= h read as `fill`; 1: replicate edges
-  int fill;
-  int rgb_comp;                     // -1 plane; 0/1/2 = Y/Cb/Cr computed from RGB888
-  int zigzag_out;                   // 1: store each block in zigzag order (device entropy coder)
-  uint16_t q[64];                   // natural order
-  int16_t* coefs;                   // [hblocks*wblocks][64]
-};
-
 struct Fdct8Plane {                 // one launch covers every plane of an image (fdct8.cu)
   const uint8_t* src;
   int stride;                       // bytes per row for planes, pixels per row for RGB888
@@ -180,7 +167,6 @@ bool yuv420_fast_eligible(const YuvConvParams& p);
 cudaError_t launch_yuv420_fast(const YuvConvParams& p, cudaStream_t s);
 cudaError_t launch_rgb_to_ycc(const RgbToYccParams& p, cudaStream_t s);
 cudaError_t launch_resize_map(const ResizeMapParams& p, cudaStream_t s);
-cudaError_t launch_fdct_quant(const DctPlaneParams& p, cudaStream_t s);
 cudaError_t launch_fdct8(const Fdct8Params& p, cudaStream_t s);
 cudaError_t launch_idct_dequant(const IdctPlaneParams& p, cudaStream_t s);
 cudaError_t launch_ycc_to_rgba(const YccToRgbaParams& p, cudaStream_t s);

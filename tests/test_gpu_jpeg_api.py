@@ -249,3 +249,33 @@ def test_uhdr_decode_444_base(gpu, oracle_libs):
             pb, gb, mb, cgb = ref.decode(data, fmt, ct)
             assert T.md_equal(ma, mb) and cga == cgb and (ga == gb).all()
             assert (pa == pb).all(), (opts, fmt, ct, int((pa != pb).sum()))
+
+
+def test_encode_batch_matches_single_encodes(gpu, oracle_libs):
+    """uhdr_b200_encode_batch (N frames pipelined over several streams / worker threads) returns,
+    frame by frame, the bytes uhdr_encode returns for the same inputs."""
+    lib = gpu.lib
+    mine = T.UhdrApi(lib)
+    w, h, n = 640, 368, 7
+    keeps, hdrs, sdrs = [], (A.RawImage * n)(), (A.RawImage * n)()
+    singles = []
+    for i in range(n):
+        hb = T.make_p010(w, h, "smooth", seed=100 + i)
+        sb = T.make_yuv420(w, h, "smooth", seed=200 + i)
+        hdr, k1 = A.p010_image(hb, w, h, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+        sdr, k2 = A.yuv420_image(sb, w, h, A.CG_BT709)
+        keeps.append((hb, sb, k1, k2))
+        hdrs[i], sdrs[i] = hdr, sdr
+        singles.append(mine.encode(hdr, sdr))
+    cap = w * h * 6 + 65536
+    bufs = [np.zeros(cap, np.uint8) for _ in range(n)]
+    outs = (A.CompressedImage * n)()
+    for i in range(n):
+        outs[i] = A.CompressedImage(bufs[i].ctypes.data, 0, cap, -1, -1, -1)
+    cfg = A.default_gm_config()
+    for streams in (1, 3):
+        rc = lib.uhdr_b200_encode_batch(n, hdrs, sdrs, C.byref(cfg), 95, outs, streams)
+        assert rc == 0, T.gpu_err(gpu)
+        for i in range(n):
+            got = bytes(bufs[i][:outs[i].data_sz])
+            assert got == singles[i], (streams, i, len(got), len(singles[i]))
