@@ -662,12 +662,15 @@ UHDR_API int uhdr_b200_encode_batch(int n, const uhdr_raw_image_t* hdr, const uh
   std::vector<int> rcs(streams, 0);
   std::vector<std::string> errs(streams);
   std::vector<std::thread> th;
+  // `pool` is thread_local: a worker naming it would see its own (empty) instance, so the workers get
+  // the caller's codecs through a plain pointer
+  std::unique_ptr<JpegRCodec>* codecs = pool.data();
   for (int s = 0; s < streams; s++)
-    th.emplace_back([&, s]() {
+    th.emplace_back([&, s, codecs]() {
       cudaSetDevice(dev);
       for (int i = s; i < n; i += streams) {
         size_t sz = 0;
-        int rc = pool[s]->encode_host(hdr[i], sdr ? &sdr[i] : nullptr, *cfg, base_quality, nullptr, 0,
+        int rc = codecs[s]->encode_host(hdr[i], sdr ? &sdr[i] : nullptr, *cfg, base_quality, nullptr, 0,
                                       (uint8_t*)out[i].data, out[i].capacity, &sz);
         out[i].data_sz = sz;
         if (rc) { rcs[s] = rc; errs[s] = last_error(); return; }
