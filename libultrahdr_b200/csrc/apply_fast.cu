@@ -12,6 +12,10 @@
 //   * floatToHalf: values are clamped to [0, 10000/203] first; there the reference's bit routine
 //     equals one packed hardware conversion per two channels (see pack_half4)
 //   * LUT indices come out of the float mantissa (add 2^23 toward zero) instead of the conversion unit
+// k_apply_lin1 (scale 1 -> linear half float, the 8K decode configuration) adds: a persistent grid
+// with atomic tile tickets, register prefetch of the next tile, packed fp32 pairs (packed_f32.cuh),
+// clamping on the packed half bit patterns and 256-bit stores; k_apply_fast covers the other
+// integer scales and the PQ / HLG outputs.
 #include <cuda_fp16.h>
 
 #include "kernels.cuh"

@@ -2,12 +2,17 @@
 // configuration the API-0/API-1 benchmarks exercise: P010 HDR intent (HLG or PQ) + YUV 4:2:0 SDR
 // intent, map scale 1.  Arithmetic, operand order and tables are those of the generic kernels in
 // kernels.cu; what changes is the instruction count:
-//   * one thread = a 4x2 pixel tile (chroma terms of both images computed once per 2x2)
+//   * persistent CTAs, 256x8-pixel tiles handed out through an atomic ticket; one thread = a 4x2
+//     pixel tile (chroma terms of both images computed once per 2x2)
+//   * every fp32 multiply / add on packed pairs (two horizontally adjacent pixels, packed_f32.cuh)
 //   * inverse-OETF tables in shared memory in "doubled" form so that the reference's LUT index
-//     int32(double(x*(N-1)) + 0.5) becomes one multiply, one convert and one mask
+//     int32(double(x*(N-1)) + 0.5) becomes one multiply, one add toward zero (the index is read out
+//     of the mantissa) and one mask
 //   * computeGain's double-precision log2 of a float quotient through a 128-entry table + degree-8
 //     polynomial in fp64 (error < 2^-50 before narrowing to float, like glibc's / CUDA's log2,
-//     ~6x fewer instructions than the library routine)
+//     ~6x fewer instructions than the library routine), coefficients as constant-bank operands,
+//     widenings done with integer ops; the IEEE division without its range-check slow path
+// Also here: the affine pass (min/max finalisation folded in) and the 4:2:0 convertYuv kernel.
 #include <cmath>
 #include <mutex>
 
