@@ -64,18 +64,6 @@ __device__ __forceinline__ double log2_core(float q, const double2* __restrict__
   return fma(p, r, kd + t.y);
 }
 
-// a / b for positive normal operands whose quotient is far from the float range limits: the
-// compiler's own division sequence (reciprocal estimate, one Newton step, residual correction)
-// without its out-of-range check and slow-path call.  Rounds like IEEE division in that domain.
-__device__ __forceinline__ float div_pos(float a, float b) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-  const float e = __fmaf_rn(-b, r, 1.0f);
-  r = __fmaf_rn(r, e, r);
-  float q = __fmul_rn(a, r);
-  const float rem = __fmaf_rn(-b, q, a);
-  return __fmaf_rn(r, rem, q);
-}
 
 // ---- shared memory ------------------------------------------------------------------------------
 struct GmSmem {

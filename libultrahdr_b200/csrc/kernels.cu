@@ -917,6 +917,7 @@ cudaError_t launch_apply_gainmap(const ApplyParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s) {
+  if (tonemap_fast_eligible(p)) return launch_tonemap_fast(p, s);
   dim3 b(32, 8);
   const int f = p.dst_fmt == F_YUV420 ? 2 : 1;
   k_tonemap<<<grid2((p.hdr.w + f - 1) / f, (p.hdr.h + f - 1) / f, b), b, 0, s>>>(p);

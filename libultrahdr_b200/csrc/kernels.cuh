@@ -162,6 +162,8 @@ cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, unsigne
 cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream_t s);
 cudaError_t launch_powf_probe(const float* d_in, float y, float* d_out, int n, cudaStream_t s);
 cudaError_t launch_tonemap(const TonemapParams& p, cudaStream_t s);
+bool tonemap_fast_eligible(const TonemapParams& p);
+cudaError_t launch_tonemap_fast(const TonemapParams& p, cudaStream_t s);
 cudaError_t launch_yuv_convert(const YuvConvParams& p, cudaStream_t s);
 bool yuv420_fast_eligible(const YuvConvParams& p);
 cudaError_t launch_yuv420_fast(const YuvConvParams& p, cudaStream_t s);
