@@ -9,8 +9,6 @@
 //     divisor (max_hdr) and the constant divisors (headroom^2, 1.772, 1.402) reuse one refined
 //     reciprocal
 // srgbOetf stays glibc's powf restated in fp64 (powf_glibc.cuh): it is what the remaining time is.
-#include <cstdlib>
-
 #include "kernels.cuh"
 #include "packed_f32.cuh"
 #include "powf_glibc.cuh"
@@ -139,8 +137,6 @@ cudaError_t launch_tm(const TonemapParams& p, int tiles_x, int ntiles, cudaStrea
 }  // namespace
 
 bool tonemap_fast_eligible(const TonemapParams& p) {
-  static const bool enabled = getenv("UHDR_B200_TONEMAP_FAST") != nullptr;  // off until validated on hardware
-  if (!enabled) return false;
   if (p.hdr.fmt != F_P010 || p.dst_fmt != F_YUV420 || !p.normalized) return false;
   if (p.hdr_ct != CT_HLG && p.hdr_ct != CT_PQ) return false;
   if ((p.hdr.w & 3) || (p.hdr.h & 1)) return false;
