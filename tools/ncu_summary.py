@@ -38,7 +38,7 @@ KEEP = {
 # ncu kernel-name substring -> bench.py kernel name
 BENCH_NAMES = (("k_gainmap_fast<0", "gainmap_pass1"), ("k_gainmap_fast<1", "gainmap_onepass"),
                ("k_gainmap_affine", "gainmap_affine"), ("k_affine_fast", "gainmap_affine"), ("k_fdct8", "fdct_quant"), ("k_huff_encode", "huff_encode"),
-               ("k_apply_lin1", "apply_gainmap"), ("k_tonemap", "tonemap"), ("k_yuv_convert", "yuv_convert"))
+               ("k_apply_lin1", "apply_gainmap"), ("k_tonemap", "tonemap"), ("k_yuv420_fast", "yuv_convert"), ("k_yuv_convert", "yuv_convert"))
 
 
 def to_bytes(v, unit):
