@@ -98,7 +98,10 @@ char* take_parked(bool pinned, int device, size_t bytes, size_t* got) {
     if (v[i].size < bytes || (!pinned && v[i].device != device)) continue;
     if (best < 0 || v[i].size < v[best].size) best = i;
   }
-  if (best < 0 || v[best].size > 4 * bytes + ((size_t)64 << 20)) return nullptr;  // do not burn a huge block on a small need
+  // a handle of the same kind asks for the same block sizes in the same order, so near-exact matches
+  // are the rule; handing a much larger block to a small request would only force the next large
+  // request back to the driver
+  if (best < 0 || v[best].size > bytes + bytes / 4 + ((size_t)1 << 20)) return nullptr;
   char* base = v[best].base;
   *got = v[best].size;
   g_parked_bytes[pinned ? 1 : 0] -= v[best].size;
