@@ -587,14 +587,24 @@ def extra_measurements(lib, api, hbm):
                                             "relaxation_rounds_last": int(st1[2])},
                         "note": "uhdr_dec_set_image + uhdr_decode + uhdr_get_decoded_image through the C ABI, best of 6; "
                                 "output 64bppRGBAHalfFloat in handle-owned pinned memory"}
-            # several decoder handles in flight (one host thread each): stream in / pixels out overlap
+            # several decoder handles in flight, one host thread each, every handle reused through
+            # uhdr_reset_decoder (its arenas stay sized): stream in / pixels out of different images overlap
             nthr, per = 4, 6
             bar = threading.Barrier(nthr + 1)
 
-            def worker():
-                timed_decode(lib, 2)   # warm-up: arenas of this thread's handles get sized and parked
-                bar.wait()
-                timed_decode(lib, per)
+            def worker(data=data, w=w):
+                buf = np.frombuffer(data, np.uint8).copy()
+                ci = A.CompressedImage(buf.ctypes.data, len(data), len(data), -1, -1, -1)
+                dec = C.c_void_p(lib.uhdr_create_decoder())
+                for it in range(2 + per):
+                    if it == 2:
+                        bar.wait()
+                    lib.uhdr_reset_decoder(dec)
+                    assert lib.uhdr_dec_set_image(dec, C.byref(ci)).error_code == 0
+                    e = lib.uhdr_decode(dec)
+                    assert e.error_code == 0, e.detail
+                    assert lib.uhdr_get_decoded_image(dec).contents.w == w
+                lib.uhdr_release_decoder(dec)
             ths = [threading.Thread(target=worker) for _ in range(nthr)]
             for t in ths:
                 t.start()
