@@ -417,7 +417,8 @@ def bench_b200(args, rank, world):
                 "peak_kind": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "how": "CUDA events around every launch on its stream, %d steps with one encoder in flight" % args.steps}
 
-    extra = extra_measurements(lib, api, hbm)
+    # single-GPU side measurements (config 2 / config 3 kernels, decode): N = 1 only
+    extra = extra_measurements(lib, api, hbm) if world == 1 else {"note": "side measurements run at N=1 only"}
 
     # ---------------- CPU baseline: the reference's own code on this box's host cores --------------
     # what the link itself gives on this box: plain pinned<->device copies of 256 MB, CUDA events
@@ -450,7 +451,10 @@ def bench_b200(args, rank, world):
         os.sched_setaffinity(0, range(ncpu_all))
     except OSError:
         pass
-    cpu = cpu_baseline(frames[:max(2, min(len(frames), ncpu_all // 4))])
+    if world == 1:
+        cpu = cpu_baseline(frames[:max(2, min(len(frames), ncpu_all // 4))])
+    else:
+        cpu = {"value": None, "unit": "MPix/s", "cores": 0, "kind": "reference", "sample": "timed at N=1 only"}
 
     line = {
         "metric": "MPix/s encode(API-1) at 4K",
