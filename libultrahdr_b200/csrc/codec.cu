@@ -168,7 +168,7 @@ JpegRCodec::~JpegRCodec() {
   if (map_ready_) cudaEventDestroy(map_ready_);
 }
 
-int JpegRCodec::decode_jpeg_dev(Workspace& ws_, const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* h) {
+int JpegRCodec::decode_jpeg_dev(Workspace& ws, const uint8_t* data, size_t size, int mode, DevImage* out, JpegHeader* h) {
   if (!data) return fail(E_INVALID_PARAM, "received nullptr for compressed image data");
   if (size == 0) return fail(E_INVALID_PARAM, "received bad compressed image size %zd", size);
   int rc = jpeg_read_header(data, size, h);
@@ -190,7 +190,7 @@ int JpegRCodec::decode_jpeg_dev(Workspace& ws_, const uint8_t* data, size_t size
   int strides[3] = {0, 0, 0};
   for (int c = 0; c < f.ncomp; c++) {
     strides[c] = f.comp[c].wblocks * 8;
-    planes[c] = (uint8_t*)ws_.dalloc((size_t)strides[c] * f.comp[c].hblocks * 8);
+    planes[c] = (uint8_t*)ws.dalloc((size_t)strides[c] * f.comp[c].hblocks * 8);
     if (!planes[c]) return E_MEM;
   }
   // entropy decoding: on the device (huffdec.cu) for anything sizeable, else -- or when the device
@@ -199,21 +199,21 @@ int JpegRCodec::decode_jpeg_dev(Workspace& ws_, const uint8_t* data, size_t size
   bool on_device = dec_mode == 2 || (dec_mode == 0 && size - h->scan_offset >= (64u << 10));
   if (on_device) {
     int16_t* d_coefs[3] = {nullptr, nullptr, nullptr};
-    rc = jpeg_entropy_decode_dev(ws_, data, size, *h, d_coefs);
+    rc = jpeg_entropy_decode_dev(ws, data, size, *h, d_coefs);
     if (rc == kHuffDecFallback) on_device = false;
     else if (rc) return rc;
-    else rc = jpeg_idct_dev(ws_, *h, d_coefs, planes, strides);
+    else rc = jpeg_idct_dev(ws, *h, d_coefs, planes, strides);
     if (on_device && rc) return rc;
   }
   if (!on_device) {
     int16_t* h_coefs[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < f.ncomp; c++) {
-      h_coefs[c] = (int16_t*)ws_.halloc(f.blocks(c) * 128);
+      h_coefs[c] = (int16_t*)ws.halloc(f.blocks(c) * 128);
       if (!h_coefs[c]) return E_MEM;
     }
     rc = jpeg_host_decode_coefs(data, size, *h, h_coefs);
     if (rc) return rc;
-    rc = jpeg_inverse_dev(ws_, *h, h_coefs, planes, strides);
+    rc = jpeg_inverse_dev(ws, *h, h_coefs, planes, strides);
     if (rc) return rc;
   }
   if (mode == 1) {
@@ -222,7 +222,7 @@ int JpegRCodec::decode_jpeg_dev(Workspace& ws_, const uint8_t* data, size_t size
         f.comp[1].v_samp != 1 || f.comp[2].h_samp != 1 || f.comp[2].v_samp != 1)
       return fail(E_UNSUPPORTED, "RGB output is implemented for 4:4:4, 4:2:2 and 4:2:0 JPEG input");
     DevImage rgba;
-    rc = alloc_dev_image(ws_, F_RGBA8888, f.width, f.height, 1, &rgba);
+    rc = alloc_dev_image(ws, F_RGBA8888, f.width, f.height, 1, &rgba);
     if (rc) return rc;
     YccToRgbaParams p;
     p.y = planes[0]; p.cb = planes[1]; p.cr = planes[2];
@@ -236,7 +236,7 @@ int JpegRCodec::decode_jpeg_dev(Workspace& ws_, const uint8_t* data, size_t size
     p.ch = (f.height + f.max_v - 1) / f.max_v;
     p.dst = (uint8_t*)rgba.v.p[0];
     p.dst_stride = rgba.v.stride[0];
-    TIMED(ws_, "ycc_to_rgba", launch_ycc_to_rgba(p, ws_.stream()));
+    TIMED(ws, "ycc_to_rgba", launch_ycc_to_rgba(p, ws.stream()));
     rgba.range = UHDR_CR_FULL_RANGE;
     *out = rgba;
     out->cg = out->ct = -1;
