@@ -626,6 +626,29 @@ def extra_measurements(lib, api, hbm):
             del p8, y8, data
     except Exception as e:  # noqa: BLE001
         out["error"] = repr(e)
+    # config 5: generateGainMap (two-pass, multichannel, scale 1) at 4K over transfer x HDR gamut, SDR
+    # intent BT.709: kernel times of pass 1 + affine pass by CUDA events.  The gamut decides which side
+    # carries the 3x3 conversion (jpegr.cpp:607-638), the transfer which inverse-OETF table is staged.
+    try:
+        gpu = T.Gpu()
+        p010, yuv = make_frame(W4K, H4K, 11)
+        sdr, _ks = A.yuv420_image(yuv, W4K, H4K, A.CG_BT709)
+        lib.uhdr_b200_set_kernel_timing(1)
+        sweep = {}
+        for ct_name, ct in (("hlg", A.CT_HLG), ("pq", A.CT_PQ)):
+            for cg_name, cg in (("bt709", A.CG_BT709), ("p3", A.CG_P3), ("bt2100", A.CG_BT2100)):
+                hdr, _kh = A.p010_image(p010, W4K, H4K, cg, ct, A.CR_LIMITED)
+                gpu.generate(sdr, hdr)
+                kernel_report(lib)
+                for _ in range(3):
+                    gpu.generate(sdr, hdr)
+                kt = kernel_report(lib)
+                ms = sum(kt[k][1] / kt[k][0] for k in ("gainmap_pass1", "gainmap_affine") if k in kt)
+                sweep[ct_name + "_" + cg_name] = {"kernels_ms": round(ms, 4), "mpix_s": round(MPIX_4K / (ms * 1e-3), 1)}
+        lib.uhdr_b200_set_kernel_timing(0)
+        out["config5_generate_gainmap_4k"] = sweep
+    except Exception as e:  # noqa: BLE001
+        out["config5_error"] = repr(e)
     return out
 
 
