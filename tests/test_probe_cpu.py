@@ -86,3 +86,41 @@ def test_probe_rejects_what_the_reference_rejects(oracle_libs):
     # truncated streams (the reference build used as checker crashes on these): must be refused cleanly
     for bad in (good[:200], good[:second] + good[second:second + 40], good[:3], good[:second + 2]):
         assert "error" in _probe(mine_lib, bad), len(bad)
+
+
+def test_probe_survives_mutated_streams(oracle_libs):
+    """byte flips, truncations and deletions all over a valid file: the host-side parsers (container
+    split, marker walk, ISO 21496-1 metadata, ICC gamut) must answer with a verdict, never crash."""
+    if not oracle_libs.have_ref():
+        pytest.skip("reference build not available (used here only to write the seed file)")
+    import os
+    mine_lib = C.CDLL(os.path.join(oracle_libs.ROOT, "libultrahdr_b200", "libuhdr_b200.so"))
+    ref = T.UhdrApi(oracle_libs.Ref().lib)
+    w, h = 64, 64
+    hb = T.make_p010(w, h, "smooth")
+    sb = T.make_yuv420(w, h, "smooth")
+    hdr, k1 = A.p010_image(hb, w, h, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+    sdr, k2 = A.yuv420_image(sb, w, h, A.CG_BT709)
+    good = bytearray(ref.encode(hdr, sdr))
+    n = len(good)
+    rs = np.random.RandomState(20240607)
+    verdicts = [0, 0]
+    for it in range(600):
+        bad = bytearray(good)
+        mode = it % 4
+        if mode == 0:
+            for _ in range(rs.randint(1, 6)):
+                bad[rs.randint(0, n)] = rs.randint(0, 256)
+        elif mode == 1:
+            bad = bad[:rs.randint(1, n)]
+        elif mode == 2:
+            a = rs.randint(0, n)
+            del bad[a:min(n, a + rs.randint(1, 64))]
+        else:
+            a = rs.randint(0, min(n, 1200))   # marker / metadata region
+            for _ in range(rs.randint(1, 4)):
+                bad[min(len(bad) - 1, a + rs.randint(0, 32))] = rs.randint(0, 256)
+        if not bad:
+            continue
+        verdicts["error" in _probe(mine_lib, bytes(bad))] += 1
+    assert verdicts[0] > 0 and verdicts[1] > 0, verdicts
