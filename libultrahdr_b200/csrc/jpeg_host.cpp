@@ -328,6 +328,25 @@ int jpeg_stream_pieces(const JpegEncodeJob& job, const void* icc, size_t icc_siz
 }
 
 // ---- decoder: marker parser (jdmarker.c subset) + Huffman decoder (jdhuff.c semantics) ----------
+// jdhuff.c jpeg_make_d_derived_tbl's sanity checks, applied to the tables a scan refers to: the
+// code lengths must describe a prefix code, and a DC table may only hold categories 0..15
+// (libjpeg: JERR_BAD_HUFF_TABLE, "Bogus Huffman table definition")
+static bool huff_table_ok(const uint8_t bits[17], const uint8_t* vals, bool is_dc) {
+  long code = 0;
+  int total = 0;
+  for (int len = 1; len <= 16; len++) {
+    code += bits[len];
+    total += bits[len];
+    if (bits[len] && code >= (1L << len)) return false;   // the all-ones code of a length is reserved
+    code <<= 1;
+  }
+  if (total > 256) return false;
+  if (is_dc)
+    for (int i = 0; i < total; i++)
+      if (vals[i] > 15) return false;
+  return true;
+}
+
 int jpeg_read_header(const uint8_t* d, size_t n, JpegHeader* h) {
   *h = JpegHeader();
   memset(h->bits, 0, sizeof h->bits);
@@ -409,6 +428,9 @@ int jpeg_read_header(const uint8_t* d, size_t n, JpegHeader* h) {
         h->ac_sel[c] = s[2 + 2 * c] & 15;
         if (h->dc_sel[c] > 1 || h->ac_sel[c] > 1 || !h->have_tbl[0][h->dc_sel[c]] || !h->have_tbl[1][h->ac_sel[c]])
           return fail(E_ERROR, "Huffman table was not defined");
+        if (!huff_table_ok(h->bits[0][h->dc_sel[c]], h->vals[0][h->dc_sel[c]], true) ||
+            !huff_table_ok(h->bits[1][h->ac_sel[c]], h->vals[1][h->ac_sel[c]], false))
+          return fail(E_ERROR, "Bogus Huffman table definition");
       }
       h->scan_offset = p + len;
       return E_OK;
@@ -509,7 +531,7 @@ int jpeg_host_decode_coefs(const uint8_t* data, size_t size, const JpegHeader& h
             int16_t* blk = (bx < k.wblocks && by < k.hblocks) ? coefs[c] + ((size_t)by * k.wblocks + bx) * 64 : sink;
             memset(blk, 0, 128);
             const int s = decode_symbol(bs, dt);
-            if (s) pred[c] += sign_extend(bs.take(s), s);
+            if (s) pred[c] = (int)((unsigned)pred[c] + (unsigned)sign_extend(bs.take(s), s));  // wraps like the int16 it feeds
             blk[0] = (int16_t)pred[c];
             for (int z = 1; z < 64; z++) {
               const int rs = decode_symbol(bs, at);
