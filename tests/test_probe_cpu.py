@@ -124,3 +124,37 @@ def test_probe_survives_mutated_streams(oracle_libs):
             continue
         verdicts["error" in _probe(mine_lib, bytes(bad))] += 1
     assert verdicts[0] > 0 and verdicts[1] > 0, verdicts
+
+
+def test_host_parsers_under_sanitizers(oracle_libs, tmp_path):
+    """the same mutations, 6000 of them, through the host sources compiled with AddressSanitizer and
+    UndefinedBehaviorSanitizer (tests/cpp/host_parsers_fuzz.cpp): no report may appear."""
+    if not oracle_libs.have_ref():
+        pytest.skip("reference build not available (used here only to write the seed file)")
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = oracle_libs.ROOT
+    ref = T.UhdrApi(oracle_libs.Ref().lib)
+    w, h = 64, 64
+    hb = T.make_p010(w, h, "smooth")
+    sb = T.make_yuv420(w, h, "smooth")
+    hdr, k1 = A.p010_image(hb, w, h, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+    sdr, k2 = A.yuv420_image(sb, w, h, A.CG_BT709)
+    seed = tmp_path / "seed.jpg"
+    seed.write_bytes(ref.encode(hdr, sdr))
+    exe = str(tmp_path / "fuzz")
+    csrc = os.path.join(root, "libultrahdr_b200", "csrc")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I", csrc,
+           "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+           os.path.join(root, "tests", "cpp", "host_parsers_fuzz.cpp"), os.path.join(csrc, "container.cpp"),
+           os.path.join(csrc, "jpeg_host.cpp"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("toolchain without sanitizer runtimes")
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe, str(seed), "7", "6000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "harness done" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+    assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-2000:]
