@@ -72,6 +72,10 @@ UHDR_EXTERN int uhdr_b200_jpeg_decode(const void* data, size_t size, int mode, u
 UHDR_EXTERN void uhdr_b200_set_kernel_timing(int on);
 UHDR_EXTERN int uhdr_b200_kernel_timing_report(char* buf, size_t cap, int reset);
 UHDR_EXTERN int uhdr_b200_enc_rearm(uhdr_codec_private_t* enc);
+/* Released handles park their device / pinned arena blocks in a process-wide cache (at most 8 GiB of
+ * HBM and 4 GiB of pinned host memory) so that the reference's create / run / release per image pattern
+ * does not pay cudaHostAlloc every time.  This returns the cache to the driver; result = bytes freed. */
+UHDR_EXTERN size_t uhdr_b200_trim_cache(void);
 /* Where JpegDecoderHelper's entropy decoding (libjpeg-turbo jdhuff.c behind jpegdecoderhelper.cpp:397-411)
  * runs: 0 = automatic (device for scans of 64 KiB and more), 1 = host, 2 = device whenever the stream
  * allows it.  Process-wide; returns the previous setting.  Results are identical either way. */

@@ -527,6 +527,7 @@ UHDR_API int uhdr_b200_kernel_timing_report(char* buf, size_t cap, int reset) {
   memcpy(buf, r.c_str(), r.size() + 1);
   return (int)r.size();
 }
+UHDR_API size_t uhdr_b200_trim_cache(void) { return trim_parked_blocks(); }
 UHDR_API int uhdr_b200_enc_rearm(uhdr_codec_private_t* enc) {
   Encoder* h = as<Encoder>(enc);
   if (!h) return fail(E_INVALID_PARAM, "received nullptr for uhdr codec instance");
@@ -657,7 +658,7 @@ UHDR_API int uhdr_b200_encode_batch(int n, const uhdr_raw_image_t* hdr, const uh
   while ((int)pool.size() < streams) {
     pool.emplace_back(new JpegRCodec());
     int rc = pool.back()->init();
-    if (rc) return rc;
+    if (rc) { pool.pop_back(); return rc; }
   }
   std::vector<int> rcs(streams, 0);
   std::vector<std::string> errs(streams);
@@ -667,7 +668,7 @@ UHDR_API int uhdr_b200_encode_batch(int n, const uhdr_raw_image_t* hdr, const uh
   std::unique_ptr<JpegRCodec>* codecs = pool.data();
   for (int s = 0; s < streams; s++)
     th.emplace_back([&, s, codecs]() {
-      cudaSetDevice(dev);
+      if (cudaSetDevice(dev) != cudaSuccess) { rcs[s] = E_ERROR; errs[s] = "cudaSetDevice failed in a batch worker"; return; }
       for (int i = s; i < n; i += streams) {
         size_t sz = 0;
         int rc = codecs[s]->encode_host(hdr[i], sdr ? &sdr[i] : nullptr, *cfg, base_quality, nullptr, 0,

@@ -64,7 +64,9 @@ int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b
     sdr = ycc;
   }
   if (sdr_in) {
-    rc = convert_yuv_dev(ws_, &sdr, sdr.cg, UHDR_CG_DISPLAY_P3);  // :277
+    // :277.  `sdr` may be the caller's resident input (uhdr_enc_set_raw_image uploads once, the handle
+    // can be encoded again): never convert it in place
+    rc = convert_yuv_dev(ws_, &sdr, sdr.cg, UHDR_CG_DISPLAY_P3, /*in_place=*/false);
     if (rc) return rc;
   }
   rc = block_stage(ws_, sdr, base_quality, &base_jpeg);

@@ -419,8 +419,10 @@ int tonemap_dev(Workspace& ws, const DevImage& hdr, DevImage* sdr) {
   return E_OK;
 }
 
-int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg) {
-  // jpegr.cpp:436-518
+int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg, bool in_place) {
+  // jpegr.cpp:436-518.  The reference converts its own deep copy of the intent in place; a device
+  // image that must survive the call (resident encoder inputs) is converted into workspace scratch
+  // and *img is redirected to it.
   if (src_cg < 0 || src_cg > 2) return fail(E_INVALID_PARAM, "Unrecognized src color gamut %d", src_cg);
   if (dst_cg < 0 || dst_cg > 2) return fail(E_INVALID_PARAM, "Unrecognized dest color gamut %d", dst_cg);
   if (src_cg == dst_cg) return E_OK;
@@ -428,10 +430,20 @@ int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg) {
     return fail(E_UNSUPPORTED, "No implementation available for performing gamut conversion for color format %d", img->v.fmt);
   YuvConvParams p;
   yuv_matrix(src_cg, dst_cg, p.m);
-  for (int i = 0; i < 3; i++) {
-    p.p[i] = (uint8_t*)img->v.p[i];
-    p.stride[i] = img->v.stride[i];
+  DevImage dst = *img;
+  if (!in_place) {
+    int rc = alloc_dev_image(ws, img->v.fmt, img->v.w, img->v.h, 64, &dst);
+    if (rc) return rc;
+    dst.cg = img->cg; dst.ct = img->ct; dst.range = img->range;
+    dst.v.full_range = img->v.full_range;
   }
+  for (int i = 0; i < 3; i++) {
+    p.p[i] = (const uint8_t*)img->v.p[i];
+    p.stride[i] = img->v.stride[i];
+    p.d[i] = (uint8_t*)dst.v.p[i];
+    p.dstride[i] = dst.v.stride[i];
+  }
+  *img = dst;
   p.w = img->v.w;
   p.h = img->v.h;
   p.fmt = img->v.fmt;

@@ -42,7 +42,8 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
                       const uhdr_gainmap_metadata_t& md, int out_ct, float max_display_boost,
                       DevImage* dst /* allocated by caller, fmt F16 / 1010102 */);
 int tonemap_dev(Workspace& ws, const DevImage& hdr, DevImage* sdr /* allocated by caller */);
-int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg);
+// in_place = false: the result goes to workspace scratch and *img is redirected to it (the source stays intact)
+int convert_yuv_dev(Workspace& ws, DevImage* img, int src_cg, int dst_cg, bool in_place = true);
 // convert_raw_input_to_ycbcr for RGBA8888 / RGB888 (gainmapmath.cpp:1440-1467): new YCbCr 4:4:4 device image
 int rgb_to_ycbcr_dev(Workspace& ws, const DevImage& rgb, DevImage* out);
 

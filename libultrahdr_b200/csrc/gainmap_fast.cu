@@ -361,12 +361,10 @@ __global__ void __launch_bounds__(256) k_yuv420_fast(const YuvConvParams p, cons
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
   if (x >= p.w || y >= p.h) return;
-  unsigned* py0 = reinterpret_cast<unsigned*>(p.p[0] + (size_t)y * p.stride[0] + x);
-  unsigned* py1 = reinterpret_cast<unsigned*>(p.p[0] + (size_t)(y + 1) * p.stride[0] + x);
-  uint16_t* pu = reinterpret_cast<uint16_t*>(p.p[1] + (size_t)(y >> 1) * p.stride[1] + (x >> 1));
-  uint16_t* pv = reinterpret_cast<uint16_t*>(p.p[2] + (size_t)(y >> 1) * p.stride[2] + (x >> 1));
-  const unsigned yw[2] = {*py0, *py1};
-  const unsigned uu = *pu, vv = *pv;
+  const unsigned yw[2] = {*reinterpret_cast<const unsigned*>(p.p[0] + (size_t)y * p.stride[0] + x),
+                          *reinterpret_cast<const unsigned*>(p.p[0] + (size_t)(y + 1) * p.stride[0] + x)};
+  const unsigned uu = *reinterpret_cast<const uint16_t*>(p.p[1] + (size_t)(y >> 1) * p.stride[1] + (x >> 1));
+  const unsigned vv = *reinterpret_cast<const uint16_t*>(p.p[2] + (size_t)(y >> 1) * p.stride[2] + (x >> 1));
   const V2 k255i = bc(1 / 255.0f), k255 = bc(255.0f), khalf = bc(0.5f);
   const V2 m0 = bc(p.m[0]), m3 = bc(p.m[3]), m6 = bc(p.m[6]);
   unsigned oy[2] = {0, 0}, ou = 0, ov = 0;
@@ -396,10 +394,10 @@ __global__ void __launch_bounds__(256) k_yuv420_fast(const YuvConvParams p, cons
     ou |= (__float_as_uint(__fadd_rz(tu, 8388608.0f)) & 0xff) << (8 * k);
     ov |= (__float_as_uint(__fadd_rz(tv, 8388608.0f)) & 0xff) << (8 * k);
   }
-  *py0 = oy[0];
-  *py1 = oy[1];
-  *pu = (uint16_t)ou;
-  *pv = (uint16_t)ov;
+  *reinterpret_cast<unsigned*>(p.d[0] + (size_t)y * p.dstride[0] + x) = oy[0];
+  *reinterpret_cast<unsigned*>(p.d[0] + (size_t)(y + 1) * p.dstride[0] + x) = oy[1];
+  *reinterpret_cast<uint16_t*>(p.d[1] + (size_t)(y >> 1) * p.dstride[1] + (x >> 1)) = (uint16_t)ou;
+  *reinterpret_cast<uint16_t*>(p.d[2] + (size_t)(y >> 1) * p.dstride[2] + (x >> 1)) = (uint16_t)ov;
 }
 
 // host: table of the log2 kernel, uploaded once per device
@@ -494,6 +492,8 @@ cudaError_t launch_affine_fast(const AffineParams& p, const GainmapFinalizeParam
 bool yuv420_fast_eligible(const YuvConvParams& p) {
   if (p.fmt != F_YUV420 || (p.w & 3) || (p.h & 1)) return false;
   if ((p.stride[0] & 3) || (p.stride[1] & 1) || (p.stride[2] & 1)) return false;
+  if ((p.dstride[0] & 3) || (p.dstride[1] & 1) || (p.dstride[2] & 1)) return false;
+  if (((size_t)p.d[0] & 3) || ((size_t)p.d[1] & 1) || ((size_t)p.d[2] & 1)) return false;
   return !(((size_t)p.p[0] & 3) || ((size_t)p.p[1] & 1) || ((size_t)p.p[2] & 1));
 }
 cudaError_t launch_yuv420_fast(const YuvConvParams& p, cudaStream_t s) {

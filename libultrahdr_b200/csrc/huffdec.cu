@@ -22,6 +22,7 @@
 // Streams with restart markers, or that do not reach a fixed point in kMaxRounds rounds, return
 // kHuffDecFallback and the caller uses the host decoder of jpeg_host.cpp.
 #include <atomic>
+#include <mutex>
 #include <climits>
 #include <cstring>
 
@@ -308,7 +309,7 @@ void build_tables(const JpegHeader& h, HdTables* t) {
       for (int len = 1; len <= 16; len++) {
         t->valoff[ti][len] = k - code;
         for (int i = 0; i < bits[len]; i++, k++, code++)
-          if (len <= kLutBits)
+          if (len <= kLutBits && code < (1 << len))  // guard: never index past `lut` whatever the lengths say
             for (int r = 0; r < (1 << (kLutBits - len)); r++)
               t->lut[ti][(code << (kLutBits - len)) | r] = (uint16_t)((len << 8) | h.vals[cls][id][k & 255]);
         t->maxcode[ti][len] = bits[len] ? code - 1 : -1;
@@ -428,13 +429,15 @@ int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, con
   CUDA_TRY(cudaMemcpyAsync(d_bits, h_bits, padded, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d_hs, h_hs, sizeof hs, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemsetAsync(d_flags, 0, sizeof(unsigned) * (kMaxRounds + 8), s));
-  static bool zig_done[64] = {false};
-  {
+  {  // once per device, synchronously and under a lock: decodes run concurrently on several streams / threads
+    static std::mutex zig_mu;
+    static bool zig_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !zig_done[dev]) {
-      CUDA_TRY(cudaMemcpyToSymbolAsync(kZigzagDev, kZigzag, 64, 0, cudaMemcpyHostToDevice, s));
-      zig_done[dev] = true;
+    std::lock_guard<std::mutex> lk(zig_mu);
+    if (dev < 0 || dev >= 64 || !zig_done[dev]) {
+      CUDA_TRY(cudaMemcpyToSymbol(kZigzagDev, kZigzag, 64, 0, cudaMemcpyHostToDevice));
+      if (dev >= 0 && dev < 64) zig_done[dev] = true;
     }
   }
   // coefficient blocks start as zeros; only non-zero coefficients are written

@@ -432,6 +432,15 @@ int jpeg_read_header(const uint8_t* d, size_t n, JpegHeader* h) {
             !huff_table_ok(h->bits[1][h->ac_sel[c]], h->vals[1][h->ac_sel[c]], false))
           return fail(E_ERROR, "Bogus Huffman table definition");
       }
+      // libjpeg derives decoding tables lazily, for the tables a scan selects only: a malformed table
+      // nobody refers to is legal input.  Forget such tables here so that no table builder (host or
+      // device) ever sees code lengths that do not describe a prefix code.
+      for (int cls = 0; cls < 2; cls++)
+        for (int id = 0; id < 2; id++)
+          if (h->have_tbl[cls][id] && !huff_table_ok(h->bits[cls][id], h->vals[cls][id], cls == 0)) {
+            h->have_tbl[cls][id] = false;
+            memset(h->bits[cls][id], 0, sizeof h->bits[cls][id]);
+          }
       h->scan_offset = p + len;
       return E_OK;
     }
@@ -453,7 +462,7 @@ struct DecodeTable {
     for (int len = 1; len <= 16; len++) {
       valptr[len] = k - code;
       for (int i = 0; i < bits[len]; i++, k++, code++)
-        if (len <= 10)
+        if (len <= 10 && code < (1 << len) && k < 256)  // guards: never index past `fast` / `v` whatever the lengths say
           for (int r = 0; r < (1 << (10 - len)); r++) fast[(code << (10 - len)) | r] = (uint16_t)((len << 8) | v[k]);
       maxcode[len] = bits[len] ? code - 1 : -1;
       code <<= 1;

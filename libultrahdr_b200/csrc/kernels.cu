@@ -670,12 +670,10 @@ __global__ void __launch_bounds__(256) k_yuv_convert(const YuvConvParams p) {
   const int ty = blockIdx.y * blockDim.y + threadIdx.y;
   if (p.fmt == F_YUV420) {
     if (tx >= p.w / 2 || ty >= p.h / 2) return;
-    uint8_t* y0 = p.p[0] + (size_t)(ty * 2) * p.stride[0] + tx * 2;
-    uint8_t* y1 = y0 + p.stride[0];
-    uint8_t* pu = p.p[1] + (size_t)ty * p.stride[1] + tx;
-    uint8_t* pv = p.p[2] + (size_t)ty * p.stride[2] + tx;
-    const float u = (float)((int)*pu - 128) * (1 / 255.0f);
-    const float v = (float)((int)*pv - 128) * (1 / 255.0f);
+    const uint8_t* y0 = p.p[0] + (size_t)(ty * 2) * p.stride[0] + tx * 2;
+    const uint8_t* y1 = y0 + p.stride[0];
+    const float u = (float)((int)p.p[1][(size_t)ty * p.stride[1] + tx] - 128) * (1 / 255.0f);
+    const float v = (float)((int)p.p[2][(size_t)ty * p.stride[2] + tx] - 128) * (1 / 255.0f);
     const unsigned ys[4] = {y0[0], y0[1], y1[0], y1[1]};
     float ny[4], su = 0.f, sv = 0.f;
     for (int k = 0; k < 4; k++) {
@@ -688,23 +686,22 @@ __global__ void __launch_bounds__(256) k_yuv_convert(const YuvConvParams p) {
     }
     su /= 4.0f;
     sv /= 4.0f;
-    y0[0] = (uint8_t)clip255(ny[0] * 255.0f + 0.5f);
-    y0[1] = (uint8_t)clip255(ny[1] * 255.0f + 0.5f);
-    y1[0] = (uint8_t)clip255(ny[2] * 255.0f + 0.5f);
-    y1[1] = (uint8_t)clip255(ny[3] * 255.0f + 0.5f);
-    *pu = (uint8_t)clip255(su * 255.0f + 128.0f + 0.5f);
-    *pv = (uint8_t)clip255(sv * 255.0f + 128.0f + 0.5f);
+    uint8_t* d0 = p.d[0] + (size_t)(ty * 2) * p.dstride[0] + tx * 2;
+    uint8_t* d1 = d0 + p.dstride[0];
+    d0[0] = (uint8_t)clip255(ny[0] * 255.0f + 0.5f);
+    d0[1] = (uint8_t)clip255(ny[1] * 255.0f + 0.5f);
+    d1[0] = (uint8_t)clip255(ny[2] * 255.0f + 0.5f);
+    d1[1] = (uint8_t)clip255(ny[3] * 255.0f + 0.5f);
+    p.d[1][(size_t)ty * p.dstride[1] + tx] = (uint8_t)clip255(su * 255.0f + 128.0f + 0.5f);
+    p.d[2][(size_t)ty * p.dstride[2] + tx] = (uint8_t)clip255(sv * 255.0f + 128.0f + 0.5f);
   } else {  // 4:4:4
     if (tx >= p.w || ty >= p.h) return;
-    uint8_t* py = p.p[0] + (size_t)ty * p.stride[0] + tx;
-    uint8_t* pu = p.p[1] + (size_t)ty * p.stride[1] + tx;
-    uint8_t* pv = p.p[2] + (size_t)ty * p.stride[2] + tx;
-    const float yy = (float)*py * (1 / 255.0f);
-    const float u = (float)((int)*pu - 128) * (1 / 255.0f);
-    const float v = (float)((int)*pv - 128) * (1 / 255.0f);
-    *py = (uint8_t)clip255((yy * p.m[0] + u * p.m[1] + v * p.m[2]) * 255.0f + 0.5f);
-    *pu = (uint8_t)clip255((yy * p.m[3] + u * p.m[4] + v * p.m[5]) * 255.0f + 128.0f + 0.5f);
-    *pv = (uint8_t)clip255((yy * p.m[6] + u * p.m[7] + v * p.m[8]) * 255.0f + 128.0f + 0.5f);
+    const float yy = (float)p.p[0][(size_t)ty * p.stride[0] + tx] * (1 / 255.0f);
+    const float u = (float)((int)p.p[1][(size_t)ty * p.stride[1] + tx] - 128) * (1 / 255.0f);
+    const float v = (float)((int)p.p[2][(size_t)ty * p.stride[2] + tx] - 128) * (1 / 255.0f);
+    p.d[0][(size_t)ty * p.dstride[0] + tx] = (uint8_t)clip255((yy * p.m[0] + u * p.m[1] + v * p.m[2]) * 255.0f + 0.5f);
+    p.d[1][(size_t)ty * p.dstride[1] + tx] = (uint8_t)clip255((yy * p.m[3] + u * p.m[4] + v * p.m[5]) * 255.0f + 128.0f + 0.5f);
+    p.d[2][(size_t)ty * p.dstride[2] + tx] = (uint8_t)clip255((yy * p.m[6] + u * p.m[7] + v * p.m[8]) * 255.0f + 128.0f + 0.5f);
   }
 }
 

@@ -87,8 +87,10 @@ struct TonemapParams {              // toneMap, jpegr.cpp:1985-2222
 };
 
 struct YuvConvParams {              // transformYuv420/444, gainmapmath.cpp:686-748
-  uint8_t* p[3];
+  const uint8_t* p[3];              // source planes
   int stride[3];
+  uint8_t* d[3];                    // destination planes (== p for the reference's in-place form)
+  int dstride[3];
   int w, h, fmt;
   float m[9];
 };

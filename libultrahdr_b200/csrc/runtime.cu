@@ -88,7 +88,7 @@ struct ParkedBlock { char* base; size_t size; int device; };
 std::mutex g_park_mu;
 std::vector<ParkedBlock> g_parked[2];              // [0] device memory, [1] pinned host memory
 size_t g_parked_bytes[2] = {0, 0};
-constexpr size_t kParkCap[2] = {(size_t)24 << 30, (size_t)8 << 30};
+constexpr size_t kParkCap[2] = {(size_t)8 << 30, (size_t)4 << 30};
 
 char* take_parked(bool pinned, int device, size_t bytes, size_t* got) {
   std::lock_guard<std::mutex> lk(g_park_mu);
@@ -118,6 +118,33 @@ bool park(bool pinned, int device, char* base, size_t size) {
 }
 }  // namespace
 
+size_t trim_parked_blocks() {
+  std::vector<ParkedBlock> take[2];
+  {
+    std::lock_guard<std::mutex> lk(g_park_mu);
+    for (int k = 0; k < 2; k++) {
+      take[k].swap(g_parked[k]);
+      g_parked_bytes[k] = 0;
+    }
+  }
+  size_t freed = 0;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  for (auto& b : take[0]) {
+    if (b.device >= 0 && b.device != cur) cudaSetDevice(b.device);
+    cudaFree(b.base);
+    freed += b.size;
+    if (b.device >= 0 && b.device != cur && cur >= 0) cudaSetDevice(cur);
+  }
+  for (auto& b : take[1]) {
+    cudaFreeHost(b.base);
+    freed += b.size;
+  }
+  return freed;
+}
+
+// Callers (Workspace) drain their stream before the arenas go away: a parked block may be handed to
+// another handle on another stream at once, and unlike cudaFree parking does not synchronise.
 Arena::~Arena() {
   for (auto& b : blocks_) {
     if (park(pinned_, device_, b.base, b.size)) continue;
@@ -168,7 +195,14 @@ size_t Arena::reserved() const {
 
 Workspace::Workspace() {}
 Workspace::~Workspace() {
-  if (stream_) cudaStreamDestroy(stream_);
+  if (stream_) {
+    // error returns can leave kernels / async copies in flight on this stream; they must have
+    // finished before the arena blocks (destroyed after this body) are parked for other handles
+    cudaStreamSynchronize(stream_);
+    cudaStreamDestroy(stream_);
+  }
+  for (auto& s : spans_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
 }
 int Workspace::init() {
   if (stream_) return E_OK;

@@ -60,6 +60,9 @@ struct PhaseTrace {  // UHDR_B200_TRACE=1: wall-clock phases of one call on stde
   }
 };
 
+// release every parked arena block back to the driver; returns the bytes freed
+size_t trim_parked_blocks();
+
 class Arena {
  public:
   explicit Arena(bool pinned_host) : pinned_(pinned_host) {}

@@ -158,3 +158,18 @@ def test_host_parsers_under_sanitizers(oracle_libs, tmp_path):
     r = subprocess.run([exe, str(seed), "7", "6000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "harness done" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-2000:]
+    # regression (round-1 advisor finding): a DHT table that no scan component selects may be malformed
+    # (libjpeg derives tables lazily, so such a file is legal); the table builders must never see it.
+    # Gray JPEG using tables DC0/AC0 + an extra DC table id 1 whose 255 one-bit codes describe no prefix code.
+    olib = oracle_libs.Oracle().lib
+    g = (np.add.outer(np.arange(32), np.arange(32)) * 3 % 256).astype(np.uint8)
+    img = A.raw_image(A.FMT_Y400, -1, -1, 1, 32, 32, [g], [32])
+    good = T.oracle_encode(olib, img, 90)
+    sos = good.index(b"\xff\xda")
+    bogus = b"\xff\xc4" + (2 + 17 + 255).to_bytes(2, "big") + bytes([0x01, 255] + [0] * 15) + bytes(range(255))
+    for name, table in (("unused", bogus), ("unused_ac", bogus.replace(b"\x01\xff", b"\x11\xff", 1))):
+        poc = tmp_path / ("poc_%s.jpg" % name)
+        poc.write_bytes(good[:sos] + table + good[sos:])
+        r = subprocess.run([exe, str(poc), "single"], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and "single rc=0" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+        assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-2000:]

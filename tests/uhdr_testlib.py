@@ -1,7 +1,8 @@
 """Shared helpers for the test-suite: library loading, seeded synthetic frames and thin ctypes
 wrappers.  Three implementations expose the same four stage calls:
 
-  * ``Ref``    -- oracle/_ref/libuhdr_ref.so : the UNMODIFIED reference sources compiled in place
+  * ``Ref``    -- oracle/_ref/libuhdr_ref_turbo.so (else libuhdr_ref.so) : the UNMODIFIED reference
+                  sources compiled in place, JPEG through the real libjpeg-turbo
   * ``Oracle`` -- oracle/liboracle.so        : the plain-C restatement (the "port")
   * ``Gpu``    -- libultrahdr_b200/libuhdr_b200.so : the product (CUDA), host-buffer C ABI
 
@@ -17,7 +18,12 @@ from libultrahdr_b200.ctypes_api import *  # noqa: F401,F403
 from libultrahdr_b200 import ctypes_api as A
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_SO = os.path.join(ROOT, "oracle", "_ref", "libuhdr_ref.so")
+# two builds of the reference (oracle/Makefile): "turbo" = every reference source incl. its own
+# jpeg{en,de}coderhelper.cpp on the real libjpeg-turbo (preferred); "shim" = the JPEG helper classes on
+# oracle/jpeg_oracle.c (fallback when no libjpeg-turbo binary is around)
+REF_SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "libuhdr_ref.so")
+REF_TURBO_SO = os.path.join(ROOT, "oracle", "_ref", "libuhdr_ref_turbo.so")
+REF_SO = REF_TURBO_SO if os.path.exists(REF_TURBO_SO) else REF_SHIM_SO
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 GPU_SO = os.path.join(ROOT, "libultrahdr_b200", "libuhdr_b200.so")
 REF_DATA = "/root/reference/tests/data"
@@ -26,13 +32,17 @@ SEED = 20240607
 
 def ensure_oracle_built():
     if not os.path.exists(ORACLE_SO) or (os.path.isdir("/root/reference/lib/src")
-                                          and not os.path.exists(REF_SO)):
+                                          and not (os.path.exists(REF_SHIM_SO) and os.path.exists(REF_TURBO_SO))):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "all"],
                               stdout=subprocess.DEVNULL)
 
 
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+def ref_is_turbo():
+    return REF_SO == REF_TURBO_SO and os.path.exists(REF_TURBO_SO)
 
 
 # ------------------------------------------------------------------------------------------------
