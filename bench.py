@@ -16,7 +16,8 @@ uhdr_get_encoded_stream).  Frames shard across ranks with no data-path collectiv
   extra : 8K decode (config 3) and 4K API-0 (config 2) device-resident numbers + applyGainMap roofline.
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref: the reference sources
-compiled in place; JPEG arithmetic through oracle/jpeg_oracle.c) on the host cores.
+compiled in place, its JPEG helper classes on the real libjpeg-turbo binary of this image) on all host
+threads.
 """
 import argparse
 import ctypes as C
@@ -386,6 +387,38 @@ def bench_b200(args, rank, world):
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * F * args.steps * MPIX_4K / t_e2e
 
+    # ---------------- decode arm of the metric (config 3): 8K JPEG/R -> RGBA half float ------------
+    # through uhdr_dec_set_image / uhdr_decode / uhdr_get_decoded_image with the compressed stream in
+    # host memory and the pixels delivered to host memory (D2H of 265 MB per image inside the timed
+    # region); 4 reused decoder handles (host threads) per GPU, every rank decodes its own images
+    dec_handles, dec_per = 4, max(2, min(6, args.steps))
+    p8, y8 = make_frame(W8K, H8K, 7 + rank)
+    h8, s8, _k8 = frame_descs(p8, y8, W8K, H8K)
+    data8 = api.encode(h8, s8)
+    del p8, y8, h8, s8, _k8
+    buf8 = np.frombuffer(data8, np.uint8).copy()
+    ci8 = A.CompressedImage(buf8.ctypes.data, len(data8), len(data8), -1, -1, -1)
+    decs = [C.c_void_p(lib.uhdr_create_decoder()) for _ in range(dec_handles)]
+
+    def dec_round(n):
+        def work(i):
+            for _ in range(n):
+                lib.uhdr_reset_decoder(decs[i])
+                assert lib.uhdr_dec_set_image(decs[i], C.byref(ci8)).error_code == 0
+                e = lib.uhdr_decode(decs[i])
+                assert e.error_code == 0, e.detail
+                assert lib.uhdr_get_decoded_image(decs[i]).contents.w == W8K
+        run_threads(dec_handles, work)
+    dec_round(2)
+    barrier()
+    t0 = time.perf_counter()
+    dec_round(dec_per)
+    torch.cuda.synchronize()
+    t_dec = max_over_ranks(time.perf_counter() - t0)
+    dec_value = world * dec_handles * dec_per * (W8K * H8K / 1e6) / t_dec
+    for d in decs:
+        lib.uhdr_release_decoder(d)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -452,7 +485,7 @@ def bench_b200(args, rank, world):
     except OSError:
         pass
     if world == 1:
-        cpu = cpu_baseline(frames[:max(2, min(len(frames), ncpu_all // 4))])
+        cpu = cpu_baseline(frames)
     else:
         cpu = {"value": None, "unit": "MPix/s", "cores": 0, "kind": "reference", "sample": "timed at N=1 only"}
 
@@ -470,6 +503,13 @@ def bench_b200(args, rank, world):
                 "d2h_bytes_per_step": int(sum(e2e_out)), "ms_per_step": round(t_e2e / args.steps * 1e3, 3),
                 "h2d_achieved_gbs": round(in_bytes / (t_e2e / args.steps) / 1e9, 1), "pcie_probe": pcie,
                 "bound": "pcie h2d: 37.3 MB of raw pixels enter per 4K frame, 2.3 MB of JPEG/R leave"},
+        "decode": {"metric": "MPix/s decode 8K JPEG/R -> RGBA half float", "e2e": {"value": round(dec_value, 1), "unit": "MPix/s",
+                   "h2d_bytes_per_image": len(data8), "d2h_bytes_per_image": W8K * H8K * 8,
+                   "d2h_achieved_gbs": round(dec_value * 8e6 / 1e9 / world, 1)},
+                   "images": world * dec_handles * dec_per, "handles_per_gpu": dec_handles,
+                   "cpu_baseline": (cpu_decode_baseline(data8, W8K, H8K) if world == 1 else None),
+                   "how": "uhdr_dec_set_image + uhdr_decode + uhdr_get_decoded_image through the C ABI, compressed stream and "
+                          "pixels in host memory, wall clock between device-wide synchronisations, max over ranks"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": roof,
@@ -477,6 +517,8 @@ def bench_b200(args, rank, world):
         "cpu_baseline": cpu,
         "extra": extra,
         "stream_bytes_per_frame": int(sum(out_bytes) / max(1, F)),
+        "stream_bytes_per_frame_e2e": int(sum(e2e_out) / max(1, F)),
+        "resident_equals_e2e_streams": [int(x) for x in out_bytes] == [int(x) for x in e2e_out],
     }
     emit(line)
     if world > 1:
@@ -652,28 +694,79 @@ def extra_measurements(lib, api, hbm):
     return out
 
 
+def ref_jpeg_note():
+    import uhdr_testlib as T
+    if T.ref_is_turbo():
+        return "reference sources incl. its own jpeg{en,de}coderhelper.cpp on the real libjpeg-turbo (Pillow's 3.1.x binary, SIMD)"
+    return "reference sources, JPEG through oracle/jpeg_oracle.c (scalar) because no libjpeg-turbo binary was found"
+
+
+def ref_concurrency(gb_per_call):
+    """concurrent reference calls: one per host thread (measured here: throughput still rises up to
+    one call per hardware thread although each call also spawns the reference's own <=4 workers),
+    bounded by free memory"""
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    conc = ncpu
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                conc = min(conc, max(1, int(int(ln.split()[1]) / 1048576 * 0.6 / gb_per_call)))
+    except OSError:
+        pass
+    return max(1, conc), ncpu
+
+
 def cpu_baseline(frames, reps=1):
     """reference CPU path (oracle/_ref) on the host cores: API-1 4K encode of a bounded sample."""
     import uhdr_testlib as T
     if not T.have_ref():
         return {"value": None, "unit": "MPix/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
     api, lib = load_api(T.REF_SO)
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    conc = max(1, min(len(frames), ncpu // 4))  # the reference uses min(hw,4) threads per call
+    conc, ncpu = ref_concurrency(0.5)
     descs = [frame_descs(p, y, W4K, H4K) for (p, y) in frames]
+    api.encode(descs[0][0], descs[0][1])  # first call builds the reference's static LUTs
     t0 = time.perf_counter()
-    done = [0]
+    done = [0] * conc
 
     def work(i):
         for r in range(reps):
             api.encode(descs[i % len(descs)][0], descs[i % len(descs)][1])
-            done[0] += 1
+            done[i] += 1
     run_threads(conc, work)
     dt = time.perf_counter() - t0
-    return {"value": round(done[0] * MPIX_4K / dt, 2), "unit": "MPix/s", "cores": min(ncpu, conc * 4), "kind": "reference",
-            "sample": "%d x 4K API-1 uhdr_encode calls, %d concurrent (each call uses the reference's own 4 worker threads), "
-                      "%.1f s; JPEG entropy/DCT via oracle/jpeg_oracle.c in place of libjpeg-turbo" % (done[0], conc, dt),
+    n = sum(done)
+    return {"value": round(n * MPIX_4K / dt, 2), "unit": "MPix/s", "cores": ncpu, "kind": "reference",
+            "sample": "%d x 4K API-1 uhdr_encode calls, %d concurrent on %d host threads, %.1f s; %s" % (n, conc, ncpu, dt, ref_jpeg_note()),
             "host_cpus": ncpu}
+
+
+def cpu_decode_baseline(data, w, h, reps=1):
+    """reference uhdr_decode (-> RGBA half float) of one JPEG/R, one call per host thread"""
+    import uhdr_testlib as T
+    if not T.have_ref():
+        return None
+    api, lib = load_api(T.REF_SO)
+    conc, ncpu = ref_concurrency(w * h * 40 / 1e9)
+    buf = np.frombuffer(data, np.uint8).copy()
+    ci = A.CompressedImage(buf.ctypes.data, len(data), len(data), -1, -1, -1)
+
+    def one():
+        dec = C.c_void_p(lib.uhdr_create_decoder())
+        assert lib.uhdr_dec_set_image(dec, C.byref(ci)).error_code == 0
+        e = lib.uhdr_decode(dec)
+        assert e.error_code == 0, e.detail
+        assert lib.uhdr_get_decoded_image(dec).contents.w == w
+        lib.uhdr_release_decoder(dec)
+    t0 = time.perf_counter()
+    one()
+    t_single = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    run_threads(conc, lambda i: [one() for _ in range(reps)])
+    dt = time.perf_counter() - t0
+    return {"value": round(conc * reps * w * h / 1e6 / dt, 2), "unit": "MPix/s", "cores": ncpu, "kind": "reference",
+            "single_call_ms": round(t_single * 1e3, 1),
+            "sample": "%d uhdr_decode calls of one %dx%d JPEG/R -> RGBA half float, %d concurrent on %d host threads, %.1f s; %s"
+                      % (conc * reps, w, h, conc, ncpu, dt, ref_jpeg_note())}
 
 
 def bench_reference(args, rank, world):
@@ -685,29 +778,50 @@ def bench_reference(args, rank, world):
         emit({"impl": "reference", "unavailable": "oracle/_ref/libuhdr_ref.so not built (needs /root/reference at build time)"})
         return
     api, lib = load_api(T.REF_SO)
-    ncpu = os.cpu_count() or 1
-    conc = max(1, ncpu // 4)
-    frames = [make_frame(W4K, H4K, i) for i in range(min(conc, 4))]
+    conc, ncpu = ref_concurrency(0.5)
+    frames = [make_frame(W4K, H4K, i) for i in range(min(conc, 8))]
     descs = [frame_descs(p, y, W4K, H4K) for (p, y) in frames]
-    per_step = conc
+    per_step = conc   # a step = one 4K frame per concurrent call: the bounded sample of the GPU arm's 32-frame batch
 
     def step():
         run_threads(conc, lambda i: api.encode(descs[i % len(descs)][0], descs[i % len(descs)][1]))
-    for _ in range(min(args.warmup, 1)):
+    t0 = time.perf_counter()
+    step()            # also builds the reference's static LUTs
+    t_first = time.perf_counter() - t0
+    # keep the whole run within a few minutes whatever K and W the driver passes
+    steps, warmup = args.steps, args.warmup
+    budget = 150.0
+    if (steps + warmup) * t_first > budget:
+        warmup = min(warmup, 1)
+        steps = max(1, min(steps, int(budget / t_first) - warmup))
+    for _ in range(max(0, warmup - 1)):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    v = per_step * args.steps * MPIX_4K / dt
-    sample = "%d concurrent 4K API-1 uhdr_encode calls per step (reference uses 4 worker threads per call)" % conc
+    v = per_step * steps * MPIX_4K / dt
+    sample = "%d concurrent 4K API-1 uhdr_encode calls per step on %d host threads; %s" % (conc, ncpu, ref_jpeg_note())
+    # decode arm of the metric (config 3): 8K JPEG/R written by the reference itself, all host threads
+    decode = None
+    try:
+        p8, y8 = make_frame(W8K, H8K, 7)
+        h8, s8, _k8 = frame_descs(p8, y8, W8K, H8K)
+        data8 = api.encode(h8, s8)
+        del p8, y8
+        decode = cpu_decode_baseline(data8, W8K, H8K)
+        decode["metric"] = "MPix/s decode 8K JPEG/R -> RGBA half float"
+    except Exception as e:  # noqa: BLE001
+        decode = {"error": repr(e)}
     emit({
         "impl": "reference", "metric": "MPix/s encode(API-1) at 4K", "value": round(v, 2), "unit": "MPix/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 1),
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(dt / steps * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "api1_encode_3840x2160_p010hlg_bt2100+yuv420_bt709", "frames_per_step": per_step},
-        "cpu_baseline": {"value": round(v, 2), "unit": "MPix/s", "cores": min(ncpu, conc * 4), "kind": "reference", "sample": sample},
+        "config": {"workload": "api1_encode_3840x2160_p010hlg_bt2100+yuv420_bt709", "frames_per_step": per_step,
+                   "steps_requested": args.steps, "warmup_requested": args.warmup},
+        "cpu_baseline": {"value": round(v, 2), "unit": "MPix/s", "cores": ncpu, "kind": "reference", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "decode": decode,
     })
 
 
@@ -740,8 +854,6 @@ def main():
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     if args.impl == "reference":
-        if args.steps > 3:
-            args.steps = 3  # bounded sample: each step is seconds of CPU work
         bench_reference(args, rank, world)
     else:
         if args.warmup < 3:

@@ -20,13 +20,28 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
-def needs_build():
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
+STAMP = OUT + ".stamp"
+
+
+def source_digest():
+    """content hash of everything the library is built from (mtimes do not survive the trip to the GPU box)"""
+    import hashlib
+    h = hashlib.sha256()
     deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) \
-        + glob.glob(os.path.join(HERE, "..", "include", "*.h")) + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+        + glob.glob(os.path.join(CSRC, "*.inc")) + glob.glob(os.path.join(HERE, "..", "include", "*.h")) \
+        + glob.glob(os.path.join(HERE, "..", "include", "*.hpp")) + [os.path.abspath(__file__)]
+    for d in sorted(deps):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def needs_build():
+    if not os.path.exists(OUT) or not os.path.exists(STAMP):
+        return True
+    with open(STAMP) as f:
+        return f.read().strip() != source_digest()
 
 
 def build(force=False, verbose=False):
@@ -49,6 +64,8 @@ def build(force=False, verbose=False):
     if not ok:
         raise RuntimeError("nvcc failed")
     subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-lcudart", "-lpthread"])
+    with open(STAMP, "w") as f:
+        f.write(source_digest())
     return OUT
 
 
