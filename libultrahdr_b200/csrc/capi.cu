@@ -569,10 +569,7 @@ UHDR_API int uhdr_b200_jpeg_encode(const uhdr_raw_image_t* img, int quality, con
   int rc = upload_image(c->ws(), *img, &d);
   if (rc) return rc;
   JpegEncodeJob job;
-  JpegFrame probe;
-  rc = jpeg_frame_init(&probe, img->fmt, img->w, img->h, quality);
-  if (rc) return rc;
-  const bool dev = gpu_entropy_available() && !probe.has_dummy_blocks();
+  const bool dev = gpu_entropy_available();
   rc = jpeg_forward_dev(c->ws(), d, quality, &job, dev);
   if (rc) return rc;
   rc = dev ? jpeg_entropy_dev(c->ws(), &job) : jpeg_fetch_coefs(c->ws(), &job);

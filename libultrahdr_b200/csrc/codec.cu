@@ -14,16 +14,12 @@ namespace uhdr_b200 {
 // ------------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------------
-static bool use_device_entropy(int fmt, int w, int h) {
-  JpegFrame f;
-  if (jpeg_frame_init(&f, fmt, w, h, 90) != E_OK) return false;
-  return gpu_entropy_available() && !f.has_dummy_blocks();
-}
+// forward block stage + entropy coding, both on the device for every geometry (MCUs that reach past
+// the block grid included: huffman.cu codes libjpeg's dummy blocks)
 static int block_stage(Workspace& ws, const DevImage& img, int quality, JpegEncodeJob* job) {
-  const bool dev = use_device_entropy(img.v.fmt, img.v.w, img.v.h);
-  int rc = jpeg_forward_dev(ws, img, quality, job, dev);
+  int rc = jpeg_forward_dev(ws, img, quality, job, /*zigzag=*/true);
   if (rc) return rc;
-  return dev ? jpeg_entropy_dev(ws, job) : jpeg_fetch_coefs(ws, job);
+  return jpeg_entropy_dev(ws, job);
 }
 
 int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b200_gm_config_t& cfg_in,

@@ -9,6 +9,8 @@
 // A warp owns 4 horizontally adjacent blocks, a CTA 32; all planes of an image go in ONE launch
 // (grid.z), the three components of an RGB888 gain map are produced from one read of the pixels.
 // Arithmetic is libjpeg-turbo's jccolor.c / jfdctint.c / jcdctmgr.c integer arithmetic: bit-exact.
+#include <cstring>
+
 #include "kernels.cuh"
 
 namespace uhdr_b200 {
@@ -57,9 +59,49 @@ __device__ __forceinline__ int unzig_rt(int n) { return kUnzigTab[n]; }
 
 constexpr int kTileStride = 72;  // ints per block tile: 64 + 8 padding (4 blocks of a warp on distinct banks)
 
+// Side information for the device entropy coder (huffman.cu), computed while the quantised block is
+// still in the warp's shared-memory tile (zigzag order): the 64-bit mask of its non-zero
+// coefficients and the number of code bits its AC part takes (jchuff.c encode_one_block: run/size
+// Huffman codes, magnitude bits, a ZRL per 16 zeros, EOB unless coefficient 63 is non-zero).  Lane j
+// of the block's 8 lanes takes zigzag positions j, j+8, ... so that the few non-zeros of a typical
+// block, which sit at the lowest positions, spread over the lanes.
+__device__ __forceinline__ void block_meta(const int16_t* t16, const uint4 q, int lane_r, const uint8_t* aclen, uint4* meta_out) {
+  auto nz2 = [](unsigned w) { return ((w & 0xffffu) ? 1u : 0u) | ((w >> 16) ? 2u : 0u); };
+  const unsigned m8 = nz2(q.x) | (nz2(q.y) << 2) | (nz2(q.z) << 4) | (nz2(q.w) << 6);  // positions 8r .. 8r+7
+  unsigned lo = lane_r < 4 ? m8 << (8 * lane_r) : 0u, hi = lane_r >= 4 ? m8 << (8 * (lane_r - 4)) : 0u;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {  // OR over the 8 lanes of the block (aligned group: xor stays inside)
+    lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+    hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+  }
+  const unsigned long long mask = ((unsigned long long)hi << 32) | lo;
+  const unsigned long long anchored = mask | 1ull;  // runs are counted from the DC position
+  unsigned bits = 0;
+  const unsigned zrl = aclen[0xF0];
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    unsigned mj = ((half ? hi : lo) >> lane_r) & 0x01010101u;
+    if (half == 0 && lane_r == 0) mj &= ~1u;  // the DC coefficient is not part of the AC code
+    while (mj) {
+      const int k = lane_r + (__ffs(mj) - 1) + 32 * half;
+      mj &= mj - 1;
+      const int prev = 63 - __clzll((long long)(anchored & ((1ull << k) - 1ull)));
+      const int run = k - prev - 1;
+      const int v = t16[k];
+      const int nb = 32 - __clz(abs(v));
+      bits += aclen[((run & 15) << 4) | nb] + nb + (run >> 4) * zrl;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+  if (!(hi >> 31)) bits += aclen[0];  // EOB
+  if (lane_r == 0 && meta_out) *meta_out = make_uint4(lo, hi, bits, (unsigned)(int)t16[0]);
+}
+
 template <bool ZIGZAG>
 __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int lane_r, const unsigned* sdiv,
-                                            const unsigned* smag, const uint8_t* sunzig, int16_t* gout_block_base) {
+                                            const unsigned* smag, const uint8_t* sunzig, int16_t* gout_block_base,
+                                            const uint8_t* aclen, uint4* meta_out) {
   // pass 1 on this lane's row, park it
   dct1d<0>(d);
   int* t = tile + lane_b * kTileStride;
@@ -86,7 +128,9 @@ __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int
   }
   __syncwarp();
   // 16 bytes per lane: coefficients [8*lane_r, 8*lane_r + 8) of block lane_b
-  if (gout_block_base) *(uint4*)(gout_block_base + lane_r * 8) = *(const uint4*)(t16 + lane_r * 8);
+  const uint4 q = *(const uint4*)(t16 + lane_r * 8);
+  if (gout_block_base) *(uint4*)(gout_block_base + lane_r * 8) = q;
+  if (ZIGZAG) block_meta(t16, q, lane_r, aclen, meta_out);  // all 32 lanes take part (shuffles); dead lanes store nothing
   __syncwarp();
 }
 
@@ -95,6 +139,11 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
   __shared__ unsigned sdiv[2][64], smag[2][64];
   __shared__ int tiles[8][4 * kTileStride];
   __shared__ uint8_t sunzig[64];
+  __shared__ uint8_t saclen[2][256];
+  if (ZIGZAG) {
+    saclen[0][threadIdx.x] = P.aclen[0][threadIdx.x];
+    saclen[1][threadIdx.x] = P.aclen[1][threadIdx.x];
+  }
   if (threadIdx.x >= 128 && threadIdx.x < 192) sunzig[threadIdx.x - 128] = (uint8_t)unzig_rt(threadIdx.x - 128);
   if (threadIdx.x < 128) {
     const int t = threadIdx.x >> 6, i = threadIdx.x & 63;
@@ -131,8 +180,10 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
         d[4 + k] = (int)((v.y >> (8 * k)) & 0xff) - 128;
       }
     }
-    int16_t* out = live ? pl.coefs[0] + ((size_t)by * pl.wblocks + bx) * 64 : nullptr;
-    block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, out);
+    const size_t bidx = (size_t)by * pl.wblocks + bx;
+    int16_t* out = live ? pl.coefs[0] + bidx * 64 : nullptr;
+    block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, out, saclen[pl.hsel[0]],
+                        live && pl.meta[0] ? pl.meta[0] + bidx : nullptr);
   } else {
     // RGB888: libjpeg's scanline path replicates the last column / row (jcsample.c, jcprepct.c)
     const int y = min(by * 8 + lane_r, pl.h - 1);
@@ -166,8 +217,10 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
         else v = (32768 * r[k] - 27439 * g[k] - 5329 * b[k] + (128 << 16) + 32767) >> 16;
         d[k] = v - 128;
       }
-      int16_t* out = live ? pl.coefs[comp] + ((size_t)by * pl.wblocks + bx) * 64 : nullptr;
-      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[comp]], smag[pl.tq[comp]], sunzig, out);
+      const size_t bidx = (size_t)by * pl.wblocks + bx;
+      int16_t* out = live ? pl.coefs[comp] + bidx * 64 : nullptr;
+      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[comp]], smag[pl.tq[comp]], sunzig, out, saclen[pl.hsel[comp]],
+                          live && pl.meta[comp] ? pl.meta[comp] + bidx : nullptr);
     }
   }
   }
@@ -175,9 +228,24 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
 
 }  // namespace
 
+void jpeg_std_codebook(int which, uint32_t out[256]);  // jpeg_host.cpp: (code << 8 | length) per symbol
+
 cudaError_t launch_fdct8(const Fdct8Params& Pin, cudaStream_t s) {
   count_launches(1);
   Fdct8Params P = Pin;
+  if (P.zigzag) {
+    struct Lens { uint8_t v[2][256]; };
+    static const Lens lens = [] {  // thread-safe one-time initialisation
+      Lens l;
+      uint32_t cb[256];
+      for (int t = 0; t < 2; t++) {
+        jpeg_std_codebook(t == 0 ? 1 : 3, cb);
+        for (int i = 0; i < 256; i++) l.v[t][i] = (uint8_t)(cb[i] & 0xff);
+      }
+      return l;
+    }();
+    memcpy(P.aclen, lens.v, sizeof lens.v);
+  }
   for (int t = 0; t < 2; t++)
     for (int i = 0; i < 64; i++) {
       const unsigned d = (unsigned)P.q[t][i] << 3;
@@ -189,12 +257,15 @@ cudaError_t launch_fdct8(const Fdct8Params& Pin, cudaStream_t s) {
     P.tile_end[i] = total;
   }
   if (total == 0) return cudaSuccess;
-  static int resident = 0;  // CTAs of one wave (same for both instantiations: identical resources)
+  static int resident_tab[2] = {0, 0};  // CTAs of one wave, per instantiation
+  int& resident = resident_tab[P.zigzag ? 1 : 0];
   if (!resident) {
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fdct8<true>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const cudaError_t oe = P.zigzag ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fdct8<true>, 256, 0)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fdct8<false>, 256, 0);
+    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
     resident = per_sm * (sms > 0 ? sms : 148);
   }
   const int ctas = total < resident ? total : resident;

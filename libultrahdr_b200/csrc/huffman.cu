@@ -1,14 +1,20 @@
 // Baseline-JPEG entropy coding on the device, bit-identical to libjpeg-turbo's jchuff.c for the
-// reference's settings (default Annex-K tables, one interleaved scan, no restart markers).
+// reference's settings (default Annex-K tables, one interleaved scan, no restart markers), including
+// libjpeg's dummy blocks for MCUs that reach past a component's block grid (jccoefct.c
+// compress_data: zero AC, DC repeated from the block coded before, jpegencoderhelper.cpp:254-296 for
+// the padded sample rows that feed the real edge blocks).
 //
-//   E1  k_huff_encode  : CTAs of 128 consecutive blocks (scan order): stage the coefficients in
-//                        shared memory, count each block's code bits, chain the bit offsets across
-//                        CTAs with a decoupled look-back, encode into a word-aligned shared-memory
-//                        image of the CTA's segment and store it; partial boundary words travel
-//                        from CTA to CTA (details at the kernel).
-//   E2  k_stuff_lb     : pad the last byte with ones, insert 0x00 after every 0xFF (count, look-back
-//                        over 1024-word tiles and write in one launch).
-// Only the final stuffed segment (a few MB at 4K) crosses PCIe.
+// ONE kernel, one pass over the coefficients.  The forward stage (fdct8.cu) leaves, per block, the
+// 64-bit mask of its non-zero coefficients, the number of code bits of its AC part and its DC value,
+// so a block's total code length is known from 16 bytes and the coefficients are visited exactly
+// once, non-zero ones only.  k_huff_encode, per CTA of 256 consecutive blocks of the scan:
+//   1. per thread: locate the block (or dummy block) and its DC predecessor, total its code bits
+//   2. CTA scan + decoupled look-back over CTAs -> absolute bit offset of every block
+//   3. per thread: emit the block's codes into a word-aligned shared-memory image of the CTA's segment
+//   4. partial boundary words travel from CTA to CTA (no pre-zeroed stream, no global atomics)
+//   5. byte stuffing folded in: the 0xFF bytes of the words a CTA owns are counted, a second
+//      look-back gives the number of stuffed zeros in front of them, the CTA writes its final bytes
+// Only the final stuffed segment (a few MB at 4K) exists in global memory and crosses PCIe.
 #include <cstring>
 
 #include "jpeg.h"
@@ -19,37 +25,65 @@ void jpeg_std_codebook(int which, uint32_t out[256]);
 
 namespace {
 
-constexpr int kMaxWordsPerBlock = 52;  // (20 + 63*26 bits) / 32 rounded up
-constexpr int kPersistentCtas = 148 * 2;  // one wave of 1024-thread CTAs on the 148 SMs
+constexpr int kEncThreads = 256;                        // blocks of the scan per CTA, one thread each
+// shared-memory image of the CTA's segment: 2048 words = 256 bits per block on average.  Heavier
+// segments (noise at high quality; the worst case is 52 words per block) are produced in several
+// windows of this size; a block is encoded only for the windows its bits fall into.
+constexpr unsigned kSegWords = 2048;
+constexpr int kWordsPerThread = kSegWords / kEncThreads;  // 8
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
 
 struct HuffFrame {
-  const int16_t* coefs[3];
-  int wblocks[3], mw[3], mh[3], koff[3];
+  const int16_t* coefs[3];   // zigzag-ordered blocks, [block raster][64]
+  const uint4* meta[3];      // {mask lo, mask hi, AC code bits, DC} per block (fdct8.cu block_meta)
+  int wblocks[3], hblocks[3], mw[3], mh[3], koff[3];
   int ncomp, mcus_per_row, blocks_per_mcu;
-  unsigned nblocks;
+  unsigned nblocks;          // blocks of the scan = MCUs x blocks per MCU (dummy blocks included)
 };
 
-__device__ __forceinline__ void locate(const HuffFrame& f, unsigned s, int& c, unsigned& blk, long long& prev) {
-  const unsigned m = s / f.blocks_per_mcu, k = s - m * f.blocks_per_mcu;
-  c = (f.ncomp > 2 && k >= (unsigned)f.koff[2]) ? 2 : ((f.ncomp > 1 && k >= (unsigned)f.koff[1]) ? 1 : 0);
-  const unsigned kk = k - f.koff[c];
-  const unsigned mx = m % f.mcus_per_row, my = m / f.mcus_per_row;
-  const unsigned mw = f.mw[c], mh = f.mh[c];
-  blk = (my * mh + kk / mw) * f.wblocks[c] + mx * mw + kk % mw;
-  if (kk > 0) {
-    const unsigned pk = kk - 1;
-    prev = (long long)(my * mh + pk / mw) * f.wblocks[c] + mx * mw + pk % mw;
-  } else if (m > 0) {
-    const unsigned pm = m - 1, pk = mw * mh - 1;
-    const unsigned pmx = pm % f.mcus_per_row, pmy = pm / f.mcus_per_row;
-    prev = (long long)(pmy * mh + pk / mw) * f.wblocks[c] + pmx * mw + pk % mw;
-  } else {
-    prev = -1;
-  }
-}
+struct Loc {
+  int c;            // component
+  bool real;        // false: dummy block (outside the component's block grid)
+  unsigned blk;     // raster index inside the component (real blocks)
+  long long pred;   // raster index of the last real block of the component before this one in scan order, -1: none
+};
 
-// ---- exclusive scan of u32 (three-phase, tiles of 1024) -------------------------------------------
-constexpr int kScanTile = 1024;
+// Position s of the scan -> block.  DC prediction runs over the blocks of a component in scan order;
+// a dummy block repeats the DC of the block before it (difference 0), so the predecessor that matters
+// is the most recent REAL block.  The first block of every MCU is real, so the walk back is short.
+__device__ __forceinline__ Loc locate(const HuffFrame& f, unsigned s) {
+  Loc L;
+  const unsigned m = s / f.blocks_per_mcu, k = s - m * f.blocks_per_mcu;
+  const int c = (f.ncomp > 2 && k >= (unsigned)f.koff[2]) ? 2 : ((f.ncomp > 1 && k >= (unsigned)f.koff[1]) ? 1 : 0);
+  const unsigned mw = f.mw[c], mh = f.mh[c], per = mw * mh;
+  const unsigned wb = f.wblocks[c], hb = f.hblocks[c];
+  unsigned kk = k - f.koff[c];
+  unsigned mx = m % f.mcus_per_row, my = m / f.mcus_per_row;
+  unsigned bx = mx * mw + kk % mw, by = my * mh + kk / mw;
+  L.c = c;
+  L.real = bx < wb && by < hb;
+  L.blk = by * wb + bx;
+  L.pred = -1;
+  unsigned pm = m;
+  for (unsigned it = 0; it < 2 * per; it++) {
+    if (kk > 0) {
+      kk--;
+    } else {
+      if (pm == 0) break;
+      pm--;
+      mx = pm % f.mcus_per_row;
+      my = pm / f.mcus_per_row;
+      kk = per - 1;
+    }
+    bx = mx * mw + kk % mw;
+    by = my * mh + kk / mw;
+    if (bx < wb && by < hb) {
+      L.pred = (long long)by * wb + bx;
+      break;
+    }
+  }
+  return L;
+}
 
 __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* total) {
   __shared__ unsigned warp_sums[32];
@@ -78,29 +112,6 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
   return r;
 }
 
-// ---- E1: encode, chain the bit offsets across CTAs, write the stream ------------------------------
-// One CTA = kEncBlocks consecutive blocks of the scan, taken in ticket order so that a CTA's
-// predecessors are always already running (the cross-CTA steps below spin on them).
-//   a. the coefficient blocks are staged in shared memory with coalesced loads (stride-129 word
-//      tile: thread j then reads word r of its block at tile[r*129 + j] without bank conflicts)
-//   b. pass A: each thread builds the 64-bit non-zero mask of its block and counts its code bits
-//      (only the non-zero coefficients are visited)
-//   c. CTA-wide exclusive scan -> bit offset of each block inside the CTA's segment and the total
-//   d. decoupled look-back over per-CTA status words (aggregate / inclusive prefix) -> the
-//      segment's absolute bit offset
-//   e. pass B: the blocks are encoded again, now ORing their bits into a shared-memory image of the
-//      segment that is aligned to the 32-bit words of the output stream
-//   f. interior words are stored coalesced; the trailing partial word is handed to the successor
-//      CTA, which merges it with its own leading bits and stores the word.  No pre-zeroed stream,
-//      no scratch, no global atomics on the stream.
-constexpr int kEncBlocks = 128;
-constexpr int kTileStride = kEncBlocks + 1;
-// shared-memory image of the CTA's segment: 1024 words = 256 bits per block on average.  Heavier
-// segments (noise at high quality; the worst case is 52 words per block) are produced in several
-// windows of this size, pass B running once per window.
-constexpr unsigned kSegWords = 1024;
-constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
-
 // Decoupled look-back (one warp): sum of the values of all predecessors of `idx`.  status[i] carries a
 // 2-bit flag and a 32-bit value: kFlagAgg = the value of i alone, kFlagPrefix = the inclusive prefix up
 // to i.  Predecessors are running or finished (ticket order), so the spin loops terminate.
@@ -123,277 +134,270 @@ __device__ __forceinline__ unsigned lookback_sum(const unsigned long long* statu
     hi -= 32;
   }
 }
+// publish the aggregate of CTA `idx`, look back, publish the inclusive prefix; warp 0 calls it, the
+// exclusive prefix lands in *out (shared memory) -- the caller synchronises the CTA afterwards
+__device__ __forceinline__ void chain_prefix(unsigned long long* status, unsigned idx, unsigned agg, int j, unsigned* out) {
+  if (j == 0) *reinterpret_cast<volatile unsigned long long*>(status + idx) = (idx == 0 ? kFlagPrefix : kFlagAgg) | agg;
+  if (idx == 0) {
+    if (j == 0) *out = 0;
+    return;
+  }
+  if (j < 32) {
+    const unsigned base = lookback_sum(status, idx, j);
+    if (j == 0) {
+      *out = base;
+      *reinterpret_cast<volatile unsigned long long*>(status + idx) = kFlagPrefix | (unsigned long long)(base + agg);
+    }
+  }
+}
 
-struct EncSmem {
-  uint32_t tile[32 * kTileStride];
-  uint32_t seg[kSegWords];
+// One block's codes, jchuff.c encode_one_block, into the window [win, win + wn) of the segment image
+// (word indices relative to the CTA's first word).  Words that lie wholly inside the block's bit range
+// belong to this thread alone and are stored; the first and the last word are shared with the
+// neighbouring blocks and are ORed into the zero-initialised image.
+struct Emitter {
+  uint32_t* seg;
+  unsigned win, wn, first_w, last_w;
+  unsigned long long acc;
+  int fill;
+  unsigned widx;
+  __device__ __forceinline__ void store(unsigned v) {
+    const unsigned r = widx - win;
+    if (r < wn) {
+      if (widx == first_w || widx == last_w) atomicOr(seg + r, v);
+      else seg[r] = v;
+    }
+  }
+  __device__ __forceinline__ void put(unsigned bits, int n) {
+    acc = (acc << n) | bits;
+    fill += n;
+    if (fill >= 32) {
+      store((unsigned)(acc >> (fill - 32)));
+      widx++;
+      fill -= 32;
+    }
+  }
 };
 
-template <bool EMIT>
-__device__ __forceinline__ unsigned encode_block(const uint32_t* __restrict__ tile, int j, unsigned long long mask, int dc_diff,
-                                                 const uint32_t* __restrict__ dcb, const uint32_t* __restrict__ acb, uint32_t* seg,
-                                                 unsigned bitpos, unsigned win) {
-  unsigned total = 0;
-  unsigned long long acc = 0;
-  int fill = (int)(bitpos & 31);
-  unsigned widx = bitpos >> 5;
-  auto put = [&](unsigned bits, int n) {
-    total += n;
-    if (EMIT) {
-      acc = (acc << n) | bits;
-      fill += n;
-      if (fill >= 32) {
-        if (widx - win < kSegWords) atomicOr(seg + (widx - win), (unsigned)(acc >> (fill - 32)));
-        widx++;
-        fill -= 32;
-      }
-    }
-  };
+__device__ __forceinline__ int coef_at(const uint4& c8, const int16_t* __restrict__ src, int k) {
+  if (k < 8) {  // the first eight zigzag coefficients came with the 16-byte load of phase 1
+    const unsigned w = (k & 4) ? ((k & 2) ? c8.w : c8.z) : ((k & 2) ? c8.y : c8.x);
+    return (int)(short)((w >> ((k & 1) * 16)) & 0xffffu);
+  }
+  return (int)__ldg(src + k);
+}
+
+__device__ __forceinline__ void emit_block(Emitter& E, unsigned long long mask, int dc_diff, const uint4& c8,
+                                           const int16_t* __restrict__ src, const uint32_t* dcb, const uint32_t* acb) {
   {
     const int mag = abs(dc_diff);
     const int nb = mag ? 32 - __clz(mag) : 0;
-    const uint32_t e = __ldg(dcb + nb);
+    const uint32_t e = dcb[nb];
     const unsigned low = (unsigned)(dc_diff < 0 ? dc_diff - 1 : dc_diff) & ((1u << nb) - 1u);
-    put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
+    E.put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
   }
   int last = 0;
-  const uint32_t zrl = __ldg(acb + 0xF0);
+  const uint32_t zrl = acb[0xF0];
   while (mask) {
     const int k = __ffsll((long long)mask) - 1;
     mask &= mask - 1;
     int run = k - last - 1;
     last = k;
     while (run > 15) {
-      put(zrl >> 8, (int)(zrl & 0xff));
+      E.put(zrl >> 8, (int)(zrl & 0xff));
       run -= 16;
     }
-    const uint32_t w = tile[(k >> 1) * kTileStride + j];
-    const int v = (int)(short)((w >> ((k & 1) * 16)) & 0xffff);
+    const int v = coef_at(c8, src, k);
     const int mag = abs(v);
     const int nb = 32 - __clz(mag);
-    const uint32_t e = __ldg(acb + ((run << 4) | nb));
+    const uint32_t e = acb[(run << 4) | nb];
     const unsigned low = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
-    put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
+    E.put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
   }
   if (last != 63) {
-    const uint32_t e = __ldg(acb);
-    put(e >> 8, (int)(e & 0xff));
+    const uint32_t e = acb[0];
+    E.put(e >> 8, (int)(e & 0xff));
   }
-  if (EMIT && (fill & 31) && widx - win < kSegWords) atomicOr(seg + (widx - win), (unsigned)(acc << (32 - fill)));
-  return total;
+  if (E.fill) E.store((unsigned)(E.acc << (32 - E.fill)));
 }
 
-// status[i]: look-back word of CTA i (flag | bits);  tails[i]: (1 << 32 | trailing partial word) once known
-// ctl[0] <- total bits, ctl[5] = ticket counter (zeroed by the caller together with status / tails)
-__global__ void __launch_bounds__(kEncBlocks) k_huff_encode(const HuffFrame f, const uint32_t* __restrict__ books,
-                                                            unsigned long long* status, unsigned long long* tails,
-                                                            unsigned* __restrict__ stream, unsigned cap_words, unsigned* ctl) {
-  extern __shared__ uint32_t enc_smem_raw[];
-  EncSmem& sm = *reinterpret_cast<EncSmem*>(enc_smem_raw);
-  __shared__ unsigned s_cta, s_base, s_total;
-  __shared__ const int16_t* s_src[kEncBlocks];
-  const int j = threadIdx.x;
-  if (j == 0) s_cta = atomicAdd(ctl + 5, 1u);
-  __syncthreads();
-  const unsigned cta = s_cta;
-  const unsigned s = cta * kEncBlocks + j;
-  const bool live = s < f.nblocks;
-  int c = 0;
-  int pred = 0;
-  if (live) {
-    unsigned blk;
-    long long prev;
-    locate(f, s, c, blk, prev);
-    s_src[j] = f.coefs[c] + (size_t)blk * 64;
-    pred = prev >= 0 ? (int)__ldg(f.coefs[c] + (size_t)prev * 64) : 0;
-  } else {
-    s_src[j] = nullptr;
-  }
-  __syncthreads();
-  // a. 8 lanes per block, 16 bytes each: 4 blocks = 512 contiguous bytes per warp instruction when the
-  //    blocks are neighbours in their plane
-  for (int i = j; i < kEncBlocks * 8; i += kEncBlocks) {
-    const int b = i >> 3, ch = i & 7;
-    const int16_t* src = s_src[b];
-    if (src) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + ch);
-      uint32_t* t = sm.tile + (ch * 4) * kTileStride + b;
-      t[0] = q.x; t[kTileStride] = q.y; t[2 * kTileStride] = q.z; t[3 * kTileStride] = q.w;
-    }
-  }
-  __syncthreads();
-  // b. non-zero mask and bit count
-  unsigned long long mask = 0;
-  int dc_diff = 0;
-  unsigned nbits = 0;
-  // code books (4 KB, hot in L1) are read through the read-only path: keeping them out of shared
-  // memory buys two more resident CTAs per SM
-  const uint32_t* dcb = books + (c == 0 ? 0 : 512);
-  const uint32_t* acb = books + (c == 0 ? 256 : 768);
-  if (live) {
-#pragma unroll
-    for (int r = 0; r < 32; r++) {
-      const uint32_t w = sm.tile[r * kTileStride + j];
-      if (w & 0xffffu) mask |= 1ull << (2 * r);
-      if (w >> 16) mask |= 2ull << (2 * r);
-    }
-    dc_diff = (int)(short)(sm.tile[j] & 0xffff) - pred;
-    mask &= ~1ull;
-    nbits = encode_block<false>(sm.tile, j, mask, dc_diff, dcb, acb, nullptr, 0, 0);
-  }
-  // c. offsets inside the CTA
-  unsigned total;
-  const unsigned off = block_exclusive_scan(nbits, &total);
-  // d. absolute offset: publish the aggregate, then look back (warp 0, 32 predecessors at a time)
-  if (j == 0) {
-    *reinterpret_cast<volatile unsigned long long*>(status + cta) = (cta == 0 ? kFlagPrefix : kFlagAgg) | total;
-    s_total = total;
-  }
-  if (j < 32 && cta > 0) {
-    const unsigned base = lookback_sum(status, cta, j);
-    if (j == 0) {
-      s_base = base;
-      *reinterpret_cast<volatile unsigned long long*>(status + cta) = kFlagPrefix | (unsigned long long)(base + total);
-    }
-  } else if (j == 0 && cta == 0) {
-    s_base = 0;
-  }
-  __syncthreads();
-  const unsigned base = s_base;
-  const unsigned sh = base & 31, first = base >> 5;
-  const unsigned endbit = sh + total;              // relative to word `first`
-  const unsigned nwords = (endbit + 31) >> 5;      // words of the segment image in use
-  const bool overflow = (unsigned long long)first + nwords + 1 > cap_words;
-  // e./f. segment image, one window of kSegWords words at a time; full words are stored coalesced,
-  //       the head word (index 0) and the trailing partial word (index lastw) are kept for step g
-  const unsigned tailbits = endbit & 31;
-  const unsigned lastw = endbit >> 5;              // index (relative) of the word holding the trailing partial bits
-  const bool is_last = (cta + 1) * (unsigned)kEncBlocks >= f.nblocks;
-  __shared__ unsigned s_head, s_tail;
-  for (unsigned win = 0; win < nwords; win += kSegWords) {
-    const unsigned wn = min(kSegWords, nwords - win);
-    for (unsigned i = j; i < wn; i += kEncBlocks) sm.seg[i] = 0;
-    __syncthreads();
-    if (live) encode_block<true>(sm.tile, j, mask, dc_diff, dcb, acb, sm.seg, sh + off, win);
-    __syncthreads();
-    if (!overflow)
-      for (unsigned i = j; i < wn; i += kEncBlocks) {
-        const unsigned w = win + i;
-        if (w >= 1 && w < lastw) stream[first + w] = sm.seg[i];
-      }
-    if (j == 0) {
-      if (win == 0) s_head = sm.seg[0];
-      if (lastw >= win && lastw < win + wn) s_tail = sm.seg[lastw - win];
-    }
-    __syncthreads();
-  }
-  // g. boundary words
-  if (j == 0) {
-    // a non-degenerate segment hands its trailing partial word on *before* waiting for the
-    // predecessor's: otherwise every CTA would wait for the whole chain in front of it
-    const unsigned tail = (lastw > 0 && tailbits) ? s_tail : 0u;
-    if (lastw > 0) {
-      *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | tail;
-      if (is_last && tailbits && !overflow) stream[first + lastw] = tail;
-    }
-    unsigned head = s_head;
-    if (sh > 0) {  // leading bits of word `first` belong to the predecessor
-      unsigned long long t;
-      do { t = *reinterpret_cast<volatile unsigned long long*>(tails + cta - 1); } while ((t >> 32) == 0);
-      head |= (unsigned)t;
-    }
-    if (lastw > 0) {
-      if (!overflow) stream[first] = head;
-    } else {
-      // the whole segment lies inside word `first` (only a short last CTA can be this small): the
-      // merged word is also our trailing partial word
-      if (is_last && !overflow) stream[first] = head;
-      *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | head;
-    }
-    if (overflow) ctl[4] = 1;
-    if (is_last) ctl[0] = base + total;
-  }
-}
-
-// ---- E2: byte stuffing ---------------------------------------------------------------------------
-// logical word j of `stream` holds stream bytes 4j..4j+3, first byte in the most significant bits
-__device__ __forceinline__ unsigned load_padded_word(const unsigned* stream, unsigned j, unsigned total_bits) {
-  unsigned v = stream[j];
-  const unsigned total_bytes = (total_bits + 7) >> 3;
-  const unsigned pad = total_bytes * 8 - total_bits;  // jchuff.c flush_bits: fill with ones
-  if (pad && j == (total_bytes - 1) >> 2) {
-    const unsigned byte_in_word = (total_bytes - 1) & 3;
-    v |= ((1u << pad) - 1u) << (24 - 8 * byte_in_word);
-  }
-  return v;
-}
-__device__ __forceinline__ unsigned ff_count(unsigned v, unsigned j, unsigned total_bytes) {
+__device__ __forceinline__ unsigned ff_count(unsigned v, int nvalid) {
   unsigned c = 0;
 #pragma unroll
   for (int b = 0; b < 4; b++)
-    if (4 * j + b < total_bytes && ((v >> (24 - 8 * b)) & 0xff) == 0xff) c++;
+    if (b < nvalid && ((v >> (24 - 8 * b)) & 0xff) == 0xff) c++;
   return c;
 }
-// count + look-back + write in one launch: persistent CTAs take 1024-word tiles in ticket order
-// ctl[0] total bits (in), ctl[3] <- stuffed bytes, ctl[4] <- overflow, ctl[6] = tile tickets (zeroed by the caller)
-__global__ void __launch_bounds__(kScanTile) k_stuff_lb(const unsigned* __restrict__ stream, unsigned* ctl, unsigned long long* status,
-                                                        uint8_t* __restrict__ out, unsigned out_cap) {
-  __shared__ unsigned s_tile, s_base;
-  const unsigned total_bits = ctl[0];
-  const unsigned total_bytes = (total_bits + 7) >> 3;
-  const unsigned nwords = (total_bytes + 3) >> 2;
-  const unsigned ntiles = (nwords + kScanTile - 1) / kScanTile;
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = atomicAdd(ctl + 6, 1u);
-    __syncthreads();
-    const unsigned tile = s_tile;
-    if (tile >= ntiles) break;
-    const unsigned j = tile * kScanTile + threadIdx.x;
-    unsigned v = 0, c = 0;
-    if (j < nwords) {
-      v = load_padded_word(stream, j, total_bits);
-      c = ff_count(v, j, total_bytes);
+
+// status   : bit-count look-back words, one per CTA        ffstatus : the same for the stuffed-zero counts
+// tails[i] : (1 << 32 | trailing partial word of CTA i) once known
+// ctl[0] <- total bits, ctl[3] <- stuffed bytes, ctl[4] <- overflow flag, ctl[5] = CTA tickets (all zeroed by the caller)
+__global__ void __launch_bounds__(kEncThreads) k_huff_encode(const __grid_constant__ HuffFrame f, const uint32_t* __restrict__ books,
+                                                             unsigned long long* status, unsigned long long* ffstatus,
+                                                             unsigned long long* tails, uint8_t* __restrict__ out,
+                                                             unsigned out_cap, unsigned* ctl) {
+  __shared__ uint32_t s_books[1024];  // (code << 8 | length): DC lum, AC lum, DC chr, AC chr
+  __shared__ uint32_t seg[kSegWords];
+  __shared__ unsigned s_cta, s_base, s_ffbase, s_predtail, s_ffrun;
+  const int j = threadIdx.x;
+  if (j == 0) {
+    s_cta = atomicAdd(ctl + 5, 1u);  // ticket order: every predecessor is already running or done
+    s_ffrun = 0;
+    s_predtail = 0;
+  }
+  for (int i = j; i < 1024; i += kEncThreads) s_books[i] = __ldg(books + i);
+  __syncthreads();
+  const unsigned cta = s_cta;
+  const unsigned s = cta * kEncThreads + j;
+  const bool live = s < f.nblocks;
+
+  // 1. the block, its code length
+  unsigned long long mask = 0;
+  unsigned nbits = 0;
+  int dc_diff = 0, c = 0;
+  uint4 c8 = make_uint4(0, 0, 0, 0);
+  const int16_t* src = nullptr;
+  if (live) {
+    const Loc L = locate(f, s);
+    c = L.c;
+    const int pred = L.pred >= 0 ? (int)__ldg(&f.meta[c][L.pred].w) : 0;
+    if (L.real) {
+      const uint4 m = __ldg(f.meta[c] + L.blk);
+      mask = (((unsigned long long)m.y << 32) | m.x) & ~1ull;
+      src = f.coefs[c] + (size_t)L.blk * 64;
+      c8 = __ldg(reinterpret_cast<const uint4*>(src));
+      dc_diff = (int)m.w - pred;
+      nbits = m.z;
+    } else {
+      nbits = s_books[(c ? 768 : 256)] & 0xff;  // dummy block: DC difference 0, then EOB
     }
-    unsigned t;
-    const unsigned e = block_exclusive_scan(c, &t);
-    if (threadIdx.x == 0) {
-      *reinterpret_cast<volatile unsigned long long*>(status + tile) = (tile == 0 ? kFlagPrefix : kFlagAgg) | t;
-      if (tile == 0) s_base = 0;
-    }
-    if (threadIdx.x < 32 && tile > 0) {
-      const unsigned b = lookback_sum(status, tile, (int)threadIdx.x);
-      if (threadIdx.x == 0) {
-        s_base = b;
-        *reinterpret_cast<volatile unsigned long long*>(status + tile) = kFlagPrefix | (unsigned long long)(b + t);
+    const int mag = abs(dc_diff);
+    const int nb = mag ? 32 - __clz(mag) : 0;
+    nbits += (s_books[(c ? 512 : 0) + nb] & 0xff) + nb;
+  }
+  const uint32_t* dcb = s_books + (c ? 512 : 0);
+  const uint32_t* acb = s_books + (c ? 768 : 256);
+
+  // 2. bit offsets
+  unsigned total;
+  const unsigned off = block_exclusive_scan(nbits, &total);
+  chain_prefix(status, cta, total, j, &s_base);
+  __syncthreads();
+  const unsigned base = s_base;
+  const unsigned sh = base & 31, first = base >> 5;
+  const unsigned endbit = sh + total;            // relative to word `first`
+  const unsigned nwords = (endbit + 31) >> 5;    // words of the segment image in use
+  const unsigned tailbits = endbit & 31;
+  const unsigned lastw = endbit >> 5;            // index of the word holding the trailing partial bits (if any)
+  const bool is_last = (cta + 1) * (unsigned)kEncThreads >= f.nblocks;
+  // words this CTA writes out: those whose last bit lies in its segment -- 0 .. lastw-1 -- and, for the
+  // last CTA, the padded partial word.  Word 0 may start with bits of the predecessor (sh > 0).
+  const unsigned own_end = lastw + ((is_last && tailbits) ? 1u : 0u);
+  const unsigned pos_lo = sh + off, pos_hi = pos_lo + nbits;  // this thread's bits, relative to word `first`
+  const int npass = nwords > kSegWords ? 2 : 1;   // several windows: count the 0xFF bytes first, write in a second sweep
+
+  for (int pass = 0; pass < npass; pass++) {
+    const bool do_write = pass == npass - 1;
+    for (unsigned win = 0; win < nwords; win += kSegWords) {
+      const unsigned wn = min(kSegWords, nwords - win);
+      for (unsigned i = j; i < wn; i += kEncThreads) seg[i] = 0;
+      __syncthreads();
+      // 3. codes of the blocks that reach into this window
+      if (live && pos_hi > win * 32 && pos_lo < (win + wn) * 32) {
+        Emitter E;
+        E.seg = seg; E.win = win; E.wn = wn;
+        E.first_w = pos_lo >> 5; E.last_w = (pos_hi - 1) >> 5;
+        E.acc = 0; E.fill = (int)(pos_lo & 31); E.widx = pos_lo >> 5;
+        emit_block(E, mask, dc_diff, c8, src, dcb, acb);
       }
-    }
-    __syncthreads();
-    const unsigned base = s_base;
-    if (tile == ntiles - 1 && threadIdx.x == 0) {
-      ctl[3] = total_bytes + base + t;
-      if (total_bytes + base + t > out_cap) ctl[4] = 1;
-    }
-    if (j < nwords) {
-      unsigned pos = 4 * j + base + e;
-#pragma unroll
-      for (int b = 0; b < 4; b++) {
-        if (4 * j + b >= total_bytes) break;
-        const uint8_t byte = (uint8_t)((v >> (24 - 8 * b)) & 0xff);
-        if (pos < out_cap) out[pos] = byte;
-        pos++;
-        if (byte == 0xff) {
-          if (pos < out_cap) out[pos] = 0;
-          pos++;
+      __syncthreads();
+      // 4. boundary words
+      if (j == 0) {
+        const bool tail_here = tailbits && lastw >= win && lastw < win + wn;
+        // a non-degenerate segment hands its trailing partial word on *before* waiting for the
+        // predecessor's: otherwise every CTA would wait for the whole chain in front of it
+        if (pass == 0 && tail_here && lastw > 0)
+          *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | seg[lastw - win];
+        if (win == 0 && sh > 0) {  // leading bits of word `first` belong to the predecessor
+          if (pass == 0) {
+            unsigned long long t;
+            do { t = *reinterpret_cast<volatile unsigned long long*>(tails + cta - 1); } while ((t >> 32) == 0);
+            s_predtail = (unsigned)t;
+          }
+          seg[0] |= s_predtail;
+        }
+        // the whole segment lies inside word `first` (only a short last CTA can be this small): the
+        // merged word is also our trailing partial word
+        if (pass == 0 && tail_here && lastw == 0)
+          *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | seg[0];
+        if (is_last && tail_here) {  // jchuff.c flush_bits: fill the last byte with ones
+          const unsigned pad = (8 - (tailbits & 7)) & 7;
+          seg[lastw - win] |= ((1u << pad) - 1u) << (32 - tailbits - pad);
         }
       }
+      __syncthreads();
+      // 5. byte stuffing: thread j takes words win + 8j .. win + 8j + 7 of the image
+      unsigned w[kWordsPerThread];
+      int nv[kWordsPerThread];
+      unsigned cnt = 0;
+#pragma unroll
+      for (int u = 0; u < kWordsPerThread; u++) {
+        const unsigned r = j * kWordsPerThread + u, i = win + r;
+        nv[u] = 0;
+        w[u] = 0;
+        if (r < wn && i < own_end) {
+          w[u] = seg[r];
+          nv[u] = (is_last && i == lastw) ? (int)((tailbits + 7) >> 3) : 4;
+          cnt += ff_count(w[u], nv[u]);
+        }
+      }
+      unsigned ffwin;
+      const unsigned ffoff = block_exclusive_scan(cnt, &ffwin);
+      if (npass == 1) {
+        chain_prefix(ffstatus, cta, ffwin, j, &s_ffbase);
+        __syncthreads();
+      }
+      if (do_write) {
+        const unsigned ffb = s_ffbase + s_ffrun + ffoff;
+        unsigned pos = 4u * (first + win + j * kWordsPerThread) + ffb;
+        bool ovf = false;
+#pragma unroll
+        for (int u = 0; u < kWordsPerThread; u++) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (b < nv[u]) {
+              const unsigned byte = (w[u] >> (24 - 8 * b)) & 0xff;
+              if (pos < out_cap) out[pos] = (uint8_t)byte; else ovf = true;
+              pos++;
+              if (byte == 0xff) {
+                if (pos < out_cap) out[pos] = 0; else ovf = true;
+                pos++;
+              }
+            }
+          }
+        }
+        if (ovf) ctl[4] = 1;
+      }
+      __syncthreads();
+      if (j == 0) s_ffrun += ffwin;
+      __syncthreads();
     }
+    if (npass == 2 && pass == 0) {  // all windows counted: chain the stuffed-zero counts, then sweep again
+      const unsigned agg = s_ffrun;
+      __syncthreads();
+      chain_prefix(ffstatus, cta, agg, j, &s_ffbase);
+      if (j == 0) s_ffrun = 0;
+      __syncthreads();
+    }
+  }
+  if (is_last && j == 0) {
+    const unsigned total_bits = base + total;
+    ctl[0] = total_bits;
+    ctl[3] = ((total_bits + 7) >> 3) + s_ffbase + s_ffrun;
+    if (ctl[3] > out_cap) ctl[4] = 1;
   }
 }
 
-struct DeviceBooks {
-  uint32_t* d = nullptr;
-};
 static int device_books(const uint32_t** out) {
   static thread_local int cached_dev = -1;
   static thread_local uint32_t* cached = nullptr;
@@ -417,7 +421,8 @@ bool gpu_entropy_available() { return true; }
 
 int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   const JpegFrame& fr = job->frame;
-  if (fr.has_dummy_blocks()) return fail(E_UNSUPPORTED, "device entropy coder needs whole MCUs");
+  if (!job->zigzag || !job->d_meta[0])
+    return fail(E_ERROR, "internal: device entropy coder needs the zigzag forward stage and its block side information");
   const uint32_t* books = nullptr;
   int rc = device_books(&books);
   if (rc) return rc;
@@ -428,51 +433,37 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   int k = 0;
   for (int c = 0; c < fr.ncomp; c++) {
     f.coefs[c] = job->d_coefs[c];
+    f.meta[c] = job->d_meta[c];
     f.wblocks[c] = fr.comp[c].wblocks;
+    f.hblocks[c] = fr.comp[c].hblocks;
     f.mw[c] = fr.ncomp == 1 ? 1 : fr.comp[c].h_samp;
     f.mh[c] = fr.ncomp == 1 ? 1 : fr.comp[c].v_samp;
     f.koff[c] = k;
     k += f.mw[c] * f.mh[c];
   }
   f.blocks_per_mcu = k;
-  const size_t nblocks = fr.total_blocks();
+  const size_t nblocks = (size_t)fr.mcus_per_row * fr.mcu_rows * k;  // dummy blocks included
   f.nblocks = (unsigned)nblocks;
   // capacity of the entropy-coded segment: the reference's whole output buffer is w*h*6 bytes
   // (ultrahdr_api.cpp:1294); a single scan can never need more than that in a valid encode
   const size_t cap = ((size_t)fr.width * fr.height * 6 + 4096 + 3) / 4 * 4;
-  const unsigned cap_words = (unsigned)(cap / 4);
-  const unsigned ntiles_words = (cap_words + kScanTile - 1) / kScanTile;
-  const unsigned ncta = (unsigned)((nblocks + kEncBlocks - 1) / kEncBlocks);
-  // [ctl 64 B][status ncta x 8][tails ncta x 8], zeroed together
-  const size_t ctl_bytes = 64 + (size_t)ncta * 16 + (size_t)ntiles_words * 8;
-  unsigned* ctl = (unsigned*)ws.dalloc(ctl_bytes);  // [0] total_bits [3] out_bytes [4] overflow [5] encoder CTA tickets [6] stuffing tile tickets
-  unsigned* stream = (unsigned*)ws.dalloc(cap + 64);
+  const unsigned ncta = (unsigned)((nblocks + kEncThreads - 1) / kEncThreads);
+  // [ctl 64 B][status ncta x 8][ffstatus ncta x 8][tails ncta x 8], zeroed together
+  const size_t ctl_bytes = 64 + (size_t)ncta * 24;
+  unsigned* ctl = (unsigned*)ws.dalloc(ctl_bytes);  // [0] total bits [3] out bytes [4] overflow [5] CTA tickets
   job->d_scan = (uint8_t*)ws.dalloc(cap + 64);
   job->h_scan_bytes = (unsigned*)ws.halloc(64);
-  if (!stream || !ctl || !job->d_scan || !job->h_scan_bytes) return E_MEM;
+  if (!ctl || !job->d_scan || !job->h_scan_bytes) return E_MEM;
   unsigned long long* status = reinterpret_cast<unsigned long long*>(ctl + 16);
-  unsigned long long* tails = status + ncta;
-  unsigned long long* stuff_status = tails + ncta;
+  unsigned long long* ffstatus = status + ncta;
+  unsigned long long* tails = ffstatus + ncta;
   job->d_scan_bytes = ctl + 3;
   job->scan_capacity = cap;
   cudaStream_t st = ws.stream();
   CUDA_TRY(cudaMemsetAsync(ctl, 0, ctl_bytes, st));
-  static bool smem_set[64] = {false};
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !smem_set[dev]) {
-      CUDA_TRY(cudaFuncSetAttribute(k_huff_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
-      smem_set[dev] = true;
-    }
-  }
-
-  count_launches(2);
+  count_launches(1);
   ws.t_begin("huff_encode");
-  k_huff_encode<<<ncta, kEncBlocks, sizeof(EncSmem), st>>>(f, books, status, tails, stream, cap_words, ctl);
-  ws.t_end();
-  ws.t_begin("huff_stuff");
-  k_stuff_lb<<<kPersistentCtas, kScanTile, 0, st>>>(stream, ctl, stuff_status, job->d_scan, (unsigned)cap);
+  k_huff_encode<<<ncta, kEncThreads, 0, st>>>(f, books, status, ffstatus, tails, job->d_scan, (unsigned)cap, ctl);
   ws.t_end();
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(job->h_scan_bytes, ctl, 32, cudaMemcpyDeviceToHost, st));

@@ -20,6 +20,11 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
   for (int c = 0; c < f.ncomp; c++) {
     job->d_coefs[c] = (int16_t*)ws.dalloc(f.blocks(c) * 128);
     if (!job->d_coefs[c]) return E_MEM;
+    job->d_meta[c] = nullptr;
+    if (zigzag) {  // side information for the device entropy coder
+      job->d_meta[c] = (uint4*)ws.dalloc(f.blocks(c) * sizeof(uint4));
+      if (!job->d_meta[c]) return E_MEM;
+    }
   }
   if (img.v.fmt == F_RGB888) {
     // jpeg_write_scanlines path: jccolor.c conversion, edges replicated (jcsample.c/jcprepct.c);
@@ -33,7 +38,12 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
     pl.wblocks = f.comp[0].wblocks;
     pl.hblocks = f.comp[0].hblocks;
     pl.rgb = 1;
-    for (int c = 0; c < 3; c++) { pl.tq[c] = f.comp[c].tq; pl.coefs[c] = job->d_coefs[c]; }
+    for (int c = 0; c < 3; c++) {
+      pl.tq[c] = f.comp[c].tq;
+      pl.coefs[c] = job->d_coefs[c];
+      pl.meta[c] = job->d_meta[c];
+      pl.hsel[c] = c == 0 ? 0 : 1;
+    }
   } else {
     // raw_data_in path (jpegencoderhelper.cpp:246-309): whole blocks are read from the plane
     // (device strides are >= wblocks*8 and the bytes past the width are defined, see
@@ -56,6 +66,8 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
       pl.fill = c == 0 ? 0 : 128;
       pl.tq[0] = k.tq;
       pl.coefs[0] = job->d_coefs[c];
+      pl.meta[0] = job->d_meta[c];
+      pl.hsel[0] = c == 0 ? 0 : 1;
     }
   }
   TIMED(ws, "fdct_quant", launch_fdct8(P, ws.stream()));

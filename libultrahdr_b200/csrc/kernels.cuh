@@ -119,6 +119,12 @@ struct Fdct8Plane {                 // one launch covers every plane of an image
   int fill, rgb;
   int tq[3];
   int16_t* coefs[3];                // plane: [0]; RGB888: Y, Cb, Cr
+  // entropy-coder side information, one uint4 per block (zigzag launches only; may be null):
+  //   x, y = 64-bit mask of the non-zero coefficients (bit k = zigzag position k, bit 0 = DC)
+  //   z    = code bits of the block's AC part: Huffman codes + magnitude bits + ZRLs + EOB
+  //   w    = the DC coefficient (sign extended)
+  uint4* meta[3];
+  int hsel[3];                      // Huffman table pair of the component: 0 luminance, 1 chrominance
 };
 struct Fdct8Params {
   Fdct8Plane plane[3];
@@ -126,6 +132,7 @@ struct Fdct8Params {
   uint16_t q[2][64];
   unsigned mag[2][64];              // ceil(2^32 / (8*q)), filled by launch_fdct8
   int tile_end[3];                  // cumulative count of 32-block tiles per plane, filled by launch_fdct8
+  uint8_t aclen[2][256];            // AC code length per (run << 4 | size) symbol, [0] luminance [1] chrominance
 };
 
 struct IdctPlaneParams {
