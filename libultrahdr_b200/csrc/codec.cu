@@ -271,11 +271,10 @@ int JpegRCodec::probe(const uint8_t* data, size_t size, DecodedInfo* info) {
   info->gainmap_off = go; info->gainmap_len = gl;
   grab_marker(data + po, ph, 0xE1, "Exif\0\0", 6, &info->exif);
   grab_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12, &info->icc);
-  std::vector<uint8_t> iso;
+  std::vector<uint8_t> iso, xmp;
   grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &iso);
-  if (iso.empty())
-    return fail(E_UNSUPPORTED, "gain map metadata in XMP form only; the B200 decoder reads ISO 21496-1 metadata");
-  rc = iso_decode_metadata(iso.data() + 28, iso.size() - 28, &info->metadata);
+  grab_marker(data + go, gh, 0xE1, "http://ns.adobe.com/xap/1.0/", 29, &xmp);
+  rc = parse_gainmap_metadata(iso.data(), iso.size(), xmp.data(), xmp.size(), info->exif.data(), info->exif.size(), &info->metadata);
   if (rc) return rc;
   info->has_metadata = true;
   return E_OK;
@@ -342,10 +341,11 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
       rc = jpeg_read_header(data + go, gl, &gh);
       if (rc) return rc;
     }
+    std::vector<uint8_t> xmp, exif;
     grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &blob);
-    if (blob.empty())
-      return fail(E_UNSUPPORTED, "gain map metadata in XMP form only; the B200 decoder reads ISO 21496-1 metadata");
-    rc = iso_decode_metadata(blob.data() + 28, blob.size() - 28, &md);
+    grab_marker(data + go, gh, 0xE1, "http://ns.adobe.com/xap/1.0/", 29, &xmp);
+    grab_marker(data + po, ph, 0xE1, "Exif\0\0", 6, &exif);
+    rc = parse_gainmap_metadata(blob.data(), blob.size(), xmp.data(), xmp.size(), exif.data(), exif.size(), &md);
     if (rc) return rc;
     if (md_out) *md_out = md;
   }

@@ -1,7 +1,10 @@
 #include "container.h"
 
+#include <cctype>
 #include <cmath>
 #include <cstring>
+#include <sstream>
+#include <string>
 
 #include "runtime.h"
 
@@ -214,6 +217,259 @@ const uint8_t* icc_profile(int ct, int cg, size_t* size) {
   if (ct < 0 || ct > 3 || cg < 0 || cg > 2) return nullptr;
   *size = kIccSizes[ct * 3 + cg];
   return kIccBlobs[ct * 3 + cg];
+}
+
+// ---- hdrgm XMP (Ultra HDR v1 / Apple) -----------------------------------------------------------
+namespace {
+// The reference feeds the packet to a SAX parser whose handler only looks at the rdf:Description
+// element: its attributes (hdrgm:*) and, for Apple files, its child elements HDRGainMapVersion /
+// HDRGainMapHeadroom.  The same information is collected here with a flat scan of the start tag.
+struct XmpFields {
+  std::string version, gmax, gmin, gamma, off_sdr, off_hdr, cap_min, cap_max, base_is_hdr;
+  bool has_version = false, has_gmax = false, has_gmin = false, has_gamma = false, has_off_sdr = false,
+       has_off_hdr = false, has_cap_min = false, has_cap_max = false, has_base_is_hdr = false;
+  bool apple = false, found_description = false;
+};
+bool is_name_char(char c) { return isalnum((unsigned char)c) || c == ':' || c == '_' || c == '-' || c == '.'; }
+
+void scan_xmp(const std::string& x, XmpFields* f) {
+  size_t p = x.find("<rdf:Description");
+  if (p == std::string::npos) return;
+  f->found_description = true;
+  p += 16;
+  // attributes of the start tag
+  bool self_closed = false;
+  while (p < x.size()) {
+    while (p < x.size() && isspace((unsigned char)x[p])) p++;
+    if (p >= x.size()) return;
+    if (x[p] == '>') { p++; break; }
+    if (x[p] == '/' && p + 1 < x.size() && x[p + 1] == '>') { self_closed = true; p += 2; break; }
+    size_t a = p;
+    while (p < x.size() && is_name_char(x[p])) p++;
+    if (p == a) { p++; continue; }
+    const std::string name = x.substr(a, p - a);
+    while (p < x.size() && isspace((unsigned char)x[p])) p++;
+    if (p >= x.size() || x[p] != '=') continue;
+    p++;
+    while (p < x.size() && isspace((unsigned char)x[p])) p++;
+    if (p >= x.size() || (x[p] != '"' && x[p] != '\'')) continue;
+    const char quote = x[p++];
+    a = p;
+    while (p < x.size() && x[p] != quote) p++;
+    const std::string val = x.substr(a, p - a);
+    if (p < x.size()) p++;
+    auto take = [&](const char* n, std::string* dst, bool* flag) {
+      if (name == n) { *dst = val; *flag = true; }
+    };
+    take("hdrgm:Version", &f->version, &f->has_version);
+    take("hdrgm:GainMapMax", &f->gmax, &f->has_gmax);
+    take("hdrgm:GainMapMin", &f->gmin, &f->has_gmin);
+    take("hdrgm:Gamma", &f->gamma, &f->has_gamma);
+    take("hdrgm:OffsetSDR", &f->off_sdr, &f->has_off_sdr);
+    take("hdrgm:OffsetHDR", &f->off_hdr, &f->has_off_hdr);
+    take("hdrgm:HDRCapacityMin", &f->cap_min, &f->has_cap_min);
+    take("hdrgm:HDRCapacityMax", &f->cap_max, &f->has_cap_max);
+    take("hdrgm:BaseRenditionIsHDR", &f->base_is_hdr, &f->has_base_is_hdr);
+  }
+  if (self_closed) return;
+  // child elements up to </rdf:Description>: Apple's <...:HDRGainMapVersion>n</...> and <...:HDRGainMapHeadroom>x</...>
+  const size_t end = x.find("</rdf:Description", p);
+  const std::string body = x.substr(p, end == std::string::npos ? std::string::npos : end - p);
+  auto child_text = [&](const char* key, std::string* dst) {
+    size_t q = 0;
+    while ((q = body.find(key, q)) != std::string::npos) {
+      // must be inside a start tag: the nearest '<' before it is not "</"
+      const size_t lt = body.rfind('<', q);
+      if (lt != std::string::npos && lt + 1 < body.size() && body[lt + 1] != '/') {
+        const size_t gt = body.find('>', q);
+        if (gt == std::string::npos) return false;
+        const size_t lt2 = body.find('<', gt);
+        *dst = body.substr(gt + 1, lt2 == std::string::npos ? std::string::npos : lt2 - gt - 1);
+        return true;
+      }
+      q += strlen(key);
+    }
+    return false;
+  };
+  std::string v;
+  if (child_text("HDRGainMapVersion", &v)) {
+    f->version = v;
+    f->has_version = true;
+    f->apple = true;
+  }
+  if (child_text("HDRGainMapHeadroom", &v)) {
+    f->gmax = v;
+    f->has_gmax = true;
+  }
+}
+// `stringstream >> float` of the reference
+bool parse_float(const std::string& str, float* out) {
+  std::stringstream ss(str);
+  float v;
+  if (ss >> v) { *out = v; return true; }
+  return false;
+}
+
+bool rd16(const uint8_t* d, size_t n, uint16_t* v, size_t* off, bool be) {
+  if (*off > n || n - *off < 2) return false;
+  *v = be ? (uint16_t)((d[*off] << 8) | d[*off + 1]) : (uint16_t)(d[*off] | (d[*off + 1] << 8));
+  *off += 2;
+  return true;
+}
+bool rd32(const uint8_t* d, size_t n, uint32_t* v, size_t* off, bool be) {
+  if (*off > n || n - *off < 4) return false;
+  *v = be ? ((uint32_t)d[*off] << 24) | ((uint32_t)d[*off + 1] << 16) | ((uint32_t)d[*off + 2] << 8) | d[*off + 3]
+          : (uint32_t)d[*off] | ((uint32_t)d[*off + 1] << 8) | ((uint32_t)d[*off + 2] << 16) | ((uint32_t)d[*off + 3] << 24);
+  *off += 4;
+  return true;
+}
+// getExifAppleHeadroom, jpegrutils.cpp:506-644: Apple maker-note tags 33 and 48 -> headroom
+bool exif_apple_headroom(const uint8_t* exif, size_t size, float* headroom) {
+  *headroom = 0.0f;
+  size_t offset = 0;
+  if (size < 6 || memcmp(exif, "Exif\0\0", 6) != 0) {
+    bool found = false;
+    for (size_t i = 0; i + 4 <= size; i++)
+      if ((exif[i] == 'I' && exif[i + 1] == 'I' && exif[i + 2] == 0x2A && exif[i + 3] == 0) ||
+          (exif[i] == 'M' && exif[i + 1] == 'M' && exif[i + 2] == 0 && exif[i + 3] == 0x2A)) {
+        offset = i;
+        found = true;
+        break;
+      }
+    if (!found) return false;
+  } else {
+    offset = 6;
+  }
+  if (offset + 4 > size) return false;
+  bool be = exif[offset] == 'M';
+  offset += 4;
+  uint32_t ifd;
+  if (!rd32(exif, size, &ifd, &offset, be)) return false;
+  static const uint8_t kAppleHdr[] = {'A', 'p', 'p', 'l', 'e', ' ', 'i', 'O', 'S', 0, 0, 1, 'M', 'M'};
+  bool in_apple = false, has = false;
+  double m33 = 0.0, m48 = 0.0;
+  int nifd = 0;
+  const size_t tiff = offset - 8;
+  while (ifd != 0 && nifd++ < 3) {
+    offset = tiff + ifd;
+    bool next_set = false;
+    uint16_t count;
+    if (!rd16(exif, size, &count, &offset, be)) return false;
+    for (uint16_t fidx = 0; fidx < count; ++fidx) {
+      uint16_t tag, fmt;
+      uint32_t ncomp, data;
+      if (!rd16(exif, size, &tag, &offset, be) || !rd16(exif, size, &fmt, &offset, be) ||
+          !rd32(exif, size, &ncomp, &offset, be) || !rd32(exif, size, &data, &offset, be))
+        return false;
+      if (tag == 0x8769) {
+        ifd = data;
+        next_set = true;
+        break;
+      } else if (tag == 0x927c) {
+        if (tiff + data + sizeof kAppleHdr <= size && !memcmp(exif + tiff + data, kAppleHdr, sizeof kAppleHdr)) {
+          ifd = data + (uint32_t)sizeof kAppleHdr;
+          in_apple = true;
+          next_set = true;
+          be = true;
+          break;
+        }
+      } else if (in_apple && (tag == 33 || tag == 48) && fmt == 10) {
+        if (tiff + ifd < sizeof kAppleHdr) return false;
+        size_t t = tiff + ifd - sizeof kAppleHdr;
+        if (t > SIZE_MAX - (size_t)data) return false;
+        t += data;
+        uint32_t num, den;
+        if (!rd32(exif, size, &num, &t, be) || !rd32(exif, size, &den, &t, be)) return false;
+        if (den != 0) {
+          const double v = (double)(int32_t)num / den;
+          (tag == 33 ? m33 : m48) = v;
+          has = true;
+        }
+      }
+    }
+    if (!next_set && !rd32(exif, size, &ifd, &offset, be)) return false;
+  }
+  if (!has) return false;
+  double stops;
+  if (m33 < 1.0) stops = m48 <= 0.01 ? -20.0 * m48 + 1.8 : -0.101 * m48 + 1.601;
+  else stops = m48 <= 0.01 ? -70.0 * m48 + 3.0 : -0.303 * m48 + 2.303;
+  *headroom = (float)pow(2.0, stops);
+  return true;
+}
+}  // namespace
+
+int xmp_decode_metadata(const uint8_t* xmp, size_t n, const uint8_t* exif, size_t exif_n, uhdr_gainmap_metadata_t* md) {
+  static const char kNs[] = "http://ns.adobe.com/xap/1.0/";  // 28 chars + NUL in the marker
+  const size_t ns = sizeof kNs - 1;
+  if (n < ns + 2) return fail(E_ERROR, "size of xmp block is expected to be atleast %zd bytes, received only %zd bytes", ns + 2, n);
+  if (strncmp((const char*)xmp, kNs, ns)) return fail(E_ERROR, "mismatch in namespace of xmp block. Expected %s", kNs);
+  const std::string x((const char*)xmp + ns + 1, n - ns - 1);
+  XmpFields f;
+  scan_xmp(x, &f);
+  float v;
+  if (f.apple) {  // jpegrutils.cpp:723-760
+    for (int c = 0; c < 3; c++) {
+      md->gamma[c] = 1.0f;
+      md->min_content_boost[c] = 1.0f;
+      md->offset_sdr[c] = md->offset_hdr[c] = 0.0f;
+    }
+    md->hdr_capacity_min = 1.0f;
+    float boost;
+    if (f.has_gmax && parse_float(f.gmax, &v)) boost = exp2(v);
+    else if (!(exif && exif_n > 0 && exif_apple_headroom(exif, exif_n, &boost)))
+      return fail(E_ERROR, "xml parse error, could not find attribute HDRGainMapHeadroom and Exif Headroom missing");
+    for (int c = 0; c < 3; c++) md->max_content_boost[c] = boost;
+    md->hdr_capacity_max = boost;
+    // the reference leaves use_base_cg of its (uninitialised) descriptor untouched on this branch; any
+    // non-zero garbage reads as true, which is also what the non-Apple XMP branch sets
+    md->use_base_cg = 1;
+    return E_OK;
+  }
+  // required: Version, GainMapMax, HDRCapacityMax; the others default (:762-873).  exp2 is the double
+  // function narrowed to float, like the reference's (jpegrutils.cpp has `using namespace std`: float
+  // overload, same value for float arguments)
+  if (!f.has_version) return fail(E_ERROR, "xml parse error, could not find attribute %s", "hdrgm:Version");
+  if (!(f.has_gmax && parse_float(f.gmax, &v))) return fail(E_ERROR, "xml parse error, could not find attribute %s", "hdrgm:GainMapMax");
+  md->max_content_boost[0] = std::exp2(v);
+  if (!(f.has_cap_max && parse_float(f.cap_max, &v))) return fail(E_ERROR, "xml parse error, could not find attribute %s", "hdrgm:HDRCapacityMax");
+  md->hdr_capacity_max = std::exp2(v);
+  auto opt = [&](bool has, const std::string& str, const char* name, float dflt, bool exp, float* dst) -> int {
+    float t;
+    if (parse_float(str, &t)) { *dst = exp ? std::exp2(t) : t; return E_OK; }
+    if (has) return fail(E_ERROR, "xml parse error, unable to parse attribute %s", name);
+    *dst = dflt;
+    return E_OK;
+  };
+  int rc;
+  if ((rc = opt(f.has_gmin, f.gmin, "hdrgm:GainMapMin", 1.0f, true, &md->min_content_boost[0]))) return rc;
+  if ((rc = opt(f.has_gamma, f.gamma, "hdrgm:Gamma", 1.0f, false, &md->gamma[0]))) return rc;
+  if ((rc = opt(f.has_off_sdr, f.off_sdr, "hdrgm:OffsetSDR", 1.0f / 64.0f, false, &md->offset_sdr[0]))) return rc;
+  if ((rc = opt(f.has_off_hdr, f.off_hdr, "hdrgm:OffsetHDR", 1.0f / 64.0f, false, &md->offset_hdr[0]))) return rc;
+  if ((rc = opt(f.has_cap_min, f.cap_min, "hdrgm:HDRCapacityMin", 1.0f, true, &md->hdr_capacity_min))) return rc;
+  if (f.has_base_is_hdr) {
+    if (f.base_is_hdr == "True") return fail(E_ERROR, "hdr intent as base rendition is not supported");
+    if (f.base_is_hdr != "False") return fail(E_ERROR, "xml parse error, unable to parse attribute %s", "hdrgm:BaseRenditionIsHDR");
+  }
+  md->use_base_cg = 1;
+  for (int c = 1; c < 3; c++) {
+    md->min_content_boost[c] = md->min_content_boost[0];
+    md->max_content_boost[c] = md->max_content_boost[0];
+    md->gamma[c] = md->gamma[0];
+    md->offset_hdr[c] = md->offset_hdr[0];
+    md->offset_sdr[c] = md->offset_sdr[0];
+  }
+  return validate_metadata(*md);
+}
+
+int parse_gainmap_metadata(const uint8_t* iso, size_t iso_n, const uint8_t* xmp, size_t xmp_n, const uint8_t* exif,
+                           size_t exif_n, uhdr_gainmap_metadata_t* md) {
+  static const size_t kIsoNs = 28;  // "urn:iso:std:iso:ts:21496:-1" + NUL
+  if (iso_n > 0) {
+    if (iso_n < kIsoNs) return fail(E_ERROR, "iso block size needs to be atleast %zd but got %zd", kIsoNs, iso_n);
+    return iso_decode_metadata(iso + kIsoNs, iso_n - kIsoNs, md);
+  }
+  if (xmp_n > 0) return xmp_decode_metadata(xmp, xmp_n, exif, exif_n, md);
+  return fail(E_INVALID_PARAM, "received no valid buffer to parse gainmap metadata");
 }
 
 int icc_read_gamut(const uint8_t* d, size_t n) {

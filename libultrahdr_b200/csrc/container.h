@@ -18,6 +18,15 @@ int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, std::vector<uint8_t>*
 // inverse (:195-347); validates like uhdr_validate_gainmap_metadata_descriptor
 int iso_decode_metadata(const uint8_t* data, size_t size, uhdr_gainmap_metadata_t* md);
 int validate_metadata(const uhdr_gainmap_metadata_t& md);
+// hdrgm XMP packet of the gain-map image's APP1 marker (Ultra HDR v1 files and Apple's variant carry
+// no ISO 21496-1 block): getMetadataFromXMP, jpegrutils.cpp:646-874, incl. the Apple branch that takes
+// the headroom from the XMP element or from the primary image's EXIF maker notes (:506-644).
+// `xmp` starts at the "http://ns.adobe.com/xap/1.0/" signature; `exif` may be null.
+int xmp_decode_metadata(const uint8_t* xmp, size_t size, const uint8_t* exif, size_t exif_size, uhdr_gainmap_metadata_t* md);
+// UltraHdr::parseGainMapMetadata (jpegr.cpp:1432-1466): ISO block if present, else XMP.  `iso` / `xmp`
+// are whole marker payloads (signature included) or empty.
+int parse_gainmap_metadata(const uint8_t* iso, size_t iso_size, const uint8_t* xmp, size_t xmp_size, const uint8_t* exif,
+                           size_t exif_size, uhdr_gainmap_metadata_t* md);
 
 // ICC profile (with "ICC_PROFILE" prefix) the reference writes for (ct, cg); nullptr if unknown
 const uint8_t* icc_profile(int ct, int cg, size_t* size);

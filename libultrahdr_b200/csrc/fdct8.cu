@@ -10,8 +10,10 @@
 // (grid.z), the three components of an RGB888 gain map are produced from one read of the pixels.
 // Arithmetic is libjpeg-turbo's jccolor.c / jfdctint.c / jcdctmgr.c integer arithmetic: bit-exact.
 #include <cstring>
+#include <mutex>
 
 #include "kernels.cuh"
+#include "runtime.h"
 
 namespace uhdr_b200 {
 
@@ -59,13 +61,20 @@ __device__ __forceinline__ int unzig_rt(int n) { return kUnzigTab[n]; }
 
 constexpr int kTileStride = 72;  // ints per block tile: 64 + 8 padding (4 blocks of a warp on distinct banks)
 
-// Side information for the device entropy coder (huffman.cu), computed while the quantised block is
-// still in the warp's shared-memory tile (zigzag order): the 64-bit mask of its non-zero
-// coefficients and the number of code bits its AC part takes (jchuff.c encode_one_block: run/size
-// Huffman codes, magnitude bits, a ZRL per 16 zeros, EOB unless coefficient 63 is non-zero).  Lane j
-// of the block's 8 lanes takes zigzag positions j, j+8, ... so that the few non-zeros of a typical
-// block, which sit at the lowest positions, spread over the lanes.
-__device__ __forceinline__ void block_meta(const int16_t* t16, const uint4 q, int lane_r, const uint8_t* aclen, uint4* meta_out) {
+// Entropy-coder front end (jchuff.c encode_one_block), run while the quantised block is still in the
+// warp's shared-memory tile (zigzag order).  Per block it leaves
+//   * the 64-bit mask of its non-zero coefficients, the number of code bits of its AC part (run/size
+//     Huffman codes, magnitude bits, a ZRL per 16 zeros, EOB unless coefficient 63 is non-zero) and
+//     the DC value: one uint4 of "meta";
+//   * one 32-bit entry per non-zero AC coefficient, in zigzag order, holding the coefficient's
+//     complete code word: [24:0] Huffman code followed by the magnitude bits (bit 25 of a 26-bit word
+//     is always 1: only the 16-bit codes, which all start with a one, can reach 26 bits), [29:25] the
+//     length, [31:30] the number of ZRL codes in front of it.
+// huffman.cu then only concatenates: coefficients are never stored for the device path.
+// Lane j of the block's 8 lanes takes zigzag positions j, j+8, ... so that the few non-zeros of a
+// typical block, which sit at the lowest positions, spread over the lanes.
+__device__ __forceinline__ void block_code(const int16_t* t16, const uint4 q, int lane_r, const uint32_t* acb, uint32_t* ent,
+                                           uint32_t* gout_entries, uint4* meta_out) {
   auto nz2 = [](unsigned w) { return ((w & 0xffffu) ? 1u : 0u) | ((w >> 16) ? 2u : 0u); };
   const unsigned m8 = nz2(q.x) | (nz2(q.y) << 2) | (nz2(q.z) << 4) | (nz2(q.w) << 6);  // positions 8r .. 8r+7
   unsigned lo = lane_r < 4 ? m8 << (8 * lane_r) : 0u, hi = lane_r >= 4 ? m8 << (8 * (lane_r - 4)) : 0u;
@@ -76,8 +85,9 @@ __device__ __forceinline__ void block_meta(const int16_t* t16, const uint4 q, in
   }
   const unsigned long long mask = ((unsigned long long)hi << 32) | lo;
   const unsigned long long anchored = mask | 1ull;  // runs are counted from the DC position
+  const unsigned long long mask_ac = mask & ~1ull;
   unsigned bits = 0;
-  const unsigned zrl = aclen[0xF0];
+  const unsigned zrl = acb[0xF0] & 0xff;
 #pragma unroll
   for (int half = 0; half < 2; half++) {
     unsigned mj = ((half ? hi : lo) >> lane_r) & 0x01010101u;
@@ -85,23 +95,33 @@ __device__ __forceinline__ void block_meta(const int16_t* t16, const uint4 q, in
     while (mj) {
       const int k = lane_r + (__ffs(mj) - 1) + 32 * half;
       mj &= mj - 1;
-      const int prev = 63 - __clzll((long long)(anchored & ((1ull << k) - 1ull)));
+      const unsigned long long below = (1ull << k) - 1ull;
+      const int prev = 63 - __clzll((long long)(anchored & below));
       const int run = k - prev - 1;
       const int v = t16[k];
       const int nb = 32 - __clz(abs(v));
-      bits += aclen[((run & 15) << 4) | nb] + nb + (run >> 4) * zrl;
+      const uint32_t e = acb[((run & 15) << 4) | nb];
+      const unsigned low = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
+      const unsigned len = (e & 0xff) + nb;
+      bits += len + (run >> 4) * zrl;
+      ent[__popcll(mask_ac & below)] = ((((e >> 8) << nb) | low) & 0x1ffffffu) | (len << 25) | ((unsigned)(run >> 4) << 30);
     }
   }
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
-  if (!(hi >> 31)) bits += aclen[0];  // EOB
+  if (!(hi >> 31)) bits += acb[0] & 0xff;  // EOB
+  __syncwarp();
+  if (gout_entries) {  // 16 bytes per lane and round; the tail of the last vector is don't-care
+    const int n = __popcll(mask_ac);
+    for (int base = 4 * lane_r; base < n; base += 32) *(uint4*)(gout_entries + base) = *(const uint4*)(ent + base);
+  }
   if (lane_r == 0 && meta_out) *meta_out = make_uint4(lo, hi, bits, (unsigned)(int)t16[0]);
 }
 
 template <bool ZIGZAG>
 __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int lane_r, const unsigned* sdiv,
                                             const unsigned* smag, const uint8_t* sunzig, int16_t* gout_block_base,
-                                            const uint8_t* aclen, uint4* meta_out) {
+                                            const uint32_t* acb, uint32_t* ent, uint4* meta_out) {
   // pass 1 on this lane's row, park it
   dct1d<0>(d);
   int* t = tile + lane_b * kTileStride;
@@ -129,8 +149,13 @@ __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int
   __syncwarp();
   // 16 bytes per lane: coefficients [8*lane_r, 8*lane_r + 8) of block lane_b
   const uint4 q = *(const uint4*)(t16 + lane_r * 8);
-  if (gout_block_base) *(uint4*)(gout_block_base + lane_r * 8) = q;
-  if (ZIGZAG) block_meta(t16, q, lane_r, aclen, meta_out);  // all 32 lanes take part (shuffles); dead lanes store nothing
+  if (ZIGZAG) {
+    // device entropy coder follows: code words instead of coefficients (all 32 lanes take part in the
+    // shuffles; dead lanes store nothing).  The block's slot holds 64 entries of 4 bytes.
+    block_code(t16, q, lane_r, acb, ent + lane_b * 64, gout_block_base ? reinterpret_cast<uint32_t*>(gout_block_base) : nullptr, meta_out);
+  } else if (gout_block_base) {
+    *(uint4*)(gout_block_base + lane_r * 8) = q;
+  }
   __syncwarp();
 }
 
@@ -139,10 +164,11 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
   __shared__ unsigned sdiv[2][64], smag[2][64];
   __shared__ int tiles[8][4 * kTileStride];
   __shared__ uint8_t sunzig[64];
-  __shared__ uint8_t saclen[2][256];
+  __shared__ uint32_t sacb[ZIGZAG ? 2 : 1][ZIGZAG ? 256 : 1];       // AC code books (code << 8 | length)
+  __shared__ uint32_t sent[ZIGZAG ? 8 : 1][ZIGZAG ? 4 * 64 : 1];      // per warp: code-word entries of its 4 blocks
   if (ZIGZAG) {
-    saclen[0][threadIdx.x] = P.aclen[0][threadIdx.x];
-    saclen[1][threadIdx.x] = P.aclen[1][threadIdx.x];
+    sacb[0][threadIdx.x] = __ldg(P.acbooks + threadIdx.x);
+    sacb[1][threadIdx.x] = __ldg(P.acbooks + 256 + threadIdx.x);
   }
   if (threadIdx.x >= 128 && threadIdx.x < 192) sunzig[threadIdx.x - 128] = (uint8_t)unzig_rt(threadIdx.x - 128);
   if (threadIdx.x < 128) {
@@ -181,9 +207,9 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
       }
     }
     const size_t bidx = (size_t)by * pl.wblocks + bx;
-    int16_t* out = live ? pl.coefs[0] + bidx * 64 : nullptr;
-    block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, out, saclen[pl.hsel[0]],
-                        live && pl.meta[0] ? pl.meta[0] + bidx : nullptr);
+    int16_t* out = live ? pl.coefs[0] + bidx * (ZIGZAG ? 128 : 64) : nullptr;
+    block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, out, sacb[ZIGZAG ? pl.hsel[0] : 0],
+                        sent[ZIGZAG ? warp : 0], live && pl.meta[0] ? pl.meta[0] + bidx : nullptr);
   } else {
     // RGB888: libjpeg's scanline path replicates the last column / row (jcsample.c, jcprepct.c)
     const int y = min(by * 8 + lane_r, pl.h - 1);
@@ -218,9 +244,9 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
         d[k] = v - 128;
       }
       const size_t bidx = (size_t)by * pl.wblocks + bx;
-      int16_t* out = live ? pl.coefs[comp] + bidx * 64 : nullptr;
-      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[comp]], smag[pl.tq[comp]], sunzig, out, saclen[pl.hsel[comp]],
-                          live && pl.meta[comp] ? pl.meta[comp] + bidx : nullptr);
+      int16_t* out = live ? pl.coefs[comp] + bidx * (ZIGZAG ? 128 : 64) : nullptr;
+      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[comp]], smag[pl.tq[comp]], sunzig, out, sacb[ZIGZAG ? pl.hsel[comp] : 0],
+                          sent[ZIGZAG ? warp : 0], live && pl.meta[comp] ? pl.meta[comp] + bidx : nullptr);
     }
   }
   }
@@ -230,21 +256,33 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
 
 void jpeg_std_codebook(int which, uint32_t out[256]);  // jpeg_host.cpp: (code << 8 | length) per symbol
 
+// the two AC code books (luminance, chrominance), once per device
+static int fdct_device_books(const uint32_t** out) {
+  static std::mutex mu;
+  static uint32_t* per_dev[64] = {nullptr};
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(E_ERROR, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (!per_dev[dev]) {
+    uint32_t host[512];
+    jpeg_std_codebook(1, host);
+    jpeg_std_codebook(3, host + 256);
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof host));
+    CUDA_TRY(cudaMemcpy(d, host, sizeof host, cudaMemcpyHostToDevice));
+    per_dev[dev] = d;
+  }
+  *out = per_dev[dev];
+  return E_OK;
+}
+
 cudaError_t launch_fdct8(const Fdct8Params& Pin, cudaStream_t s) {
   count_launches(1);
   Fdct8Params P = Pin;
   if (P.zigzag) {
-    struct Lens { uint8_t v[2][256]; };
-    static const Lens lens = [] {  // thread-safe one-time initialisation
-      Lens l;
-      uint32_t cb[256];
-      for (int t = 0; t < 2; t++) {
-        jpeg_std_codebook(t == 0 ? 1 : 3, cb);
-        for (int i = 0; i < 256; i++) l.v[t][i] = (uint8_t)(cb[i] & 0xff);
-      }
-      return l;
-    }();
-    memcpy(P.aclen, lens.v, sizeof lens.v);
+    int rc = fdct_device_books(&P.acbooks);
+    if (rc) return cudaErrorUnknown;
   }
   for (int t = 0; t < 2; t++)
     for (int i = 0; i < 64; i++) {

@@ -30,14 +30,23 @@ constexpr int kEncThreads = 256;                        // blocks of the scan pe
 // segments (noise at high quality; the worst case is 52 words per block) are produced in several
 // windows of this size; a block is encoded only for the windows its bits fall into.
 constexpr unsigned kSegWords = 2048;
-constexpr int kWordsPerThread = kSegWords / kEncThreads;  // 8
 constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
 
+// floor(n / d) for the small runtime divisors of the scan geometry: one multiply instead of the
+// ~20-instruction integer division.  Exact while n * d < 2^32 (here n < 2^23, d <= 1024).
+struct FastDiv {
+  unsigned d, m;  // m = ceil(2^32 / d); d == 1 is flagged with m = 0
+  __device__ __forceinline__ unsigned div(unsigned n) const { return m ? __umulhi(n, m) : n; }
+};
+
 struct HuffFrame {
-  const int16_t* coefs[3];   // zigzag-ordered blocks, [block raster][64]
-  const uint4* meta[3];      // {mask lo, mask hi, AC code bits, DC} per block (fdct8.cu block_meta)
-  int wblocks[3], hblocks[3], mw[3], mh[3], koff[3];
-  int ncomp, mcus_per_row, blocks_per_mcu;
+  const uint32_t* ents[3];   // [block raster][64] code-word entries of the non-zero AC coefficients (fdct8.cu block_code)
+  const uint4* meta[3];      // {mask lo, mask hi, AC code bits, DC} per block
+  int wblocks[3], hblocks[3], koff[3];
+  FastDiv mw[3];             // blocks per MCU row of the component
+  int per[3];                // blocks per MCU of the component (mw * mh)
+  FastDiv bpm, mpr;          // blocks per MCU, MCUs per row
+  int ncomp, has_dummy;
   unsigned nblocks;          // blocks of the scan = MCUs x blocks per MCU (dummy blocks included)
 };
 
@@ -53,30 +62,35 @@ struct Loc {
 // is the most recent REAL block.  The first block of every MCU is real, so the walk back is short.
 __device__ __forceinline__ Loc locate(const HuffFrame& f, unsigned s) {
   Loc L;
-  const unsigned m = s / f.blocks_per_mcu, k = s - m * f.blocks_per_mcu;
+  const unsigned m = f.bpm.div(s), k = s - m * f.bpm.d;
   const int c = (f.ncomp > 2 && k >= (unsigned)f.koff[2]) ? 2 : ((f.ncomp > 1 && k >= (unsigned)f.koff[1]) ? 1 : 0);
-  const unsigned mw = f.mw[c], mh = f.mh[c], per = mw * mh;
+  const FastDiv mwd = f.mw[c];
+  const unsigned mw = mwd.d, per = f.per[c], mh = per / mw;
   const unsigned wb = f.wblocks[c], hb = f.hblocks[c];
   unsigned kk = k - f.koff[c];
-  unsigned mx = m % f.mcus_per_row, my = m / f.mcus_per_row;
-  unsigned bx = mx * mw + kk % mw, by = my * mh + kk / mw;
+  unsigned my = f.mpr.div(m), mx = m - my * f.mpr.d;
+  unsigned ky = mwd.div(kk), kx = kk - ky * mw;
+  unsigned bx = mx * mw + kx, by = my * mh + ky;
   L.c = c;
   L.real = bx < wb && by < hb;
   L.blk = by * wb + bx;
   L.pred = -1;
   unsigned pm = m;
-  for (unsigned it = 0; it < 2 * per; it++) {
+  const unsigned tries = f.has_dummy ? 2 * per : 1;
+  for (unsigned it = 0; it < tries; it++) {
     if (kk > 0) {
       kk--;
     } else {
       if (pm == 0) break;
       pm--;
-      mx = pm % f.mcus_per_row;
-      my = pm / f.mcus_per_row;
+      my = f.mpr.div(pm);
+      mx = pm - my * f.mpr.d;
       kk = per - 1;
     }
-    bx = mx * mw + kk % mw;
-    by = my * mh + kk / mw;
+    ky = mwd.div(kk);
+    kx = kk - ky * mw;
+    bx = mx * mw + kx;
+    by = my * mh + ky;
     if (bx < wb && by < hb) {
       L.pred = (long long)by * wb + bx;
       break;
@@ -179,16 +193,9 @@ struct Emitter {
   }
 };
 
-__device__ __forceinline__ int coef_at(const uint4& c8, const int16_t* __restrict__ src, int k) {
-  if (k < 8) {  // the first eight zigzag coefficients came with the 16-byte load of phase 1
-    const unsigned w = (k & 4) ? ((k & 2) ? c8.w : c8.z) : ((k & 2) ? c8.y : c8.x);
-    return (int)(short)((w >> ((k & 1) * 16)) & 0xffffu);
-  }
-  return (int)__ldg(src + k);
-}
-
-__device__ __forceinline__ void emit_block(Emitter& E, unsigned long long mask, int dc_diff, const uint4& c8,
-                                           const int16_t* __restrict__ src, const uint32_t* dcb, const uint32_t* acb) {
+// DC code, the block's AC code words in order (each preceded by its ZRLs), EOB
+__device__ __forceinline__ void emit_block(Emitter& E, int n, bool eob, int dc_diff, uint4 cur, const uint4* __restrict__ src,
+                                           const uint32_t* dcb, const uint32_t* acb) {
   {
     const int mag = abs(dc_diff);
     const int nb = mag ? 32 - __clz(mag) : 0;
@@ -196,25 +203,15 @@ __device__ __forceinline__ void emit_block(Emitter& E, unsigned long long mask, 
     const unsigned low = (unsigned)(dc_diff < 0 ? dc_diff - 1 : dc_diff) & ((1u << nb) - 1u);
     E.put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
   }
-  int last = 0;
   const uint32_t zrl = acb[0xF0];
-  while (mask) {
-    const int k = __ffsll((long long)mask) - 1;
-    mask &= mask - 1;
-    int run = k - last - 1;
-    last = k;
-    while (run > 15) {
-      E.put(zrl >> 8, (int)(zrl & 0xff));
-      run -= 16;
-    }
-    const int v = coef_at(c8, src, k);
-    const int mag = abs(v);
-    const int nb = 32 - __clz(mag);
-    const uint32_t e = acb[(run << 4) | nb];
-    const unsigned low = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
-    E.put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
+  for (int i = 0; i < n; i++) {
+    if ((i & 3) == 0 && i) cur = __ldg(src + (i >> 2));  // the first vector came with the loads of phase 1
+    const unsigned e = (i & 2) ? ((i & 1) ? cur.w : cur.z) : ((i & 1) ? cur.y : cur.x);
+    for (unsigned z = e >> 30; z; z--) E.put(zrl >> 8, (int)(zrl & 0xff));
+    const int len = (int)((e >> 25) & 31u);
+    E.put((e & 0x1ffffffu) | (len == 26 ? 1u << 25 : 0u), len);
   }
-  if (last != 63) {
+  if (eob) {
     const uint32_t e = acb[0];
     E.put(e >> 8, (int)(e & 0xff));
   }
@@ -232,7 +229,7 @@ __device__ __forceinline__ unsigned ff_count(unsigned v, int nvalid) {
 // status   : bit-count look-back words, one per CTA        ffstatus : the same for the stuffed-zero counts
 // tails[i] : (1 << 32 | trailing partial word of CTA i) once known
 // ctl[0] <- total bits, ctl[3] <- stuffed bytes, ctl[4] <- overflow flag, ctl[5] = CTA tickets (all zeroed by the caller)
-__global__ void __launch_bounds__(kEncThreads) k_huff_encode(const __grid_constant__ HuffFrame f, const uint32_t* __restrict__ books,
+__global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_constant__ HuffFrame f, const uint32_t* __restrict__ books,
                                                              unsigned long long* status, unsigned long long* ffstatus,
                                                              unsigned long long* tails, uint8_t* __restrict__ out,
                                                              unsigned out_cap, unsigned* ctl) {
@@ -252,20 +249,22 @@ __global__ void __launch_bounds__(kEncThreads) k_huff_encode(const __grid_consta
   const bool live = s < f.nblocks;
 
   // 1. the block, its code length
-  unsigned long long mask = 0;
+  int nent = 0;        // code-word entries (non-zero AC coefficients)
+  bool eob = true;
   unsigned nbits = 0;
   int dc_diff = 0, c = 0;
-  uint4 c8 = make_uint4(0, 0, 0, 0);
-  const int16_t* src = nullptr;
+  uint4 e4 = make_uint4(0, 0, 0, 0);
+  const uint4* src = nullptr;
   if (live) {
     const Loc L = locate(f, s);
     c = L.c;
     const int pred = L.pred >= 0 ? (int)__ldg(&f.meta[c][L.pred].w) : 0;
     if (L.real) {
       const uint4 m = __ldg(f.meta[c] + L.blk);
-      mask = (((unsigned long long)m.y << 32) | m.x) & ~1ull;
-      src = f.coefs[c] + (size_t)L.blk * 64;
-      c8 = __ldg(reinterpret_cast<const uint4*>(src));
+      nent = __popc(m.x & ~1u) + __popc(m.y);
+      eob = !(m.y >> 31);
+      src = reinterpret_cast<const uint4*>(f.ents[c] + (size_t)L.blk * 64);
+      if (nent) e4 = __ldg(src);
       dc_diff = (int)m.w - pred;
       nbits = m.z;
     } else {
@@ -308,7 +307,7 @@ __global__ void __launch_bounds__(kEncThreads) k_huff_encode(const __grid_consta
         E.seg = seg; E.win = win; E.wn = wn;
         E.first_w = pos_lo >> 5; E.last_w = (pos_hi - 1) >> 5;
         E.acc = 0; E.fill = (int)(pos_lo & 31); E.widx = pos_lo >> 5;
-        emit_block(E, mask, dc_diff, c8, src, dcb, acb);
+        emit_block(E, nent, eob, dc_diff, e4, src, dcb, acb);
       }
       __syncthreads();
       // 4. boundary words
@@ -336,20 +335,13 @@ __global__ void __launch_bounds__(kEncThreads) k_huff_encode(const __grid_consta
         }
       }
       __syncthreads();
-      // 5. byte stuffing: thread j takes words win + 8j .. win + 8j + 7 of the image
-      unsigned w[kWordsPerThread];
-      int nv[kWordsPerThread];
+      // 5. byte stuffing: thread j takes wpt consecutive words of the image (one in the common case)
+      const unsigned wpt = (wn + kEncThreads - 1) / kEncThreads;
+      const unsigned r0 = j * wpt;
       unsigned cnt = 0;
-#pragma unroll
-      for (int u = 0; u < kWordsPerThread; u++) {
-        const unsigned r = j * kWordsPerThread + u, i = win + r;
-        nv[u] = 0;
-        w[u] = 0;
-        if (r < wn && i < own_end) {
-          w[u] = seg[r];
-          nv[u] = (is_last && i == lastw) ? (int)((tailbits + 7) >> 3) : 4;
-          cnt += ff_count(w[u], nv[u]);
-        }
+      for (unsigned u = 0; u < wpt; u++) {
+        const unsigned r = r0 + u, i = win + r;
+        if (r < wn && i < own_end) cnt += ff_count(seg[r], (is_last && i == lastw) ? (int)((tailbits + 7) >> 3) : 4);
       }
       unsigned ffwin;
       const unsigned ffoff = block_exclusive_scan(cnt, &ffwin);
@@ -358,20 +350,23 @@ __global__ void __launch_bounds__(kEncThreads) k_huff_encode(const __grid_consta
         __syncthreads();
       }
       if (do_write) {
-        const unsigned ffb = s_ffbase + s_ffrun + ffoff;
-        unsigned pos = 4u * (first + win + j * kWordsPerThread) + ffb;
+        unsigned pos = 4u * (first + win + r0) + s_ffbase + s_ffrun + ffoff;
         bool ovf = false;
+        for (unsigned u = 0; u < wpt; u++) {
+          const unsigned r = r0 + u, i = win + r;
+          if (r < wn && i < own_end) {
+            const unsigned v = seg[r];
+            const int nv = (is_last && i == lastw) ? (int)((tailbits + 7) >> 3) : 4;
 #pragma unroll
-        for (int u = 0; u < kWordsPerThread; u++) {
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            if (b < nv[u]) {
-              const unsigned byte = (w[u] >> (24 - 8 * b)) & 0xff;
-              if (pos < out_cap) out[pos] = (uint8_t)byte; else ovf = true;
-              pos++;
-              if (byte == 0xff) {
-                if (pos < out_cap) out[pos] = 0; else ovf = true;
+            for (int b = 0; b < 4; b++) {
+              if (b < nv) {
+                const unsigned byte = (v >> (24 - 8 * b)) & 0xff;
+                if (pos < out_cap) out[pos] = (uint8_t)byte; else ovf = true;
                 pos++;
+                if (byte == 0xff) {
+                  if (pos < out_cap) out[pos] = 0; else ovf = true;
+                  pos++;
+                }
               }
             }
           }
@@ -379,8 +374,7 @@ __global__ void __launch_bounds__(kEncThreads) k_huff_encode(const __grid_consta
         if (ovf) ctl[4] = 1;
       }
       __syncthreads();
-      if (j == 0) s_ffrun += ffwin;
-      __syncthreads();
+      if (j == 0) s_ffrun += ffwin;  // read again only after the barriers of the next window / by thread 0 itself
     }
     if (npass == 2 && pass == 0) {  // all windows counted: chain the stuffed-zero counts, then sweep again
       const unsigned agg = s_ffrun;
@@ -396,6 +390,13 @@ __global__ void __launch_bounds__(kEncThreads) k_huff_encode(const __grid_consta
     ctl[3] = ((total_bits + 7) >> 3) + s_ffbase + s_ffrun;
     if (ctl[3] > out_cap) ctl[4] = 1;
   }
+}
+
+static FastDiv fast_div(unsigned d) {
+  FastDiv f;
+  f.d = d;
+  f.m = d <= 1 ? 0u : (unsigned)((0x100000000ull + d - 1) / d);
+  return f;
 }
 
 static int device_books(const uint32_t** out) {
@@ -429,19 +430,21 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   HuffFrame f;
   memset(&f, 0, sizeof f);
   f.ncomp = fr.ncomp;
-  f.mcus_per_row = fr.mcus_per_row;
   int k = 0;
   for (int c = 0; c < fr.ncomp; c++) {
-    f.coefs[c] = job->d_coefs[c];
+    f.ents[c] = reinterpret_cast<const uint32_t*>(job->d_coefs[c]);
     f.meta[c] = job->d_meta[c];
     f.wblocks[c] = fr.comp[c].wblocks;
     f.hblocks[c] = fr.comp[c].hblocks;
-    f.mw[c] = fr.ncomp == 1 ? 1 : fr.comp[c].h_samp;
-    f.mh[c] = fr.ncomp == 1 ? 1 : fr.comp[c].v_samp;
+    const int mw = fr.ncomp == 1 ? 1 : fr.comp[c].h_samp, mh = fr.ncomp == 1 ? 1 : fr.comp[c].v_samp;
+    f.mw[c] = fast_div((unsigned)mw);
+    f.per[c] = mw * mh;
     f.koff[c] = k;
-    k += f.mw[c] * f.mh[c];
+    k += mw * mh;
   }
-  f.blocks_per_mcu = k;
+  f.bpm = fast_div((unsigned)k);
+  f.mpr = fast_div((unsigned)fr.mcus_per_row);
+  f.has_dummy = fr.has_dummy_blocks() ? 1 : 0;
   const size_t nblocks = (size_t)fr.mcus_per_row * fr.mcu_rows * k;  // dummy blocks included
   f.nblocks = (unsigned)nblocks;
   // capacity of the entropy-coded segment: the reference's whole output buffer is w*h*6 bytes

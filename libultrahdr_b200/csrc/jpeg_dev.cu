@@ -18,7 +18,9 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
   memcpy(P.q[0], f.qt[0], sizeof P.q[0]);
   memcpy(P.q[1], f.qt[1], sizeof P.q[1]);
   for (int c = 0; c < f.ncomp; c++) {
-    job->d_coefs[c] = (int16_t*)ws.dalloc(f.blocks(c) * 128);
+    // natural order: 64 coefficients per block; device entropy path: 64 code-word entries of 4 bytes
+    // per block (only the entries of non-zero coefficients are ever written or read)
+    job->d_coefs[c] = (int16_t*)ws.dalloc(f.blocks(c) * (zigzag ? 256 : 128));
     if (!job->d_coefs[c]) return E_MEM;
     job->d_meta[c] = nullptr;
     if (zigzag) {  // side information for the device entropy coder

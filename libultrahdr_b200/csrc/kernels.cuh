@@ -118,7 +118,9 @@ struct Fdct8Plane {                 // one launch covers every plane of an image
   int wblocks, hblocks;
   int fill, rgb;
   int tq[3];
-  int16_t* coefs[3];                // plane: [0]; RGB888: Y, Cb, Cr
+  // plane: [0]; RGB888: Y, Cb, Cr.  Natural-order launches: [block][64] coefficients.  Zigzag launches
+  // (device entropy coder follows): [block][64] 32-bit code-word entries instead, see fdct8.cu block_code
+  int16_t* coefs[3];
   // entropy-coder side information, one uint4 per block (zigzag launches only; may be null):
   //   x, y = 64-bit mask of the non-zero coefficients (bit k = zigzag position k, bit 0 = DC)
   //   z    = code bits of the block's AC part: Huffman codes + magnitude bits + ZRLs + EOB
@@ -132,7 +134,7 @@ struct Fdct8Params {
   uint16_t q[2][64];
   unsigned mag[2][64];              // ceil(2^32 / (8*q)), filled by launch_fdct8
   int tile_end[3];                  // cumulative count of 32-block tiles per plane, filled by launch_fdct8
-  uint8_t aclen[2][256];            // AC code length per (run << 4 | size) symbol, [0] luminance [1] chrominance
+  const uint32_t* acbooks;          // zigzag launches: device pointer, AC code books (code << 8 | length), [0..255] luminance [256..511] chrominance (filled by launch_fdct8)
 };
 
 struct IdctPlaneParams {
