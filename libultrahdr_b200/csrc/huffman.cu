@@ -25,7 +25,12 @@ void jpeg_std_codebook(int which, uint32_t out[256]);
 
 namespace {
 
-constexpr int kEncThreads = 256;                        // blocks of the scan per CTA, one thread each
+constexpr int kEncThreads = 256;
+// A CTA takes 256 * bpt consecutive blocks of the scan, bpt (1..8) chosen per launch so that the whole grid
+// is resident at once: the per-CTA chain of dependent global round trips (look-backs, boundary words) is
+// then paid once per launch instead of once per wave.
+constexpr int kMaxBpt = 8;
+constexpr int kMaxChunk = kEncThreads * kMaxBpt;
 // shared-memory image of the CTA's segment: 2048 words = 256 bits per block on average.  Heavier
 // segments (noise at high quality; the worst case is 52 words per block) are produced in several
 // windows of this size; a block is encoded only for the windows its bits fall into.
@@ -47,6 +52,7 @@ struct HuffFrame {
   int per[3];                // blocks per MCU of the component (mw * mh)
   FastDiv bpm, mpr;          // blocks per MCU, MCUs per row
   int ncomp, has_dummy;
+  int bpt;                   // blocks per thread
   unsigned nblocks;          // blocks of the scan = MCUs x blocks per MCU (dummy blocks included)
 };
 
@@ -126,43 +132,46 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
   return r;
 }
 
-// Decoupled look-back (one warp): sum of the values of all predecessors of `idx`.  status[i] carries a
-// 2-bit flag and a 32-bit value: kFlagAgg = the value of i alone, kFlagPrefix = the inclusive prefix up
-// to i.  Predecessors are running or finished (ticket order), so the spin loops terminate.
-__device__ __forceinline__ unsigned lookback_sum(const unsigned long long* status, unsigned idx, int lane) {
+// Publish the aggregate of CTA `idx`, sum the values of all its predecessors, publish the inclusive
+// prefix; returns the exclusive prefix to every thread.  The whole CTA looks back, 256 predecessors per
+// round trip: the grid starts as one wave, so nobody holds a prefix yet when the first CTAs look back
+// and a one-warp look-back would crawl forward 32 CTAs per memory round trip.
+__device__ __forceinline__ unsigned cta_chain_prefix(unsigned long long* status, unsigned idx, unsigned agg) {
+  __shared__ unsigned s_w[kEncThreads / 32], s_f[kEncThreads / 32];
+  const int j = threadIdx.x, lane = j & 31, wid = j >> 5;
+  if (j == 0) *reinterpret_cast<volatile unsigned long long*>(status + idx) = (idx == 0 ? kFlagPrefix : kFlagAgg) | agg;
+  if (idx == 0) return 0;
   unsigned base = 0;
   long long hi = (long long)idx - 1;  // highest predecessor not yet accounted for
   for (;;) {
-    const long long k = hi - lane;
+    const long long k = hi - j;
     unsigned long long st = kFlagPrefix;  // before element 0: nothing
     if (k >= 0) {
       do { st = *reinterpret_cast<const volatile unsigned long long*>(status + k); } while ((st & kFlagMask) == 0);
     }
-    const bool is_prefix = (st & kFlagMask) == kFlagPrefix;
-    const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-    const int first_prefix = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor carrying an inclusive prefix
+    const unsigned pm = __ballot_sync(0xffffffffu, (st & kFlagMask) == kFlagPrefix);
+    const int first_prefix = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor of this warp carrying an inclusive prefix
     unsigned v = (lane <= first_prefix && k >= 0) ? (unsigned)(st & 0xffffffffu) : 0u;
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    base += v;
-    if (pm) return base;
-    hi -= 32;
-  }
-}
-// publish the aggregate of CTA `idx`, look back, publish the inclusive prefix; warp 0 calls it, the
-// exclusive prefix lands in *out (shared memory) -- the caller synchronises the CTA afterwards
-__device__ __forceinline__ void chain_prefix(unsigned long long* status, unsigned idx, unsigned agg, int j, unsigned* out) {
-  if (j == 0) *reinterpret_cast<volatile unsigned long long*>(status + idx) = (idx == 0 ? kFlagPrefix : kFlagAgg) | agg;
-  if (idx == 0) {
-    if (j == 0) *out = 0;
-    return;
-  }
-  if (j < 32) {
-    const unsigned base = lookback_sum(status, idx, j);
-    if (j == 0) {
-      *out = base;
-      *reinterpret_cast<volatile unsigned long long*>(status + idx) = kFlagPrefix | (unsigned long long)(base + agg);
+    if (lane == 0) {
+      s_w[wid] = v;
+      s_f[wid] = pm;
     }
+    __syncthreads();
+    bool found = false;
+#pragma unroll
+    for (int w = 0; w < kEncThreads / 32; w++) {
+      if (!found) {
+        base += s_w[w];
+        found = s_f[w] != 0;
+      }
+    }
+    __syncthreads();
+    if (found) break;
+    hi -= kEncThreads;
   }
+  if (j == 0) *reinterpret_cast<volatile unsigned long long*>(status + idx) = kFlagPrefix | (unsigned long long)(base + agg);
+  return base;
 }
 
 // One block's codes, jchuff.c encode_one_block, into the window [win, win + wn) of the segment image
@@ -235,7 +244,11 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
                                                              unsigned out_cap, unsigned* ctl) {
   __shared__ uint32_t s_books[1024];  // (code << 8 | length): DC lum, AC lum, DC chr, AC chr
   __shared__ uint32_t seg[kSegWords];
-  __shared__ unsigned s_cta, s_base, s_ffbase, s_predtail, s_ffrun;
+  // per block of the chunk: [21:0] raster index, [23:22] component, [24] real, [25] EOB needed, [31:26] entries
+  __shared__ uint32_t s_loc[kMaxChunk];
+  __shared__ uint16_t s_nb[kMaxChunk];   // code bits
+  __shared__ int16_t s_dc[kMaxChunk];    // DC difference
+  __shared__ unsigned s_cta, s_predtail, s_ffrun;
   const int j = threadIdx.x;
   if (j == 0) {
     s_cta = atomicAdd(ctl + 5, 1u);  // ticket order: every predecessor is already running or done
@@ -245,56 +258,58 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
   for (int i = j; i < 1024; i += kEncThreads) s_books[i] = __ldg(books + i);
   __syncthreads();
   const unsigned cta = s_cta;
-  const unsigned s = cta * kEncThreads + j;
-  const bool live = s < f.nblocks;
+  const int bpt = f.bpt;
+  const unsigned chunk = (unsigned)kEncThreads * bpt;
+  const unsigned s0 = cta * chunk + j * bpt;   // this thread's first block of the scan
 
-  // 1. the block, its code length
-  int nent = 0;        // code-word entries (non-zero AC coefficients)
-  bool eob = true;
-  unsigned nbits = 0;
-  int dc_diff = 0, c = 0;
-  uint4 e4 = make_uint4(0, 0, 0, 0);
-  const uint4* src = nullptr;
-  if (live) {
-    const Loc L = locate(f, s);
-    c = L.c;
-    const int pred = L.pred >= 0 ? (int)__ldg(&f.meta[c][L.pred].w) : 0;
-    if (L.real) {
-      const uint4 m = __ldg(f.meta[c] + L.blk);
-      nent = __popc(m.x & ~1u) + __popc(m.y);
-      eob = !(m.y >> 31);
-      src = reinterpret_cast<const uint4*>(f.ents[c] + (size_t)L.blk * 64);
-      if (nent) e4 = __ldg(src);
-      dc_diff = (int)m.w - pred;
-      nbits = m.z;
-    } else {
-      nbits = s_books[(c ? 768 : 256)] & 0xff;  // dummy block: DC difference 0, then EOB
+  // 1. the blocks, their code lengths
+  unsigned tbits = 0;
+  for (int b = 0; b < bpt; b++) {
+    const unsigned s = s0 + b, i = j * bpt + b;
+    unsigned nbits = 0, loc = 0;
+    int dc_diff = 0;
+    if (s < f.nblocks) {
+      const Loc L = locate(f, s);
+      const int c = L.c;
+      const int pred = L.pred >= 0 ? (int)__ldg(&f.meta[c][L.pred].w) : 0;
+      loc = (unsigned)c << 22;
+      if (L.real) {
+        const uint4 m = __ldg(f.meta[c] + L.blk);
+        const unsigned nent = __popc(m.x & ~1u) + __popc(m.y);
+        loc |= L.blk | (1u << 24) | ((m.y >> 31) ? 0u : 1u << 25) | (nent << 26);
+        dc_diff = (int)m.w - pred;
+        nbits = m.z;
+      } else {
+        loc |= 1u << 25;                         // dummy block: DC difference 0, then EOB
+        nbits = s_books[(c ? 768 : 256)] & 0xff;
+      }
+      const int mag = abs(dc_diff);
+      const int nb = mag ? 32 - __clz(mag) : 0;
+      nbits += (s_books[(c ? 512 : 0) + nb] & 0xff) + nb;
     }
-    const int mag = abs(dc_diff);
-    const int nb = mag ? 32 - __clz(mag) : 0;
-    nbits += (s_books[(c ? 512 : 0) + nb] & 0xff) + nb;
+    s_loc[i] = loc;
+    s_nb[i] = (uint16_t)nbits;
+    s_dc[i] = (int16_t)dc_diff;
+    tbits += nbits;
   }
-  const uint32_t* dcb = s_books + (c ? 512 : 0);
-  const uint32_t* acb = s_books + (c ? 768 : 256);
 
   // 2. bit offsets
   unsigned total;
-  const unsigned off = block_exclusive_scan(nbits, &total);
-  chain_prefix(status, cta, total, j, &s_base);
-  __syncthreads();
-  const unsigned base = s_base;
+  const unsigned off = block_exclusive_scan(tbits, &total);
+  const unsigned base = cta_chain_prefix(status, cta, total);
   const unsigned sh = base & 31, first = base >> 5;
   const unsigned endbit = sh + total;            // relative to word `first`
   const unsigned nwords = (endbit + 31) >> 5;    // words of the segment image in use
   const unsigned tailbits = endbit & 31;
   const unsigned lastw = endbit >> 5;            // index of the word holding the trailing partial bits (if any)
-  const bool is_last = (cta + 1) * (unsigned)kEncThreads >= f.nblocks;
+  const bool is_last = (cta + 1) * chunk >= f.nblocks;
   // words this CTA writes out: those whose last bit lies in its segment -- 0 .. lastw-1 -- and, for the
   // last CTA, the padded partial word.  Word 0 may start with bits of the predecessor (sh > 0).
   const unsigned own_end = lastw + ((is_last && tailbits) ? 1u : 0u);
-  const unsigned pos_lo = sh + off, pos_hi = pos_lo + nbits;  // this thread's bits, relative to word `first`
+  const unsigned tpos_lo = sh + off, tpos_hi = tpos_lo + tbits;  // this thread's bits, relative to word `first`
   const int npass = nwords > kSegWords ? 2 : 1;   // several windows: count the 0xFF bytes first, write in a second sweep
 
+  unsigned ffbase = 0;  // stuffed zeros in front of this CTA's words
   for (int pass = 0; pass < npass; pass++) {
     const bool do_write = pass == npass - 1;
     for (unsigned win = 0; win < nwords; win += kSegWords) {
@@ -302,12 +317,25 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
       for (unsigned i = j; i < wn; i += kEncThreads) seg[i] = 0;
       __syncthreads();
       // 3. codes of the blocks that reach into this window
-      if (live && pos_hi > win * 32 && pos_lo < (win + wn) * 32) {
-        Emitter E;
-        E.seg = seg; E.win = win; E.wn = wn;
-        E.first_w = pos_lo >> 5; E.last_w = (pos_hi - 1) >> 5;
-        E.acc = 0; E.fill = (int)(pos_lo & 31); E.widx = pos_lo >> 5;
-        emit_block(E, nent, eob, dc_diff, e4, src, dcb, acb);
+      if (tbits && tpos_hi > win * 32 && tpos_lo < (win + wn) * 32) {
+        unsigned pos = tpos_lo;
+        for (int b = 0; b < bpt; b++) {
+          const unsigned i = j * bpt + b;
+          const unsigned nb = s_nb[i];
+          const unsigned pos_lo = pos, pos_hi = pos + nb;
+          pos = pos_hi;
+          if (!nb || pos_hi <= win * 32 || pos_lo >= (win + wn) * 32) continue;
+          const unsigned loc = s_loc[i];
+          const int c = (loc >> 22) & 3, nent = (int)(loc >> 26);
+          const uint4* src = reinterpret_cast<const uint4*>(f.ents[c] + (size_t)(loc & 0x3fffffu) * 64);
+          uint4 e4 = make_uint4(0, 0, 0, 0);
+          if (nent) e4 = __ldg(src);
+          Emitter E;
+          E.seg = seg; E.win = win; E.wn = wn;
+          E.first_w = pos_lo >> 5; E.last_w = (pos_hi - 1) >> 5;
+          E.acc = 0; E.fill = (int)(pos_lo & 31); E.widx = pos_lo >> 5;
+          emit_block(E, nent, (loc >> 25) & 1, (int)s_dc[i], e4, src, s_books + (c ? 512 : 0), s_books + (c ? 768 : 256));
+        }
       }
       __syncthreads();
       // 4. boundary words
@@ -345,12 +373,9 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
       }
       unsigned ffwin;
       const unsigned ffoff = block_exclusive_scan(cnt, &ffwin);
-      if (npass == 1) {
-        chain_prefix(ffstatus, cta, ffwin, j, &s_ffbase);
-        __syncthreads();
-      }
+      if (npass == 1) ffbase = cta_chain_prefix(ffstatus, cta, ffwin);
       if (do_write) {
-        unsigned pos = 4u * (first + win + r0) + s_ffbase + s_ffrun + ffoff;
+        unsigned pos = 4u * (first + win + r0) + ffbase + s_ffrun + ffoff;
         bool ovf = false;
         for (unsigned u = 0; u < wpt; u++) {
           const unsigned r = r0 + u, i = win + r;
@@ -379,7 +404,7 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
     if (npass == 2 && pass == 0) {  // all windows counted: chain the stuffed-zero counts, then sweep again
       const unsigned agg = s_ffrun;
       __syncthreads();
-      chain_prefix(ffstatus, cta, agg, j, &s_ffbase);
+      ffbase = cta_chain_prefix(ffstatus, cta, agg);
       if (j == 0) s_ffrun = 0;
       __syncthreads();
     }
@@ -387,7 +412,7 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
   if (is_last && j == 0) {
     const unsigned total_bits = base + total;
     ctl[0] = total_bits;
-    ctl[3] = ((total_bits + 7) >> 3) + s_ffbase + s_ffrun;
+    ctl[3] = ((total_bits + 7) >> 3) + ffbase + s_ffrun;
     if (ctl[3] > out_cap) ctl[4] = 1;
   }
 }
@@ -450,7 +475,20 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   // capacity of the entropy-coded segment: the reference's whole output buffer is w*h*6 bytes
   // (ultrahdr_api.cpp:1294); a single scan can never need more than that in a valid encode
   const size_t cap = ((size_t)fr.width * fr.height * 6 + 4096 + 3) / 4 * 4;
-  const unsigned ncta = (unsigned)((nblocks + kEncThreads - 1) / kEncThreads);
+  // blocks per thread: the smallest value for which the whole grid is resident at once
+  static int resident = 0;  // CTAs of one wave on this device type
+  if (!resident) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_huff_encode, kEncThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    resident = per_sm * (sms > 0 ? sms : 148);
+  }
+  int bpt = (int)((nblocks + (size_t)kEncThreads * resident - 1) / ((size_t)kEncThreads * resident));
+  bpt = bpt < 1 ? 1 : (bpt > kMaxBpt ? kMaxBpt : bpt);
+  f.bpt = bpt;
+  const size_t chunk = (size_t)kEncThreads * bpt;
+  const unsigned ncta = (unsigned)((nblocks + chunk - 1) / chunk);
   // [ctl 64 B][status ncta x 8][ffstatus ncta x 8][tails ncta x 8], zeroed together
   const size_t ctl_bytes = 64 + (size_t)ncta * 24;
   unsigned* ctl = (unsigned*)ws.dalloc(ctl_bytes);  // [0] total bits [3] out bytes [4] overflow [5] CTA tickets
