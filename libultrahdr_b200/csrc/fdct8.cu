@@ -63,18 +63,32 @@ constexpr int kTileStride = 72;  // ints per block tile: 64 + 8 padding (4 block
 
 // Entropy-coder front end (jchuff.c encode_one_block), run while the quantised block is still in the
 // warp's shared-memory tile (zigzag order).  Per block it leaves
-//   * the 64-bit mask of its non-zero coefficients, the number of code bits of its AC part (run/size
-//     Huffman codes, magnitude bits, a ZRL per 16 zeros, EOB unless coefficient 63 is non-zero) and
-//     the DC value: one uint4 of "meta";
-//   * one 32-bit entry per non-zero AC coefficient, in zigzag order, holding the coefficient's
-//     complete code word: [24:0] Huffman code followed by the magnitude bits (bit 25 of a 26-bit word
-//     is always 1: only the 16-bit codes, which all start with a one, can reach 26 bits), [29:25] the
-//     length, [31:30] the number of ZRL codes in front of it.
-// huffman.cu then only concatenates: coefficients are never stored for the device path.
-// Lane j of the block's 8 lanes takes zigzag positions j, j+8, ... so that the few non-zeros of a
-// typical block, which sit at the lowest positions, spread over the lanes.
+//   * "meta", one uint4: x = number of code bits of its AC part (run/size Huffman codes, magnitude
+//     bits, a ZRL per 16 zeros, EOB unless coefficient 63 is non-zero) << 16 | the DC value; y, z, w =
+//     the first 96 bits of the AC part's finished bit string (EOB included), MSB first;
+//   * bit strings longer than 96 bits: all their words in the block's slot.
+// huffman.cu then only prepends the DC code (which needs the neighbouring block) and concatenates bit
+// strings; coefficients are never stored for the device path.
+// Step 1, lane j of the block's 8 lanes takes zigzag positions j, j+8, ... (the few non-zeros of a
+// typical block sit at the lowest positions: they spread over the lanes): code word of each non-zero
+// coefficient -> ent[rank].  Step 2, lane j takes entries j, j+8, ...: prefix sum of the lengths over
+// the 8 lanes -> bit offset -> OR into the block's bit-string image.
+__device__ __forceinline__ void bs_place(uint32_t* bs, unsigned off, unsigned long long pat, unsigned plen) {
+  const unsigned long long v = pat << (64 - plen);  // left aligned
+  const unsigned A = (unsigned)(v >> 32), B = (unsigned)v;
+  const unsigned w = off >> 5, sh = off & 31;
+  const unsigned x0 = A >> sh;
+  const unsigned x1 = sh ? (A << (32 - sh)) | (B >> sh) : B;
+  const unsigned x2 = sh ? B << (32 - sh) : 0u;
+  if (x0) atomicOr(bs + w, x0);
+  if (x1) atomicOr(bs + w + 1, x1);
+  if (x2) atomicOr(bs + w + 2, x2);
+}
+
+constexpr int kBsWords = 56;  // bit-string image per block: 63 x 26 bits = 52 words at most, padded to whole uint4
+
 __device__ __forceinline__ void block_code(const int16_t* t16, const uint4 q, int lane_r, const uint32_t* acb, uint32_t* ent,
-                                           uint32_t* gout_entries, uint4* meta_out) {
+                                           uint32_t* bs, uint32_t* gout_words, uint4* meta_out) {
   auto nz2 = [](unsigned w) { return ((w & 0xffffu) ? 1u : 0u) | ((w >> 16) ? 2u : 0u); };
   const unsigned m8 = nz2(q.x) | (nz2(q.y) << 2) | (nz2(q.z) << 4) | (nz2(q.w) << 6);  // positions 8r .. 8r+7
   unsigned lo = lane_r < 4 ? m8 << (8 * lane_r) : 0u, hi = lane_r >= 4 ? m8 << (8 * (lane_r - 4)) : 0u;
@@ -87,7 +101,10 @@ __device__ __forceinline__ void block_code(const int16_t* t16, const uint4 q, in
   const unsigned long long anchored = mask | 1ull;  // runs are counted from the DC position
   const unsigned long long mask_ac = mask & ~1ull;
   unsigned bits = 0;
-  const unsigned zrl = acb[0xF0] & 0xff;
+  const unsigned zrl = acb[0xF0] & 0xff, zcode = acb[0xF0] >> 8;
+  // step 1: code words.  entry = [24:0] Huffman code followed by the magnitude bits (bit 25 of a 26-bit
+  // word is always 1: only the 16-bit codes, which all start with a one, can reach 26 bits), [29:25] its
+  // length, [31:30] the number of ZRL codes in front of it
 #pragma unroll
   for (int half = 0; half < 2; half++) {
     unsigned mj = ((half ? hi : lo) >> lane_r) & 0x01010101u;
@@ -109,19 +126,73 @@ __device__ __forceinline__ void block_code(const int16_t* t16, const uint4 q, in
   }
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
-  if (!(hi >> 31)) bits += acb[0] & 0xff;  // EOB
+  const bool eob = !(hi >> 31);
+  if (eob) bits += acb[0] & 0xff;
+  // step 2: bit string.  Items = the entries plus, if needed, EOB.  Strings of up to 96 bits (nearly all
+  // blocks of natural images) are assembled in three registers per lane and ORed over the 8 lanes; they
+  // travel inside the meta word.  Longer strings are built in the shared-memory image and go to the slot.
+  const int n = __popcll(mask_ac);
+  const int items = n + (eob ? 1 : 0);
+  int imax = items;  // rounds are warp-uniform (shuffles): the longest of the warp's 4 blocks decides
+  imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, 8));
+  imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, 16));
+  const unsigned nw = (bits + 31) >> 5;
+  const bool longb = bits > 96;
+  if (longb)
+    for (unsigned w = lane_r; w < nw; w += 8) bs[w] = 0;
   __syncwarp();
-  if (gout_entries) {  // 16 bytes per lane and round; the tail of the last vector is don't-care
-    const int n = __popcll(mask_ac);
-    for (int base = 4 * lane_r; base < n; base += 32) *(uint4*)(gout_entries + base) = *(const uint4*)(ent + base);
+  const unsigned eob_ent = ((acb[0] >> 8) & 0x1ffffffu) | ((acb[0] & 0xff) << 25);
+  unsigned base = 0, c0 = 0, c1 = 0, c2 = 0;
+  for (int t = 0; t * 8 < imax; t++) {
+    const int idx = t * 8 + lane_r;
+    const unsigned e = idx < n ? ent[idx] : (idx == n && eob ? eob_ent : 0u);
+    const unsigned zr = e >> 30, len = (e >> 25) & 31u;
+    const unsigned tl = len + zr * zrl;
+    unsigned incl = tl;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, incl, o, 8);
+      if (lane_r >= o) incl += y;
+    }
+    const unsigned off = base + incl - tl;
+    base += __shfl_sync(0xffffffffu, incl, 7, 8);
+    if (tl) {
+      unsigned long long pat = (e & 0x1ffffffu) | (len == 26 ? 1u << 25 : 0u);
+      for (unsigned z = 0; z < zr; z++) pat |= (unsigned long long)zcode << (len + z * zrl);
+      if (longb) {
+        bs_place(bs, off, pat, tl);
+      } else {
+        const unsigned long long v = pat << (64 - tl);  // left aligned
+        const unsigned A = (unsigned)(v >> 32), B = (unsigned)v;
+        const unsigned w = off >> 5, sh = off & 31;
+        const unsigned x0 = A >> sh;
+        const unsigned x1 = sh ? (A << (32 - sh)) | (B >> sh) : B;
+        const unsigned x2 = sh ? B << (32 - sh) : 0u;
+        if (w == 0) { c0 |= x0; c1 |= x1; c2 |= x2; }
+        else if (w == 1) { c1 |= x0; c2 |= x1; }
+        else c2 |= x0;
+      }
+    }
   }
-  if (lane_r == 0 && meta_out) *meta_out = make_uint4(lo, hi, bits, (unsigned)(int)t16[0]);
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    c0 |= __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 |= __shfl_xor_sync(0xffffffffu, c1, o);
+    c2 |= __shfl_xor_sync(0xffffffffu, c2, o);
+  }
+  __syncwarp();
+  if (longb) {
+    c0 = bs[0]; c1 = bs[1]; c2 = bs[2];
+    if (gout_words)  // 16 bytes per lane and round; the tail of the last vector is don't-care
+      for (unsigned w4 = 4 * lane_r; w4 < nw; w4 += 32) *(uint4*)(gout_words + w4) = *(const uint4*)(bs + w4);
+  }
+  if (lane_r == 0 && meta_out) *meta_out = make_uint4((bits << 16) | ((unsigned)(int)t16[0] & 0xffffu), c0, c1, c2);
 }
 
 template <bool ZIGZAG>
 __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int lane_r, const unsigned* sdiv,
                                             const unsigned* smag, const uint8_t* sunzig, int16_t* gout_block_base,
-                                            const uint32_t* acb, uint32_t* ent, uint4* meta_out) {
+                                            const uint32_t* acb, uint32_t* ent, uint32_t* bs, uint4* meta_out) {
   // pass 1 on this lane's row, park it
   dct1d<0>(d);
   int* t = tile + lane_b * kTileStride;
@@ -150,9 +221,10 @@ __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int
   // 16 bytes per lane: coefficients [8*lane_r, 8*lane_r + 8) of block lane_b
   const uint4 q = *(const uint4*)(t16 + lane_r * 8);
   if (ZIGZAG) {
-    // device entropy coder follows: code words instead of coefficients (all 32 lanes take part in the
-    // shuffles; dead lanes store nothing).  The block's slot holds 64 entries of 4 bytes.
-    block_code(t16, q, lane_r, acb, ent + lane_b * 64, gout_block_base ? reinterpret_cast<uint32_t*>(gout_block_base) : nullptr, meta_out);
+    // device entropy coder follows: the AC bit string instead of coefficients (all 32 lanes take part in
+    // the shuffles; dead lanes store nothing).  The block's slot holds 64 words.
+    block_code(t16, q, lane_r, acb, ent + lane_b * 64, bs + lane_b * kBsWords,
+               gout_block_base ? reinterpret_cast<uint32_t*>(gout_block_base) : nullptr, meta_out);
   } else if (gout_block_base) {
     *(uint4*)(gout_block_base + lane_r * 8) = q;
   }
@@ -160,12 +232,13 @@ __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int
 }
 
 template <bool ZIGZAG>
-__global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
+__global__ void __launch_bounds__(256, 4) k_fdct8(const Fdct8Params P) {
   __shared__ unsigned sdiv[2][64], smag[2][64];
   __shared__ int tiles[8][4 * kTileStride];
   __shared__ uint8_t sunzig[64];
   __shared__ uint32_t sacb[ZIGZAG ? 2 : 1][ZIGZAG ? 256 : 1];       // AC code books (code << 8 | length)
   __shared__ uint32_t sent[ZIGZAG ? 8 : 1][ZIGZAG ? 4 * 64 : 1];      // per warp: code-word entries of its 4 blocks
+  __shared__ __align__(16) uint32_t sbs[ZIGZAG ? 8 : 1][ZIGZAG ? 4 * kBsWords : 4];  // per warp: their bit-string images
   if (ZIGZAG) {
     sacb[0][threadIdx.x] = __ldg(P.acbooks + threadIdx.x);
     sacb[1][threadIdx.x] = __ldg(P.acbooks + 256 + threadIdx.x);
@@ -209,7 +282,7 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
     const size_t bidx = (size_t)by * pl.wblocks + bx;
     int16_t* out = live ? pl.coefs[0] + bidx * (ZIGZAG ? 128 : 64) : nullptr;
     block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, out, sacb[ZIGZAG ? pl.hsel[0] : 0],
-                        sent[ZIGZAG ? warp : 0], live && pl.meta[0] ? pl.meta[0] + bidx : nullptr);
+                        sent[ZIGZAG ? warp : 0], sbs[ZIGZAG ? warp : 0], live && pl.meta[0] ? pl.meta[0] + bidx : nullptr);
   } else {
     // RGB888: libjpeg's scanline path replicates the last column / row (jcsample.c, jcprepct.c)
     const int y = min(by * 8 + lane_r, pl.h - 1);
@@ -246,7 +319,7 @@ __global__ void __launch_bounds__(256) k_fdct8(const Fdct8Params P) {
       const size_t bidx = (size_t)by * pl.wblocks + bx;
       int16_t* out = live ? pl.coefs[comp] + bidx * (ZIGZAG ? 128 : 64) : nullptr;
       block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[comp]], smag[pl.tq[comp]], sunzig, out, sacb[ZIGZAG ? pl.hsel[comp] : 0],
-                          sent[ZIGZAG ? warp : 0], live && pl.meta[comp] ? pl.meta[comp] + bidx : nullptr);
+                          sent[ZIGZAG ? warp : 0], sbs[ZIGZAG ? warp : 0], live && pl.meta[comp] ? pl.meta[comp] + bidx : nullptr);
     }
   }
   }

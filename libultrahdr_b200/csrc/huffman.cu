@@ -15,7 +15,10 @@
 //   5. byte stuffing folded in: the 0xFF bytes of the words a CTA owns are counted, a second
 //      look-back gives the number of stuffed zeros in front of them, the CTA writes its final bytes
 // Only the final stuffed segment (a few MB at 4K) exists in global memory and crosses PCIe.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "jpeg.h"
 
@@ -45,8 +48,8 @@ struct FastDiv {
 };
 
 struct HuffFrame {
-  const uint32_t* ents[3];   // [block raster][64] code-word entries of the non-zero AC coefficients (fdct8.cu block_code)
-  const uint4* meta[3];      // {mask lo, mask hi, AC code bits, DC} per block
+  const uint32_t* slots[3];  // [block raster][64 words] AC bit string of the block, MSB first (only strings longer than 96 bits)
+  const uint4* meta[3];      // {AC code bits << 16 | DC, first three words of the AC bit string} per block (fdct8.cu block_code)
   int wblocks[3], hblocks[3], koff[3];
   FastDiv mw[3];             // blocks per MCU row of the component
   int per[3];                // blocks per MCU of the component (mw * mh)
@@ -132,14 +135,20 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
   return r;
 }
 
-// Publish the aggregate of CTA `idx`, sum the values of all its predecessors, publish the inclusive
-// prefix; returns the exclusive prefix to every thread.  The whole CTA looks back, 256 predecessors per
-// round trip: the grid starts as one wave, so nobody holds a prefix yet when the first CTAs look back
-// and a one-warp look-back would crawl forward 32 CTAs per memory round trip.
-__device__ __forceinline__ unsigned cta_chain_prefix(unsigned long long* status, unsigned idx, unsigned agg) {
+// Chain of per-CTA values (code bits; stuffed zeros).  status[i] carries a 2-bit flag and a 32-bit value:
+// kFlagAgg = the value of CTA i alone, kFlagPrefix = the inclusive prefix up to i.  A CTA publishes its
+// aggregate as early as it can, does other work, and only then sums its predecessors: by that time they
+// have normally all published and the look-back costs one memory round trip.  The whole CTA looks back,
+// 256 predecessors per round trip (the grid starts as one wave: nobody holds a prefix yet when the first
+// CTAs look back, a one-warp look-back would crawl forward 32 CTAs per round trip).  Predecessors are
+// running or finished (ticket order), so the polling loops terminate.
+__device__ __forceinline__ void chain_publish(unsigned long long* status, unsigned idx, unsigned agg) {
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(status + idx) = (idx == 0 ? kFlagPrefix : kFlagAgg) | agg;
+}
+// returns the exclusive prefix to every thread and publishes the inclusive one
+__device__ __forceinline__ unsigned chain_lookback(unsigned long long* status, unsigned idx, unsigned agg) {
   __shared__ unsigned s_w[kEncThreads / 32], s_f[kEncThreads / 32];
   const int j = threadIdx.x, lane = j & 31, wid = j >> 5;
-  if (j == 0) *reinterpret_cast<volatile unsigned long long*>(status + idx) = (idx == 0 ? kFlagPrefix : kFlagAgg) | agg;
   if (idx == 0) return 0;
   unsigned base = 0;
   long long hi = (long long)idx - 1;  // highest predecessor not yet accounted for
@@ -147,7 +156,11 @@ __device__ __forceinline__ unsigned cta_chain_prefix(unsigned long long* status,
     const long long k = hi - j;
     unsigned long long st = kFlagPrefix;  // before element 0: nothing
     if (k >= 0) {
-      do { st = *reinterpret_cast<const volatile unsigned long long*>(status + k); } while ((st & kFlagMask) == 0);
+      for (;;) {
+        st = *reinterpret_cast<const volatile unsigned long long*>(status + k);
+        if (st & kFlagMask) break;
+        __nanosleep(200);  // do not starve the stores we are waiting for
+      }
     }
     const unsigned pm = __ballot_sync(0xffffffffu, (st & kFlagMask) == kFlagPrefix);
     const int first_prefix = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor of this warp carrying an inclusive prefix
@@ -202,27 +215,35 @@ struct Emitter {
   }
 };
 
-// DC code, the block's AC code words in order (each preceded by its ZRLs), EOB
-__device__ __forceinline__ void emit_block(Emitter& E, int n, bool eob, int dc_diff, uint4 cur, const uint4* __restrict__ src,
-                                           const uint32_t* dcb, const uint32_t* acb) {
-  {
-    const int mag = abs(dc_diff);
-    const int nb = mag ? 32 - __clz(mag) : 0;
-    const uint32_t e = dcb[nb];
-    const unsigned low = (unsigned)(dc_diff < 0 ? dc_diff - 1 : dc_diff) & ((1u << nb) - 1u);
-    E.put(((e >> 8) << nb) | low, (int)(e & 0xff) + nb);
-  }
-  const uint32_t zrl = acb[0xF0];
-  for (int i = 0; i < n; i++) {
-    if ((i & 3) == 0 && i) cur = __ldg(src + (i >> 2));  // the first vector came with the loads of phase 1
-    const unsigned e = (i & 2) ? ((i & 1) ? cur.w : cur.z) : ((i & 1) ? cur.y : cur.x);
-    for (unsigned z = e >> 30; z; z--) E.put(zrl >> 8, (int)(zrl & 0xff));
-    const int len = (int)((e >> 25) & 31u);
-    E.put((e & 0x1ffffffu) | (len == 26 ? 1u << 25 : 0u), len);
-  }
-  if (eob) {
-    const uint32_t e = acb[0];
-    E.put(e >> 8, (int)(e & 0xff));
+// DC code, then the block's finished AC bit string (fdct8.cu block_code; EOB included), 32 bits at a time:
+// the first three words travel in the block's meta word, longer strings continue in the block's slot
+__device__ __forceinline__ void emit_block(Emitter& E, int dc_diff, unsigned nbits, bool real, const uint4* __restrict__ meta,
+                                           const uint4* __restrict__ slot, const uint32_t* dcb, const uint32_t* acb) {
+  const int mag = abs(dc_diff);
+  const int nb = mag ? 32 - __clz(mag) : 0;
+  const uint32_t e = dcb[nb];
+  const unsigned dclen = (e & 0xff) + nb;
+  const unsigned acbits = nbits - dclen;
+  uint4 m = make_uint4(0, 0, 0, 0);
+  if (real) m = __ldg(meta);
+  const unsigned low = (unsigned)(dc_diff < 0 ? dc_diff - 1 : dc_diff) & ((1u << nb) - 1u);
+  E.put(((e >> 8) << nb) | low, (int)dclen);
+  if (real) {
+    uint4 cur = make_uint4(0, m.y, m.z, m.w);
+    for (unsigned w = 0; w * 32 < acbits; w++) {
+      unsigned word;
+      if (w < 3) {
+        word = w == 0 ? cur.y : (w == 1 ? cur.z : cur.w);
+      } else {
+        if (w == 3 || (w & 3) == 0) cur = __ldg(slot + (w >> 2));
+        word = (w & 2) ? ((w & 1) ? cur.w : cur.z) : ((w & 1) ? cur.y : cur.x);
+      }
+      const unsigned n = min(32u, acbits - 32 * w);
+      E.put(word >> (32 - n), (int)n);
+    }
+  } else {  // dummy block: EOB
+    const uint32_t eb = acb[0];
+    E.put(eb >> 8, (int)(eb & 0xff));
   }
   if (E.fill) E.store((unsigned)(E.acc << (32 - E.fill)));
 }
@@ -241,14 +262,16 @@ __device__ __forceinline__ unsigned ff_count(unsigned v, int nvalid) {
 __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_constant__ HuffFrame f, const uint32_t* __restrict__ books,
                                                              unsigned long long* status, unsigned long long* ffstatus,
                                                              unsigned long long* tails, uint8_t* __restrict__ out,
-                                                             unsigned out_cap, unsigned* ctl) {
+                                                             unsigned out_cap, unsigned* ctl, unsigned long long* trace) {
+#define TRACE(k) do { if (trace && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); trace[(size_t)s_cta * 16 + (k)] = t_; } } while (0)
   __shared__ uint32_t s_books[1024];  // (code << 8 | length): DC lum, AC lum, DC chr, AC chr
-  __shared__ uint32_t seg[kSegWords];
-  // per block of the chunk: [21:0] raster index, [23:22] component, [24] real, [25] EOB needed, [31:26] entries
+  __shared__ uint32_t seg[kSegWords];        // window of the CTA-relative image (bit 0 = the CTA's first code bit)
+  __shared__ uint32_t oseg[kSegWords + 1];   // the same window aligned to the words of the stream
+  // per block of the chunk: [21:0] raster index, [23:22] component, [24] real (not a dummy block)
   __shared__ uint32_t s_loc[kMaxChunk];
   __shared__ uint16_t s_nb[kMaxChunk];   // code bits
   __shared__ int16_t s_dc[kMaxChunk];    // DC difference
-  __shared__ unsigned s_cta, s_predtail, s_ffrun;
+  __shared__ unsigned s_cta, s_predtail, s_ffrun, s_carry;
   const int j = threadIdx.x;
   if (j == 0) {
     s_cta = atomicAdd(ctl + 5, 1u);  // ticket order: every predecessor is already running or done
@@ -258,6 +281,7 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
   for (int i = j; i < 1024; i += kEncThreads) s_books[i] = __ldg(books + i);
   __syncthreads();
   const unsigned cta = s_cta;
+  TRACE(0);
   const int bpt = f.bpt;
   const unsigned chunk = (unsigned)kEncThreads * bpt;
   const unsigned s0 = cta * chunk + j * bpt;   // this thread's first block of the scan
@@ -271,17 +295,15 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
     if (s < f.nblocks) {
       const Loc L = locate(f, s);
       const int c = L.c;
-      const int pred = L.pred >= 0 ? (int)__ldg(&f.meta[c][L.pred].w) : 0;
+      const int pred = L.pred >= 0 ? (int)(short)(__ldg(&f.meta[c][L.pred].x) & 0xffffu) : 0;
       loc = (unsigned)c << 22;
       if (L.real) {
-        const uint4 m = __ldg(f.meta[c] + L.blk);
-        const unsigned nent = __popc(m.x & ~1u) + __popc(m.y);
-        loc |= L.blk | (1u << 24) | ((m.y >> 31) ? 0u : 1u << 25) | (nent << 26);
-        dc_diff = (int)m.w - pred;
-        nbits = m.z;
+        const unsigned mx = __ldg(&f.meta[c][L.blk].x);  // AC code bits << 16 | DC
+        loc |= L.blk | (1u << 24);
+        dc_diff = (int)(short)(mx & 0xffffu) - pred;
+        nbits = mx >> 16;
       } else {
-        loc |= 1u << 25;                         // dummy block: DC difference 0, then EOB
-        nbits = s_books[(c ? 768 : 256)] & 0xff;
+        nbits = s_books[(c ? 768 : 256)] & 0xff;  // dummy block: DC difference 0, then EOB
       }
       const int mag = abs(dc_diff);
       const int nb = mag ? 32 - __clz(mag) : 0;
@@ -293,32 +315,31 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
     tbits += nbits;
   }
 
-  // 2. bit offsets
+  // 2. bit offsets inside the CTA; the CTA's own total goes out at once, the look-back waits until
+  //    the codes are in place (relative to the CTA's first bit)
+  TRACE(1);
   unsigned total;
   const unsigned off = block_exclusive_scan(tbits, &total);
-  const unsigned base = cta_chain_prefix(status, cta, total);
-  const unsigned sh = base & 31, first = base >> 5;
-  const unsigned endbit = sh + total;            // relative to word `first`
-  const unsigned nwords = (endbit + 31) >> 5;    // words of the segment image in use
-  const unsigned tailbits = endbit & 31;
-  const unsigned lastw = endbit >> 5;            // index of the word holding the trailing partial bits (if any)
+  chain_publish(status, cta, total);
+  TRACE(2);
+  const unsigned nrel = (total + 31) >> 5;       // words of the CTA-relative image
   const bool is_last = (cta + 1) * chunk >= f.nblocks;
-  // words this CTA writes out: those whose last bit lies in its segment -- 0 .. lastw-1 -- and, for the
-  // last CTA, the padded partial word.  Word 0 may start with bits of the predecessor (sh > 0).
-  const unsigned own_end = lastw + ((is_last && tailbits) ? 1u : 0u);
-  const unsigned tpos_lo = sh + off, tpos_hi = tpos_lo + tbits;  // this thread's bits, relative to word `first`
-  const int npass = nwords > kSegWords ? 2 : 1;   // several windows: count the 0xFF bytes first, write in a second sweep
-
+  const int npass = nrel > kSegWords ? 2 : 1;  // several windows: count the 0xFF bytes first, write in a second sweep
+  // known after the look-back:
+  unsigned base = 0, sh = 0, first = 0, nwords = 0, tailbits = 0, lastw = 0, own_end = 0;
   unsigned ffbase = 0;  // stuffed zeros in front of this CTA's words
+
   for (int pass = 0; pass < npass; pass++) {
     const bool do_write = pass == npass - 1;
-    for (unsigned win = 0; win < nwords; win += kSegWords) {
-      const unsigned wn = min(kSegWords, nwords - win);
+    for (unsigned win = 0; win < nrel; win += kSegWords) {
+      const unsigned wn = min(kSegWords, nrel - win);
+      if (j == 0) s_carry = win ? seg[kSegWords - 1] : 0u;  // last relative word of the previous window
+      __syncthreads();
       for (unsigned i = j; i < wn; i += kEncThreads) seg[i] = 0;
       __syncthreads();
       // 3. codes of the blocks that reach into this window
-      if (tbits && tpos_hi > win * 32 && tpos_lo < (win + wn) * 32) {
-        unsigned pos = tpos_lo;
+      if (tbits && off + tbits > win * 32 && off < (win + wn) * 32) {
+        unsigned pos = off;
         for (int b = 0; b < bpt; b++) {
           const unsigned i = j * bpt + b;
           const unsigned nb = s_nb[i];
@@ -326,61 +347,93 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
           pos = pos_hi;
           if (!nb || pos_hi <= win * 32 || pos_lo >= (win + wn) * 32) continue;
           const unsigned loc = s_loc[i];
-          const int c = (loc >> 22) & 3, nent = (int)(loc >> 26);
-          const uint4* src = reinterpret_cast<const uint4*>(f.ents[c] + (size_t)(loc & 0x3fffffu) * 64);
-          uint4 e4 = make_uint4(0, 0, 0, 0);
-          if (nent) e4 = __ldg(src);
+          const int c = (loc >> 22) & 3;
+          const size_t blk = loc & 0x3fffffu;
           Emitter E;
           E.seg = seg; E.win = win; E.wn = wn;
           E.first_w = pos_lo >> 5; E.last_w = (pos_hi - 1) >> 5;
           E.acc = 0; E.fill = (int)(pos_lo & 31); E.widx = pos_lo >> 5;
-          emit_block(E, nent, (loc >> 25) & 1, (int)s_dc[i], e4, src, s_books + (c ? 512 : 0), s_books + (c ? 768 : 256));
+          emit_block(E, (int)s_dc[i], nb, (loc >> 24) & 1, f.meta[c] + blk, reinterpret_cast<const uint4*>(f.slots[c] + blk * 64),
+                     s_books + (c ? 512 : 0), s_books + (c ? 768 : 256));
         }
+      }
+      __syncthreads();
+      TRACE(3);
+      if (pass == 0 && win == 0) {  // now the predecessors' totals: where the segment starts in the stream
+        base = chain_lookback(status, cta, total);
+        sh = base & 31;
+        first = base >> 5;
+        const unsigned endbit = sh + total;      // relative to word `first`
+        nwords = (endbit + 31) >> 5;             // words of the stream the segment touches
+        tailbits = endbit & 31;
+        lastw = endbit >> 5;                     // index of the word holding the trailing partial bits (if any)
+        // words this CTA writes out: those whose last bit lies in its segment -- 0 .. lastw-1 -- and, for
+        // the last CTA, the padded partial word.  Word 0 may start with bits of the predecessor (sh > 0).
+        own_end = lastw + ((is_last && tailbits) ? 1u : 0u);
+      }
+      TRACE(4);
+      // stream-aligned view of the window: stream word i (relative to `first`) = relative words i-1 and i
+      // shifted by sh.  This window yields words win .. win+wn-1 and, at the very end, word nrel.
+      const bool extra = win + wn == nrel && nwords > nrel;
+      const unsigned on = wn + (extra ? 1u : 0u);
+      for (unsigned r = j; r < on; r += kEncThreads) {
+        const unsigned hi = r ? seg[r - 1] : s_carry, lo = r < wn ? seg[r] : 0u;
+        oseg[r] = sh ? __funnelshift_r(lo, hi, sh) : lo;
       }
       __syncthreads();
       // 4. boundary words
       if (j == 0) {
-        const bool tail_here = tailbits && lastw >= win && lastw < win + wn;
+        const bool tail_here = tailbits && lastw >= win && lastw < win + on;
         // a non-degenerate segment hands its trailing partial word on *before* waiting for the
         // predecessor's: otherwise every CTA would wait for the whole chain in front of it
         if (pass == 0 && tail_here && lastw > 0)
-          *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | seg[lastw - win];
+          *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | oseg[lastw - win];
         if (win == 0 && sh > 0) {  // leading bits of word `first` belong to the predecessor
           if (pass == 0) {
             unsigned long long t;
-            do { t = *reinterpret_cast<volatile unsigned long long*>(tails + cta - 1); } while ((t >> 32) == 0);
+            for (;;) {
+              t = *reinterpret_cast<volatile unsigned long long*>(tails + cta - 1);
+              if (t >> 32) break;
+              __nanosleep(100);
+            }
             s_predtail = (unsigned)t;
           }
-          seg[0] |= s_predtail;
+          oseg[0] |= s_predtail;
         }
         // the whole segment lies inside word `first` (only a short last CTA can be this small): the
         // merged word is also our trailing partial word
         if (pass == 0 && tail_here && lastw == 0)
-          *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | seg[0];
+          *reinterpret_cast<volatile unsigned long long*>(tails + cta) = (1ull << 32) | oseg[0];
         if (is_last && tail_here) {  // jchuff.c flush_bits: fill the last byte with ones
           const unsigned pad = (8 - (tailbits & 7)) & 7;
-          seg[lastw - win] |= ((1u << pad) - 1u) << (32 - tailbits - pad);
+          oseg[lastw - win] |= ((1u << pad) - 1u) << (32 - tailbits - pad);
         }
       }
       __syncthreads();
-      // 5. byte stuffing: thread j takes wpt consecutive words of the image (one in the common case)
-      const unsigned wpt = (wn + kEncThreads - 1) / kEncThreads;
+      TRACE(5);
+      // 5. byte stuffing: thread j takes wpt consecutive stream words of the window (one in the common case)
+      const unsigned wpt = (on + kEncThreads - 1) / kEncThreads;
       const unsigned r0 = j * wpt;
       unsigned cnt = 0;
       for (unsigned u = 0; u < wpt; u++) {
         const unsigned r = r0 + u, i = win + r;
-        if (r < wn && i < own_end) cnt += ff_count(seg[r], (is_last && i == lastw) ? (int)((tailbits + 7) >> 3) : 4);
+        if (r < on && i < own_end) cnt += ff_count(oseg[r], (is_last && i == lastw) ? (int)((tailbits + 7) >> 3) : 4);
       }
       unsigned ffwin;
       const unsigned ffoff = block_exclusive_scan(cnt, &ffwin);
-      if (npass == 1) ffbase = cta_chain_prefix(ffstatus, cta, ffwin);
+      TRACE(6);
+      if (npass == 1) {
+        chain_publish(ffstatus, cta, ffwin);
+        ffbase = chain_lookback(ffstatus, cta, ffwin);
+      }
+      TRACE(7);
       if (do_write) {
         unsigned pos = 4u * (first + win + r0) + ffbase + s_ffrun + ffoff;
         bool ovf = false;
         for (unsigned u = 0; u < wpt; u++) {
           const unsigned r = r0 + u, i = win + r;
-          if (r < wn && i < own_end) {
-            const unsigned v = seg[r];
+          if (r < on && i < own_end) {
+            const unsigned v = oseg[r];
             const int nv = (is_last && i == lastw) ? (int)((tailbits + 7) >> 3) : 4;
 #pragma unroll
             for (int b = 0; b < 4; b++) {
@@ -402,13 +455,16 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_huff_encode(const __grid_con
       if (j == 0) s_ffrun += ffwin;  // read again only after the barriers of the next window / by thread 0 itself
     }
     if (npass == 2 && pass == 0) {  // all windows counted: chain the stuffed-zero counts, then sweep again
+      __syncthreads();
       const unsigned agg = s_ffrun;
       __syncthreads();
-      ffbase = cta_chain_prefix(ffstatus, cta, agg);
+      chain_publish(ffstatus, cta, agg);
+      ffbase = chain_lookback(ffstatus, cta, agg);
       if (j == 0) s_ffrun = 0;
       __syncthreads();
     }
   }
+  TRACE(8);
   if (is_last && j == 0) {
     const unsigned total_bits = base + total;
     ctl[0] = total_bits;
@@ -457,7 +513,7 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   f.ncomp = fr.ncomp;
   int k = 0;
   for (int c = 0; c < fr.ncomp; c++) {
-    f.ents[c] = reinterpret_cast<const uint32_t*>(job->d_coefs[c]);
+    f.slots[c] = reinterpret_cast<const uint32_t*>(job->d_coefs[c]);
     f.meta[c] = job->d_meta[c];
     f.wblocks[c] = fr.comp[c].wblocks;
     f.hblocks[c] = fr.comp[c].hblocks;
@@ -504,7 +560,28 @@ int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   CUDA_TRY(cudaMemsetAsync(ctl, 0, ctl_bytes, st));
   count_launches(1);
   ws.t_begin("huff_encode");
-  k_huff_encode<<<ncta, kEncThreads, 0, st>>>(f, books, status, ffstatus, tails, job->d_scan, (unsigned)cap, ctl);
+  unsigned long long* trace = nullptr;
+  static const bool want_trace = getenv("UHDR_B200_HUFF_TRACE") != nullptr;
+  if (want_trace) {  // diagnostic: %globaltimer at the phase boundaries of every CTA, dumped to stderr
+    trace = (unsigned long long*)ws.dalloc((size_t)ncta * 16 * 8);
+    if (trace) cudaMemsetAsync(trace, 0, (size_t)ncta * 16 * 8, st);
+  }
+  k_huff_encode<<<ncta, kEncThreads, 0, st>>>(f, books, status, ffstatus, tails, job->d_scan, (unsigned)cap, ctl, trace);
+  if (trace) {
+    std::vector<unsigned long long> h((size_t)ncta * 16);
+    cudaMemcpyAsync(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for (unsigned c = 0; c < ncta; c++) { if (h[c * 16] && h[c * 16] < t0) t0 = h[c * 16]; if (h[c * 16 + 8] > t1) t1 = h[c * 16 + 8]; }
+    double acc[9] = {0};
+    for (unsigned c = 0; c < ncta; c++) for (int k = 1; k < 9; k++) acc[k] += (double)(h[c * 16 + k] - h[c * 16 + k - 1]);
+    fprintf(stderr, "[huff trace] ncta %u bpt %d span %.1f us; first-start..last-start %.1f us; mean us per phase: phase1 %.2f scan %.2f emit %.2f bits-chain %.2f align+boundary %.2f ffscan %.2f ff-chain %.2f write %.2f\n",
+            ncta, bpt, (t1 - t0) / 1e3, 0.0, acc[1] / ncta / 1e3, acc[2] / ncta / 1e3, acc[3] / ncta / 1e3, acc[4] / ncta / 1e3, acc[5] / ncta / 1e3, acc[6] / ncta / 1e3, acc[7] / ncta / 1e3, acc[8] / ncta / 1e3);
+    unsigned long long smin = ~0ull, smax = 0;
+    for (unsigned c = 0; c < ncta; c++) { if (h[c * 16] < smin) smin = h[c * 16]; if (h[c * 16] > smax) smax = h[c * 16]; }
+    fprintf(stderr, "[huff trace] CTA start spread %.1f us; cta0 %.1f..%.1f, last cta %.1f..%.1f (us after first start)\n", (smax - smin) / 1e3,
+            (h[0] - smin) / 1e3, (h[8] - smin) / 1e3, (h[(size_t)(ncta - 1) * 16] - smin) / 1e3, (h[(size_t)(ncta - 1) * 16 + 8] - smin) / 1e3);
+  }
   ws.t_end();
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(job->h_scan_bytes, ctl, 32, cudaMemcpyDeviceToHost, st));

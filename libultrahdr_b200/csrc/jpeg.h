@@ -40,7 +40,7 @@ void jpeg_frame_finish(JpegFrame* f);
 struct JpegEncodeJob {
   JpegFrame frame;
   int16_t* d_coefs[3] = {nullptr, nullptr, nullptr};  // device, [block][64] natural order
-  // per block {non-zero mask lo, hi, AC code bits, DC} from the forward stage (zigzag launches only)
+  // per block {AC code bits << 16 | DC, first 96 bits of the AC bit string} from the forward stage (zigzag launches only)
   uint4* d_meta[3] = {nullptr, nullptr, nullptr};
   // device-side entropy coding products (huffman.cu); null when the host path is used
   uint8_t* d_scan = nullptr;      // stuffed entropy-coded segment

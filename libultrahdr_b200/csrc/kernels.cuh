@@ -122,9 +122,8 @@ struct Fdct8Plane {                 // one launch covers every plane of an image
   // (device entropy coder follows): [block][64] 32-bit code-word entries instead, see fdct8.cu block_code
   int16_t* coefs[3];
   // entropy-coder side information, one uint4 per block (zigzag launches only; may be null):
-  //   x, y = 64-bit mask of the non-zero coefficients (bit k = zigzag position k, bit 0 = DC)
-  //   z    = code bits of the block's AC part: Huffman codes + magnitude bits + ZRLs + EOB
-  //   w    = the DC coefficient (sign extended)
+  //   x       = code bits of the block's AC part (Huffman codes + magnitude bits + ZRLs + EOB) << 16 | DC coefficient
+  //   y, z, w = the first 96 bits of the AC part's bit string, MSB first
   uint4* meta[3];
   int hsel[3];                      // Huffman table pair of the component: 0 luminance, 1 chrominance
 };
