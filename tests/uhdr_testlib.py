@@ -25,7 +25,7 @@ REF_SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "libuhdr_ref.so")
 REF_TURBO_SO = os.path.join(ROOT, "oracle", "_ref", "libuhdr_ref_turbo.so")
 REF_SO = REF_TURBO_SO if os.path.exists(REF_TURBO_SO) else REF_SHIM_SO
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
-GPU_SO = os.path.join(ROOT, "libultrahdr_b200", "libuhdr_b200.so")
+GPU_SO = os.environ.get("UHDR_B200_SO") or os.path.join(ROOT, "libultrahdr_b200", "libuhdr_b200.so")
 REF_DATA = "/root/reference/tests/data"
 SEED = 20240607
 
