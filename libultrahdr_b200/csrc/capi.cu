@@ -69,6 +69,9 @@ uhdr_error_info_t from_rc(int rc) {
 struct Encoder : uhdr_codec_private {
   std::map<int, DevImage> raw;         // UHDR_HDR_IMG / UHDR_SDR_IMG, device resident
   std::map<int, int> quality;
+  struct Compressed { std::vector<uint8_t> bytes; int cg, ct, range; };
+  std::map<int, Compressed> compressed;  // UHDR_SDR_IMG / UHDR_BASE_IMG / UHDR_GAIN_MAP_IMG (encode API-2/3/4)
+  uhdr_gainmap_metadata_t metadata{};
   std::vector<uint8_t> exif;
   int scale = 1, multichannel = 1, preset = UHDR_USAGE_BEST_QUALITY, output_format = UHDR_CODEC_JPG;
   float gamma = 1.0f, min_boost = FLT_MIN, max_boost = FLT_MAX, target_nits = -1.0f;
@@ -79,6 +82,8 @@ struct Encoder : uhdr_codec_private {
   uhdr_error_info_t status = ok();
   void defaults() {
     raw.clear();
+    compressed.clear();
+    memset(&metadata, 0, sizeof metadata);
     quality.clear();
     quality[UHDR_BASE_IMG] = 95;
     quality[UHDR_GAIN_MAP_IMG] = 95;
@@ -210,14 +215,40 @@ UHDR_API uhdr_error_info_t uhdr_enc_set_raw_image(uhdr_codec_private_t* enc, uhd
   return ok();
 }
 
-UHDR_API uhdr_error_info_t uhdr_enc_set_compressed_image(uhdr_codec_private_t* enc, uhdr_compressed_image_t*, uhdr_img_label_t) {
-  if (!as<Encoder>(enc)) return err(UHDR_CODEC_INVALID_PARAM, "received nullptr for uhdr codec instance");
-  return err(UHDR_CODEC_UNSUPPORTED_FEATURE, "compressed-intent inputs (encode API-2/3/4) are container re-muxing on the CPU "
-             "and are outside the B200 hot path");
+// uhdr_enc_validate_and_set_compressed_img, ultrahdr_api.cpp:512-617
+static uhdr_error_info_t set_compressed(uhdr_codec_private_t* enc, uhdr_compressed_image_t* img, int intent) {
+  Encoder* h = as<Encoder>(enc);
+  if (!h) return err(UHDR_CODEC_INVALID_PARAM, "received nullptr for uhdr codec instance");
+  if (!img) return err(UHDR_CODEC_INVALID_PARAM, "received nullptr for compressed image handle");
+  if (!img->data) return err(UHDR_CODEC_INVALID_PARAM, "received nullptr for compressed img->data field");
+  if (img->capacity < img->data_sz) return err(UHDR_CODEC_INVALID_PARAM, "img->capacity %zd is less than img->data_sz %zd", img->capacity, img->data_sz);
+  if (h->sailed)
+    return err(UHDR_CODEC_INVALID_OPERATION, "An earlier call to uhdr_encode() has switched the context from configurable "
+               "state to end state. The context is no longer configurable. To reuse, call reset()");
+  size_t off = 0, len = 0;
+  const int n = count_jpeg_images((const uint8_t*)img->data, img->data_sz, &off, &len);
+  if (n < 0) return err(UHDR_CODEC_INVALID_PARAM, "received bad/corrupted jpeg image as part of input configuration");
+  if (n == 0) return err(UHDR_CODEC_INVALID_PARAM, "compressed image received as part of input config contains no valid jpeg images");
+  // several images: the first one is taken, the rest ignored (:572-584)
+  Encoder::Compressed c;
+  c.bytes.assign((const uint8_t*)img->data + off, (const uint8_t*)img->data + off + len);
+  c.cg = img->cg; c.ct = img->ct; c.range = img->range;
+  h->compressed[intent] = std::move(c);
+  return ok();
 }
-UHDR_API uhdr_error_info_t uhdr_enc_set_gainmap_image(uhdr_codec_private_t* enc, uhdr_compressed_image_t*, uhdr_gainmap_metadata_t*) {
-  if (!as<Encoder>(enc)) return err(UHDR_CODEC_INVALID_PARAM, "received nullptr for uhdr codec instance");
-  return err(UHDR_CODEC_UNSUPPORTED_FEATURE, "encode API-4 (pre-compressed base + gain map) is outside the B200 hot path");
+UHDR_API uhdr_error_info_t uhdr_enc_set_compressed_image(uhdr_codec_private_t* enc, uhdr_compressed_image_t* img, uhdr_img_label_t intent) {
+  if (intent != UHDR_HDR_IMG && intent != UHDR_SDR_IMG && intent != UHDR_BASE_IMG)
+    return err(UHDR_CODEC_INVALID_PARAM, "invalid intent %d, expects one of {UHDR_HDR_IMG, UHDR_SDR_IMG, UHDR_BASE_IMG}", intent);
+  return set_compressed(enc, img, intent);
+}
+UHDR_API uhdr_error_info_t uhdr_enc_set_gainmap_image(uhdr_codec_private_t* enc, uhdr_compressed_image_t* img, uhdr_gainmap_metadata_t* metadata) {
+  if (!metadata) return err(UHDR_CODEC_INVALID_PARAM, "received nullptr for gainmap metadata descriptor");
+  int rc = validate_metadata(*metadata);
+  if (rc) return from_rc(rc);
+  uhdr_error_info_t st = set_compressed(enc, img, UHDR_GAIN_MAP_IMG);
+  if (st.error_code != UHDR_CODEC_OK) return st;
+  as<Encoder>(enc)->metadata = *metadata;
+  return st;
 }
 
 #define ENC_SETTER_PROLOGUE                                                                                   \
@@ -310,18 +341,20 @@ UHDR_API uhdr_error_info_t uhdr_encode(uhdr_codec_private_t* enc) {
   h->sailed = true;
   h->bind();
   auto hdr = h->raw.find(UHDR_HDR_IMG);
-  if (hdr == h->raw.end()) {
+  auto sdr = h->raw.find(UHDR_SDR_IMG);
+  auto cbase = h->compressed.find(UHDR_BASE_IMG), cgm = h->compressed.find(UHDR_GAIN_MAP_IMG), csdr = h->compressed.find(UHDR_SDR_IMG);
+  const bool api4 = cbase != h->compressed.end() && cgm != h->compressed.end();
+  if (!api4 && hdr == h->raw.end()) {
     h->status = err(UHDR_CODEC_INVALID_OPERATION, "resources required for uhdr_encode() operation are not present");
     return h->status;
   }
-  auto sdr = h->raw.find(UHDR_SDR_IMG);
-  const size_t cap = std::max<size_t>(64 * 1024, (size_t)hdr->second.v.w * hdr->second.v.h * 3 * 2);  // :1294
+  const size_t cap = api4 ? std::max<size_t>(64 * 1024, 2 * (cbase->second.bytes.size() + cgm->second.bytes.size()))
+                          : std::max<size_t>(64 * 1024, (size_t)hdr->second.v.w * hdr->second.v.h * 3 * 2);  // :1281,:1294
   if (h->out_cap < cap) {
     h->out.reset(new (std::nothrow) uint8_t[cap]);
     h->out_cap = h->out ? cap : 0;
   }
   if (!h->out) { h->status = err(UHDR_CODEC_MEM_ERROR, "unable to allocate %zu bytes for the encoded stream", cap); return h->status; }
-  h->codec.ws().rewind();
   uhdr_b200_gm_config_t cfg;
   cfg.scale_factor = h->scale;
   cfg.quality = h->quality[UHDR_GAIN_MAP_IMG];
@@ -334,8 +367,21 @@ UHDR_API uhdr_error_info_t uhdr_encode(uhdr_codec_private_t* enc) {
   cfg.sdr_is_601 = 0;
   cfg.use_luminance = 1;
   size_t n = 0;
-  int rc = h->codec.encode(hdr->second, sdr == h->raw.end() ? nullptr : &sdr->second, cfg, h->quality[UHDR_BASE_IMG],
+  int rc;
+  if (api4) {  // pre-compressed base + gain map: container work on the host
+    rc = JpegRCodec::encode_from_compressed(cbase->second.bytes.data(), cbase->second.bytes.size(), cbase->second.cg,
+                                            cgm->second.bytes.data(), cgm->second.bytes.size(), h->metadata, h->out.get(), cap, &n);
+  } else {
+    h->ensure();
+    if (h->init_rc) { h->status = err((uhdr_codec_err_t)h->init_rc, "%s", h->init_err.c_str()); return h->status; }
+    h->codec.ws().rewind();
+    if (csdr != h->compressed.end())  // API-2 (raw sdr intent given too) / API-3
+      rc = h->codec.encode_with_compressed_sdr(hdr->second, sdr == h->raw.end() ? nullptr : &sdr->second, csdr->second.bytes.data(),
+                                               csdr->second.bytes.size(), csdr->second.cg, cfg, h->out.get(), cap, &n);
+    else
+      rc = h->codec.encode(hdr->second, sdr == h->raw.end() ? nullptr : &sdr->second, cfg, h->quality[UHDR_BASE_IMG],
                            h->exif.empty() ? nullptr : h->exif.data(), h->exif.size(), h->out.get(), cap, &n);
+  }
   h->status = from_rc(rc);
   if (rc == E_OK) {
     h->out_desc.data = h->out.get();

@@ -10,6 +10,7 @@
 
 namespace uhdr_b200 {
 
+static void grab_marker(const uint8_t* d, const JpegHeader& h, uint8_t id, const char* sig, size_t sig_len, std::vector<uint8_t>* out);
 
 // ------------------------------------------------------------------------------------------------
 // encode
@@ -89,6 +90,91 @@ int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b
   pg.head = gm_head.data(); pg.head_len = gm_head.size();
   pb.head = base_head.data(); pb.head_len = base_head.size();
   return assemble_jpegr(pb, pg, exif, exif_size, md, out, cap, out_size);
+}
+
+int JpegRCodec::encode_from_compressed(const uint8_t* base, size_t base_size, int base_cg, const uint8_t* gainmap, size_t gainmap_size,
+                                       const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size) {
+  JpegHeader bh;
+  int rc = jpeg_read_header(base, base_size, &bh);  // parseImage :392
+  if (rc) return rc;
+  std::vector<uint8_t> blob;
+  if (!md.use_base_cg) {
+    JpegHeader gh;
+    rc = jpeg_read_header(gainmap, gainmap_size, &gh);
+    if (rc) return rc;
+    grab_marker(gainmap, gh, 0xE2, "ICC_PROFILE", 12, &blob);
+    if (blob.empty())
+      return fail(E_UNSUPPORTED, "For gainmap application space to be alternate image space, gainmap image is expected to "
+                  "contain alternate image color space in the form of ICC. The ICC marker in gainmap jpeg is missing.");
+  }
+  grab_marker(base, bh, 0xE2, "ICC_PROFILE", 12, &blob);
+  const uint8_t* icc = nullptr;
+  size_t icc_n = 0;
+  if (blob.empty()) {  // add ICC if not already present
+    if (base_cg <= UHDR_CG_UNSPECIFIED || base_cg > UHDR_CG_BT_2100) return fail(E_INVALID_PARAM, "Unrecognized 420 color gamut %d", base_cg);
+    icc = icc_profile(UHDR_CT_SRGB, base_cg, &icc_n);
+  }
+  JpegPieces pb, pg;
+  pb.head = base; pb.head_len = base_size; pb.scan = nullptr; pb.scan_len = 0; pb.whole = true;
+  pg.head = gainmap; pg.head_len = gainmap_size; pg.scan = nullptr; pg.scan_len = 0; pg.whole = true;
+  return assemble_jpegr(pb, pg, nullptr, 0, md, out, cap, out_size, icc, icc_n);
+}
+
+int JpegRCodec::encode_with_compressed_sdr(const DevImage& hdr, const DevImage* sdr_in, const uint8_t* sdr_jpg, size_t sdr_jpg_size,
+                                           int sdr_jpg_cg, const uhdr_b200_gm_config_t& cfg_in, uint8_t* out, size_t cap,
+                                           size_t* out_size) {
+  uhdr_b200_gm_config_t cfg = cfg_in;
+  DevImage sdr;
+  int rc;
+  if (sdr_in) {  // API-2: only the size of the compressed image is looked at (PARSE_STREAM :297-311)
+    JpegHeader h;
+    rc = jpeg_read_header(sdr_jpg, sdr_jpg_size, &h);
+    if (rc) return rc;
+    if (hdr.v.w != h.frame.width || hdr.v.h != h.frame.height)
+      return fail(E_INVALID_PARAM, "sdr intent resolution %dx%d and compressed image sdr intent resolution %dx%d do not match",
+                  sdr_in->v.w, sdr_in->v.h, h.frame.width, h.frame.height);
+    sdr = *sdr_in;
+    cfg.sdr_is_601 = 0;
+  } else {       // API-3: decode the input JPEG; its YCbCr encoding is BT.601
+    JpegHeader h;
+    rc = decode_jpeg_dev(ws_, sdr_jpg, sdr_jpg_size, 0, &sdr, &h);
+    if (rc) return rc;
+    std::vector<uint8_t> blob;
+    grab_marker(sdr_jpg, h, 0xE2, "ICC_PROFILE", 12, &blob);
+    if (!blob.empty()) {
+      const int cg = icc_read_gamut(blob.data(), blob.size());
+      if (cg == UHDR_CG_UNSPECIFIED || (sdr_jpg_cg != UHDR_CG_UNSPECIFIED && sdr_jpg_cg != cg))
+        return fail(E_INVALID_PARAM, "configured color gamut %d does not match with color gamut specified in icc box %d", sdr_jpg_cg, cg);
+      sdr.cg = cg;
+    } else {
+      if (sdr_jpg_cg <= UHDR_CG_UNSPECIFIED || sdr_jpg_cg > UHDR_CG_BT_2100) return fail(E_INVALID_PARAM, "Unrecognized 420 color gamut %d", sdr_jpg_cg);
+      sdr.cg = sdr_jpg_cg;
+    }
+    if (hdr.v.w != sdr.v.w || hdr.v.h != sdr.v.h)
+      return fail(E_INVALID_PARAM, "sdr intent resolution %dx%d and hdr intent resolution %dx%d do not match", sdr.v.w, sdr.v.h,
+                  hdr.v.w, hdr.v.h);
+    cfg.sdr_is_601 = 1;
+  }
+  cfg.use_luminance = 1;
+  GainmapJob gm;
+  rc = generate_gainmap_dev(ws_, sdr, hdr, cfg, 64, &gm);
+  if (rc) return rc;
+  JpegEncodeJob gm_jpeg;
+  rc = block_stage(ws_, gm.map, cfg.quality, &gm_jpeg);
+  if (rc) return rc;
+  rc = ws_.sync();
+  if (rc) return rc;
+  if ((rc = jpeg_entropy_fetch(ws_, &gm_jpeg))) return rc;
+  rc = ws_.sync();
+  if (rc) return rc;
+  uhdr_gainmap_metadata_t md;
+  finish_gainmap_metadata(gm, &md);
+  size_t icc_gm_n = 0;
+  const uint8_t* icc_gm = icc_profile(gm.map.ct, gm.map.cg, &icc_gm_n);
+  std::vector<uint8_t> gm_file;
+  rc = jpeg_finish_stream(gm_jpeg, icc_gm, icc_gm_n, jpeg_gainmap_comment(), &gm_file);
+  if (rc) return rc;
+  return encode_from_compressed(sdr_jpg, sdr_jpg_size, sdr_jpg_cg, gm_file.data(), gm_file.size(), md, out, cap, out_size);
 }
 
 int JpegRCodec::encode_host(const uhdr_raw_image_t& hdr, const uhdr_raw_image_t* sdr,

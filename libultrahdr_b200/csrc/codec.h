@@ -28,6 +28,15 @@ class JpegRCodec {
   // otherwise.  Inputs are device images previously uploaded on ws().stream().
   int encode(const DevImage& hdr, const DevImage* sdr, const uhdr_b200_gm_config_t& cfg, int base_quality,
              const uint8_t* exif, size_t exif_size, uint8_t* out, size_t cap, size_t* out_size);
+  // JpegR::encodeJPEGR API-2 (jpegr.cpp:294-324, sdr != nullptr) / API-3 (:326-386, the compressed SDR is
+  // decoded on the device and the map is computed with BT.601 luma): gain map from the intents, its JPEG,
+  // appended to the caller's compressed SDR image.  `sdr_jpg_cg`: gamut of the compressed image when it
+  // carries no ICC profile.
+  int encode_with_compressed_sdr(const DevImage& hdr, const DevImage* sdr, const uint8_t* sdr_jpg, size_t sdr_jpg_size,
+                                 int sdr_jpg_cg, const uhdr_b200_gm_config_t& cfg, uint8_t* out, size_t cap, size_t* out_size);
+  // API-4 (:388-434): container work only, no device
+  static int encode_from_compressed(const uint8_t* base, size_t base_size, int base_cg, const uint8_t* gainmap, size_t gainmap_size,
+                                    const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size);
   // convenience: host descriptors
   int encode_host(const uhdr_raw_image_t& hdr, const uhdr_raw_image_t* sdr, const uhdr_b200_gm_config_t& cfg,
                   int base_quality, const uint8_t* exif, size_t exif_size, uint8_t* out, size_t cap,

@@ -530,7 +530,8 @@ static void make_mpf(size_t primary_size, size_t secondary_size, size_t secondar
 }
 
 int assemble_jpegr(const JpegPieces& base, const JpegPieces& gm, const uint8_t* exif, size_t exif_size,
-                   const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size) {
+                   const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size,
+                   const uint8_t* icc_arg, size_t icc_arg_size) {
   static const char kIsoNs[] = "urn:iso:std:iso:ts:21496:-1";  // 27 chars + NUL
   const size_t ns_len = sizeof kIsoNs;
   std::vector<uint8_t> iso;
@@ -560,15 +561,26 @@ int assemble_jpegr(const JpegPieces& base, const JpegPieces& gm, const uint8_t* 
     if (2 + 2 + l <= bn) W(put(b + 2, 2 + l));
     bp += 2 + l;
   }
-  if (exif && exif_size) { W(put_marker(0xE1, exif_size)); W(put(exif, exif_size)); }
-  // ICC carried by the base stream is re-emitted here (jpegr.cpp:1214-1217,1266-1275)
+  // EXIF and ICC carried by the base stream are re-emitted here (jpegr.cpp:1173-1217,1239-1275)
   const uint8_t* icc = nullptr;
-  size_t icc_len = 0;
-  for (size_t q = bp; q + 4 <= bn && b[q] == 0xFF && b[q + 1] != 0xDA;) {
+  const uint8_t* base_exif = nullptr;
+  size_t icc_len = 0, base_exif_len = 0;
+  for (size_t q = 2; q + 4 <= bn && b[q] == 0xFF && b[q + 1] != 0xDA;) {
     const size_t l = (b[q + 2] << 8) | b[q + 3];
+    if (l < 2 || q + 2 + l > bn) break;
     if (b[q + 1] == 0xE2 && l > 2 + 12 && !memcmp(b + q + 4, "ICC_PROFILE", 12) && !icc) { icc = b + q + 4; icc_len = l - 2; }
+    if (b[q + 1] == 0xE1 && l > 2 + 6 && !memcmp(b + q + 4, "Exif\0\0", 6) && !base_exif) { base_exif = b + q + 4; base_exif_len = l - 2; }
     q += 2 + l;
   }
+  if (base_exif) {
+    if (exif && exif_size)
+      return fail(E_INVALID_PARAM, "received exif from uhdr_enc_set_exif_data() while the base image intent already contains "
+                  "exif, unsure which one to use");
+    exif = base_exif;
+    exif_size = base_exif_len;
+  }
+  if (exif && exif_size) { W(put_marker(0xE1, exif_size)); W(put(exif, exif_size)); }
+  if (icc_arg && icc_arg_size) { icc = icc_arg; icc_len = icc_arg_size; }
   if (icc) { W(put_marker(0xE2, icc_len)); W(put(icc, icc_len)); }
   {  // ISO version-only block (:1277-1292)
     const uint8_t zeros[4] = {0, 0, 0, 0};
@@ -589,7 +601,7 @@ int assemble_jpegr(const JpegPieces& base, const JpegPieces& gm, const uint8_t* 
   if (!sos) return fail(E_INVALID_PARAM, "SOS marker not found while reordering base jpeg segments, unable to append gainmap");
   {
     const size_t mpf_len = 2 + 86;
-    const size_t tail = (bn - sos) + base.scan_len + 2;  // SOS header + entropy-coded data + EOI
+    const size_t tail = (bn - sos) + base.scan_len + (base.whole ? 0 : 2);  // SOS header + entropy-coded data + EOI
     const size_t primary_size = pos + 2 + mpf_len + tail;
     const size_t secondary_offset = primary_size - pos - 8;
     std::vector<uint8_t> mpf;
@@ -597,13 +609,13 @@ int assemble_jpegr(const JpegPieces& base, const JpegPieces& gm, const uint8_t* 
     W(put_marker(0xE2, mpf.size())); W(put(mpf.data(), mpf.size()));
   }
   W(put(b + sos, bn - sos));
-  W(put(base.scan, base.scan_len));
-  W(put(eoi, 2));
+  if (base.scan_len) W(put(base.scan, base.scan_len));
+  if (!base.whole) W(put(eoi, 2));
   W(put(soi, 2));
   W(put_marker(0xE2, ns_len + iso.size())); W(put(kIsoNs, ns_len)); W(put(iso.data(), iso.size()));
   W(put(gm.head + 2, gm.head_len - 2));
-  W(put(gm.scan, gm.scan_len));
-  W(put(eoi, 2));
+  if (gm.scan_len) W(put(gm.scan, gm.scan_len));
+  if (!gm.whole) W(put(eoi, 2));
 #undef W
   *out_size = pos;
   return E_OK;
@@ -634,6 +646,26 @@ static bool scan_one(const uint8_t* d, size_t n, size_t start, size_t* end) {
   }
   return false;
 }
+int count_jpeg_images(const uint8_t* d, size_t n, size_t* first_off, size_t* first_len) {
+  int found = 0;
+  size_t p = 0;
+  while (p + 2 <= n) {
+    if (d[p] == 0xFF && d[p + 1] == 0xD8) {
+      size_t e;
+      if (!scan_one(d, n, p, &e)) return found ? found : -1;
+      if (!found) {
+        if (first_off) *first_off = p;
+        if (first_len) *first_len = e - p;
+      }
+      found++;
+      p = e;
+    } else {
+      p++;
+    }
+  }
+  return found;
+}
+
 int split_jpegr(const uint8_t* d, size_t n, size_t* po, size_t* pl, size_t* go, size_t* gl) {
   size_t found = 0, p = 0, off[2], len[2];
   while (found < 2 && p + 2 <= n) {

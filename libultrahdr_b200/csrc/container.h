@@ -41,12 +41,22 @@ struct JpegPieces {
   size_t head_len;
   const uint8_t* scan;
   size_t scan_len;
-  size_t total() const { return head_len + scan_len + 2; }
+  // whole = true: `head` is a complete JPEG file as the caller handed it in (encode API-2/3/4); its bytes
+  // from SOS on are copied verbatim, EOI is not implied
+  bool whole = false;
+  size_t total() const { return head_len + scan_len + (whole ? 0 : 2); }
 };
 
 // appendGainMap with UHDR_WRITE_ISO on / UHDR_WRITE_XMP off (the reference's default build).
+// icc / icc_size: profile to write when the primary image carries none (API-4, jpegr.cpp:413-431); the
+// primary image's own ICC and EXIF markers are carried over (:1173-1217), an `exif` argument next to an
+// EXIF marker in the primary image is an error like in the reference.
 int assemble_jpegr(const JpegPieces& primary, const JpegPieces& gainmap, const uint8_t* exif, size_t exif_size,
-                   const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size);
+                   const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size,
+                   const uint8_t* icc = nullptr, size_t icc_size = 0);
+// number of JPEG images in a buffer as image_io's scanner counts them and the range of the first one
+// (uhdr_enc_set_compressed_image keeps the first, ultrahdr_api.cpp:548-584); -1: corrupt
+int count_jpeg_images(const uint8_t* data, size_t size, size_t* first_off = nullptr, size_t* first_len = nullptr);
 
 // locate primary image and gain-map image inside a JPEG/R file
 int split_jpegr(const uint8_t* data, size_t size, size_t* p_off, size_t* p_len, size_t* g_off,

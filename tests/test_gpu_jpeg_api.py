@@ -279,3 +279,43 @@ def test_encode_batch_matches_single_encodes(gpu, oracle_libs):
         for i in range(n):
             got = bytes(bufs[i][:outs[i].data_sz])
             assert got == singles[i], (streams, i, len(got), len(singles[i]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,kind", [(256, 128, "smooth"), (648, 364, "noise"), (1920, 1080, "smooth")])
+def test_uhdr_encode_api2_api3_file_bytes(gpu, oracle_libs, w, h, kind):
+    """Encode API-2 (raw hdr + raw sdr + compressed sdr) and API-3 (raw hdr + compressed sdr: the JPEG is
+    decoded on the device, the gain map computed against it with BT.601 luma): files equal the reference's."""
+    if not oracle_libs.have_ref():
+        pytest.skip("reference build not available")
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    ref = T.UhdrApi(oracle_libs.Ref().lib)
+    mine = T.UhdrApi(gpu.lib)
+    hdr, sdr, keep = _frames(w, h, kind)
+    # compressed sdr intents: the reference's own base image (4:2:0, with ICC) and a Pillow file (4:2:0 / 4:4:4, no ICC)
+    base_ref = _split_base(ref.encode(hdr, sdr))
+    rgb = np.random.RandomState(5).randint(0, 256, (h, w, 3)).astype(np.uint8)
+    pil = {}
+    for ss in (2, 0):
+        b = io.BytesIO()
+        PIL.fromarray(rgb).save(b, "JPEG", quality=90, subsampling=ss)
+        pil[ss] = b.getvalue()
+    cases = [("api2", base_ref, sdr, -1, {}), ("api2", base_ref, sdr, -1, {"scale": 2, "multichannel": 0}),
+             ("api3", base_ref, None, -1, {}), ("api3", base_ref, None, A.CG_BT709, {"multichannel": 0}),
+             ("api3", pil[2], None, A.CG_P3, {}), ("api3", pil[0], None, A.CG_BT709, {"scale": 2}),
+             ("api3", pil[2], None, -1, {}),           # no ICC and no gamut: error in both
+             ("api3", base_ref, None, A.CG_BT2100, {})]  # configured gamut contradicts the ICC: error in both
+    for name, jpg, raw, cg, opts in cases:
+        a = mine.encode_with_compressed_sdr(hdr, jpg, raw, cg, **opts)
+        b = ref.encode_with_compressed_sdr(hdr, jpg, raw, cg, **opts)
+        assert type(a) is type(b), (name, cg, opts, a if isinstance(a, int) else len(a), b if isinstance(b, int) else len(b))
+        assert a == b, (name, cg, opts)
+
+
+def _split_base(data):
+    """primary image of a JPEG/R (up to the second SOI that starts a whole JPEG at an EOI boundary)"""
+    i = data.index(b"\xff\xd9\xff\xd8")
+    while b"\xff\xda" not in data[:i]:
+        i = data.index(b"\xff\xd9\xff\xd8", i + 2)
+    return data[:i + 2]

@@ -365,6 +365,29 @@ class UhdrApi:
         finally:
             L.uhdr_release_encoder(enc)
 
+    def encode_with_compressed_sdr(self, hdr, sdr_jpg, sdr=None, sdr_jpg_cg=-1, gm_quality=95, scale=1, multichannel=1):
+        """encode API-2 (raw sdr intent given too) / API-3; returns the file or the error code"""
+        L = self.lib
+        L.uhdr_enc_set_compressed_image.restype = A.ErrorInfo
+        enc = C.c_void_p(L.uhdr_create_encoder())
+        try:
+            self._ck(L.uhdr_enc_set_raw_image(enc, C.byref(hdr), A.HDR_IMG))
+            if sdr is not None:
+                self._ck(L.uhdr_enc_set_raw_image(enc, C.byref(sdr), A.SDR_IMG))
+            jb = np.frombuffer(sdr_jpg, np.uint8).copy()
+            ci = A.CompressedImage(jb.ctypes.data, len(sdr_jpg), len(sdr_jpg), sdr_jpg_cg, -1, -1)
+            self._ck(L.uhdr_enc_set_compressed_image(enc, C.byref(ci), A.SDR_IMG))
+            self._ck(L.uhdr_enc_set_quality(enc, gm_quality, A.GAIN_MAP_IMG))
+            self._ck(L.uhdr_enc_set_gainmap_scale_factor(enc, scale))
+            self._ck(L.uhdr_enc_set_using_multi_channel_gainmap(enc, multichannel))
+            e = L.uhdr_encode(enc)
+            if e.error_code:
+                return int(e.error_code)
+            o = L.uhdr_get_encoded_stream(enc).contents
+            return C.string_at(o.data, o.data_sz)
+        finally:
+            L.uhdr_release_encoder(enc)
+
     def decode(self, data, out_fmt=A.FMT_RGBAF16, out_ct=A.CT_LINEAR, boost=None):
         L = self.lib
         dec = C.c_void_p(L.uhdr_create_decoder())
