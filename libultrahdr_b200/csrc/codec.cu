@@ -423,10 +423,9 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
     tr.mark("gainmap jpeg enqueued");
   }
   if (md_out || !sdr_only) {  // :1497-1518
-    if (!want_map) {
-      rc = jpeg_read_header(data + go, gl, &gh);
-      if (rc) return rc;
-    }
+    // the reference reads the gain-map image's markers only when it decodes that image (:1484-1495):
+    // metadata alone with SDR output finds no buffer to parse
+    if (!want_map) return fail(E_INVALID_PARAM, "received no valid buffer to parse gainmap metadata");
     std::vector<uint8_t> xmp, exif;
     grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &blob);
     grab_marker(data + go, gh, 0xE1, "http://ns.adobe.com/xap/1.0/", 29, &xmp);

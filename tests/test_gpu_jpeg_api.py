@@ -294,7 +294,8 @@ def test_uhdr_encode_api2_api3_file_bytes(gpu, oracle_libs, w, h, kind):
     mine = T.UhdrApi(gpu.lib)
     hdr, sdr, keep = _frames(w, h, kind)
     # compressed sdr intents: the reference's own base image (4:2:0, with ICC) and a Pillow file (4:2:0 / 4:4:4, no ICC)
-    base_ref = _split_base(ref.encode(hdr, sdr))
+    from test_probe_cpu import _probe
+    base_ref = _probe(oracle_libs.Ref().lib, ref.encode(hdr, sdr))["base_image"]
     rgb = np.random.RandomState(5).randint(0, 256, (h, w, 3)).astype(np.uint8)
     pil = {}
     for ss in (2, 0):
@@ -311,11 +312,3 @@ def test_uhdr_encode_api2_api3_file_bytes(gpu, oracle_libs, w, h, kind):
         b = ref.encode_with_compressed_sdr(hdr, jpg, raw, cg, **opts)
         assert type(a) is type(b), (name, cg, opts, a if isinstance(a, int) else len(a), b if isinstance(b, int) else len(b))
         assert a == b, (name, cg, opts)
-
-
-def _split_base(data):
-    """primary image of a JPEG/R (up to the second SOI that starts a whole JPEG at an EOI boundary)"""
-    i = data.index(b"\xff\xd9\xff\xd8")
-    while b"\xff\xda" not in data[:i]:
-        i = data.index(b"\xff\xd9\xff\xd8", i + 2)
-    return data[:i + 2]
