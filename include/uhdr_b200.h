@@ -50,6 +50,27 @@ UHDR_EXTERN int uhdr_b200_tonemap(const uhdr_raw_image_t* hdr, uhdr_raw_image_t*
 /* UltraHdr::convertYuv (in place), ref lib/src/jpegr.cpp:436 */
 UHDR_EXTERN int uhdr_b200_convert_yuv(uhdr_raw_image_t* image, int src_cg, int dst_cg);
 
+/* The same four stages on DEVICE memory: every plane pointer in the descriptors is a device pointer (strides
+ * in pixels, as everywhere), `stream` is the caller's cudaStream_t (passed as void* to keep this header free
+ * of CUDA types; NULL = the legacy default stream).  Kernels are enqueued on that stream and the call returns
+ * without synchronising -- nothing crosses PCIe -- with one exception: uhdr_b200_generate_gainmap_dev with the
+ * two-pass preset (UHDR_USAGE_BEST_QUALITY) drains the stream before returning, because the metadata it hands
+ * back is derived from the image-wide min / max.  A maintainer chaining generateGainMap -> compressImage, or
+ * decode -> applyGainMap -> display, binds these instead of the host-pointer forms above.  Scratch memory comes
+ * from the calling host thread's workspace: keep one stream per host thread, or synchronise between calls.
+ * Alignment for the vectorised kernels (else the generic ones run): planes 16-byte aligned, strides multiples
+ * of 4 pixels.  dest / gainmap planes must be allocated by the caller: gain map (w/scale)*(h/scale)*(3|1) bytes
+ * with stride >= width, apply destination w*h*(8|4) bytes, tone-map destination in the SDR format matching the
+ * HDR one (P010 -> YCbCr420, RGBA1010102 / RGBAHalfFloat -> RGBA8888). */
+UHDR_EXTERN int uhdr_b200_generate_gainmap_dev(const uhdr_raw_image_t* sdr_dev, const uhdr_raw_image_t* hdr_dev,
+                                               const uhdr_b200_gm_config_t* cfg, uhdr_gainmap_metadata_t* metadata_out,
+                                               uhdr_raw_image_t* gainmap_dev, void* stream);
+UHDR_EXTERN int uhdr_b200_apply_gainmap_dev(const uhdr_raw_image_t* sdr_dev, const uhdr_raw_image_t* gainmap_dev,
+                                            const uhdr_gainmap_metadata_t* metadata, int output_ct, float max_display_boost,
+                                            uhdr_raw_image_t* dest_dev, void* stream);
+UHDR_EXTERN int uhdr_b200_tonemap_dev(const uhdr_raw_image_t* hdr_dev, uhdr_raw_image_t* sdr_dev, void* stream);
+UHDR_EXTERN int uhdr_b200_convert_yuv_dev(uhdr_raw_image_t* image_dev, int src_cg, int dst_cg, void* stream);
+
 /* JpegEncoderHelper::compressImage, ref lib/src/jpegencoderhelper.cpp:101.  `is_gainmap_comment`
  * is implied by the format exactly as in the reference (RGB888 / Y400 carry the COM marker).
  * out must hold `cap` bytes. */

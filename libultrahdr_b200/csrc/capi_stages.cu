@@ -160,4 +160,118 @@ UHDR_API int uhdr_b200_convert_yuv(uhdr_raw_image_t* image, int src_cg, int dst_
   return ws->sync();
 }
 
+// ---- device-pointer stage entry points (include/uhdr_b200.h, "Internal FFI" of SURVEY section 8b) ----------
+// Descriptors carry DEVICE pointers; kernels are enqueued on the caller's stream; nothing crosses PCIe.
+namespace {
+DevImage dev_view(const uhdr_raw_image_t& d) {
+  DevImage v;
+  memset(&v, 0, sizeof v);
+  v.v.fmt = d.fmt;
+  v.v.w = d.w;
+  v.v.h = d.h;
+  for (int i = 0; i < 3; i++) {
+    v.v.p[i] = d.planes[i];
+    v.v.stride[i] = d.stride[i];
+  }
+  v.v.full_range = d.range == UHDR_CR_FULL_RANGE;
+  v.cg = d.cg;
+  v.ct = d.ct;
+  v.range = d.range;
+  return v;
+}
+// The calling thread's workspace (scratch arenas) on the caller's stream for one call.  The arenas were
+// rewound on entry: device scratch of the previous call is protected by stream order, but its pinned host
+// staging (the per-call gain tables of applyGainMap) may still be waiting for its H2D copy, so a new call
+// first waits for the event the previous one left behind.
+struct StreamScope {
+  Workspace* ws;
+  cudaStream_t st;
+  static cudaEvent_t& last_event() {
+    static thread_local cudaEvent_t e = nullptr;
+    return e;
+  }
+  StreamScope(Workspace* w, void* stream) : ws(w), st((cudaStream_t)stream) {
+    if (!ws) return;
+    if (last_event()) cudaEventSynchronize(last_event());
+    ws->use_external_stream(st);
+  }
+  ~StreamScope() {
+    if (!ws) return;
+    if (!last_event()) cudaEventCreateWithFlags(&last_event(), cudaEventDisableTiming);
+    if (last_event()) cudaEventRecord(last_event(), st);
+    ws->clear_external_stream();
+  }
+};
+}  // namespace
+
+UHDR_API int uhdr_b200_generate_gainmap_dev(const uhdr_raw_image_t* sdr, const uhdr_raw_image_t* hdr, const uhdr_b200_gm_config_t* cfg,
+                                            uhdr_gainmap_metadata_t* md_out, uhdr_raw_image_t* gainmap, void* stream) {
+  if (!sdr || !hdr || !cfg || !md_out || !gainmap || !gainmap->planes[0]) return fail(E_INVALID_PARAM, "received nullptr argument");
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  StreamScope scope(ws, stream);
+  GainmapJob job;
+  job.map.v.p[0] = gainmap->planes[0];
+  job.map.v.stride[0] = gainmap->stride[0];
+  int rc = generate_gainmap_dev(*ws, dev_view(*sdr), dev_view(*hdr), *cfg, 64, &job);
+  if (rc) return rc;
+  gainmap->fmt = (uhdr_img_fmt_t)job.map.v.fmt;
+  gainmap->cg = (uhdr_color_gamut_t)job.map.cg;
+  gainmap->ct = (uhdr_color_transfer_t)job.map.ct;
+  gainmap->range = (uhdr_color_range_t)job.map.range;
+  gainmap->w = job.map.v.w;
+  gainmap->h = job.map.v.h;
+  // the two-pass preset derives the metadata from the image-wide min / max: those six floats are the only
+  // bytes that travel, and the stream has to be drained for them; the one-pass metadata is known up front
+  if (!job.onepass && (rc = ws->sync())) return rc;
+  finish_gainmap_metadata(job, md_out);
+  return E_OK;
+}
+
+UHDR_API int uhdr_b200_apply_gainmap_dev(const uhdr_raw_image_t* sdr, const uhdr_raw_image_t* gainmap, const uhdr_gainmap_metadata_t* md,
+                                         int output_ct, float max_display_boost, uhdr_raw_image_t* dest, void* stream) {
+  if (!sdr || !gainmap || !md || !dest || !dest->planes[0]) return fail(E_INVALID_PARAM, "received nullptr argument");
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  StreamScope scope(ws, stream);
+  DevImage dd = dev_view(*dest);
+  dd.v.w = sdr->w;
+  dd.v.h = sdr->h;
+  int rc = apply_gainmap_dev(*ws, dev_view(*sdr), dev_view(*gainmap), *md, output_ct, max_display_boost, &dd);
+  if (rc) return rc;
+  dest->w = sdr->w;
+  dest->h = sdr->h;
+  dest->cg = (uhdr_color_gamut_t)dd.cg;
+  dest->ct = (uhdr_color_transfer_t)output_ct;
+  dest->range = UHDR_CR_FULL_RANGE;
+  return E_OK;
+}
+
+UHDR_API int uhdr_b200_tonemap_dev(const uhdr_raw_image_t* hdr, uhdr_raw_image_t* sdr, void* stream) {
+  if (!hdr || !sdr || !sdr->planes[0]) return fail(E_INVALID_PARAM, "received nullptr argument");
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  StreamScope scope(ws, stream);
+  DevImage ds = dev_view(*sdr);
+  ds.v.w = hdr->w;
+  ds.v.h = hdr->h;
+  int rc = tonemap_dev(*ws, dev_view(*hdr), &ds);
+  if (rc) return rc;
+  sdr->w = hdr->w;
+  sdr->h = hdr->h;
+  sdr->cg = (uhdr_color_gamut_t)ds.cg;
+  sdr->ct = (uhdr_color_transfer_t)ds.ct;
+  sdr->range = (uhdr_color_range_t)ds.range;
+  return E_OK;
+}
+
+UHDR_API int uhdr_b200_convert_yuv_dev(uhdr_raw_image_t* image, int src_cg, int dst_cg, void* stream) {
+  if (!image) return fail(E_INVALID_PARAM, "received nullptr argument");
+  Workspace* ws = tls_workspace();
+  if (!ws) return E_ERROR;
+  StreamScope scope(ws, stream);
+  DevImage d = dev_view(*image);
+  return convert_yuv_dev(*ws, &d, src_cg, dst_cg, /*in_place=*/true);
+}
+
 }  // extern "C"

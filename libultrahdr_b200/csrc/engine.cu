@@ -167,7 +167,15 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   p.sdr_nits = 203.0f;
   p.hdr_nits = hdr.ct == UHDR_CT_LINEAR ? 203.0f : hdr_white_nits;
   p.luts = ws.luts();
-  int rc = alloc_dev_image(ws, cfg.multichannel ? F_RGB888 : F_Y400, mw, mh, map_align, &job->map);
+  int rc = E_OK;
+  if (job->map.v.p[0]) {  // caller-provided destination (device-pointer stage API): geometry checked, pixels written there
+    if (job->map.v.stride[0] < mw) return fail(E_INVALID_PARAM, "gain map destination stride %d is smaller than its width %d", job->map.v.stride[0], mw);
+    job->map.v.fmt = cfg.multichannel ? F_RGB888 : F_Y400;
+    job->map.v.w = mw;
+    job->map.v.h = mh;
+  } else {
+    rc = alloc_dev_image(ws, cfg.multichannel ? F_RGB888 : F_Y400, mw, mh, map_align, &job->map);
+  }
   if (rc) return rc;
   job->map.cg = hdr.cg;  // :714-716: initialised with the hdr intent's colour aspects
   job->map.ct = hdr.ct;

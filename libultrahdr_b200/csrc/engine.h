@@ -25,7 +25,7 @@ int upload_image(Workspace& ws, const uhdr_raw_image_t& src, DevImage* out);
 int download_image(Workspace& ws, const DevImage& src, uhdr_raw_image_t* dst);
 
 struct GainmapJob {      // state between enqueue and metadata finish
-  DevImage map;          // RGB888 / Y400 in device memory, stride = map_w aligned to `map_align`
+  DevImage map{};        // RGB888 / Y400 in device memory, stride = map_w aligned to `map_align`; planes preset by the caller = destination
   int nch = 0, onepass = 0;
   float hdr_white_nits = 0, gamma = 1;
   float target_nits = -1;

@@ -213,7 +213,7 @@ int Workspace::init() {
   return E_OK;
 }
 int Workspace::sync() {
-  CUDA_TRY(cudaStreamSynchronize(stream_));
+  CUDA_TRY(cudaStreamSynchronize(stream()));
   if (!spans_.empty()) t_collect();
   return E_OK;
 }
@@ -248,12 +248,12 @@ cudaEvent_t Workspace::get_event() {
 void Workspace::t_begin(const char* name) {
   if (!g_timing) return;
   Span s{name, get_event(), get_event()};
-  cudaEventRecord(s.a, stream_);
+  cudaEventRecord(s.a, stream());
   spans_.push_back(s);
 }
 void Workspace::t_end() {
   if (!g_timing || spans_.empty()) return;
-  cudaEventRecord(spans_.back().b, stream_);
+  cudaEventRecord(spans_.back().b, stream());
 }
 void Workspace::t_collect() {
   std::lock_guard<std::mutex> lk(g_timing_mu);

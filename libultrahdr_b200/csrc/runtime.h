@@ -87,7 +87,11 @@ class Workspace {
   Workspace();
   ~Workspace();
   int init();  // binds to the current device, creates the stream
-  cudaStream_t stream() const { return stream_; }
+  cudaStream_t stream() const { return ext_stream_set_ ? ext_stream_ : stream_; }
+  // run the following calls on a caller-owned stream (the *_dev stage entry points); clear_external_stream()
+  // returns to the workspace's own
+  void use_external_stream(cudaStream_t s) { ext_stream_ = s; ext_stream_set_ = true; }
+  void clear_external_stream() { ext_stream_set_ = false; }
   void* dalloc(size_t bytes) { return dev_.alloc(bytes); }
   void* halloc(size_t bytes) { return host_.alloc(bytes); }
   void rewind() { dev_.rewind(); host_.rewind(); }
@@ -104,6 +108,8 @@ class Workspace {
  private:
   Arena dev_{false}, host_{true};
   cudaStream_t stream_ = nullptr;
+  cudaStream_t ext_stream_ = nullptr;
+  bool ext_stream_set_ = false;
   const float* luts_ = nullptr;
   int device_ = -1;
   struct Span { const char* name; cudaEvent_t a, b; };
