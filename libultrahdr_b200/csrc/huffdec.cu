@@ -37,7 +37,7 @@ namespace {
 
 constexpr int kSeqBits = 1024;
 constexpr int kLutBits = 9;
-constexpr int kRoundsPerBatch = 8;
+constexpr int kRoundsPerBatch = 16;  // settled rounds cost ~a launch each (CTAs without work exit at once): one host check usually suffices
 constexpr int kMaxRounds = 512;
 
 struct HdTables {  // 0 DC table 0, 1 DC table 1, 2 AC table 0, 3 AC table 1
@@ -157,12 +157,16 @@ __device__ __forceinline__ void stage_shared(HdShared& S, const HdShared* __rest
 __global__ void __launch_bounds__(128) k_hd_sync(const uint32_t* __restrict__ bits, unsigned long long* out, unsigned long long* used, unsigned* cnt,
                                                  unsigned* changed, const HdShared* __restrict__ gs) {
   __shared__ HdShared S;
-  stage_shared(S, gs);
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S.f.nseq) return;
+  const unsigned nseq = gs->f.nseq;
   // state word: bit position | (z | c << 8) << 32
-  const unsigned long long entry = i == 0 ? 0ull : *reinterpret_cast<volatile unsigned long long*>(out + i - 1);
-  if (entry == used[i]) return;  // same start as last time: same result
+  const unsigned long long entry = (i == 0 || i >= nseq) ? 0ull : *reinterpret_cast<volatile unsigned long long*>(out + i - 1);
+  const bool todo = i < nseq && entry != used[i];  // same start as last time: same result
+  // after the second round nearly every subsequence is settled: a CTA without work leaves before it
+  // stages the 6 KB of tables, so the later rounds cost little more than their launch
+  if (!__syncthreads_or(todo ? 1 : 0)) return;
+  stage_shared(S, gs);
+  if (!todo) return;
   unsigned p = (unsigned)entry, z = (unsigned)(entry >> 32) & 0xff, c = (unsigned)(entry >> 40);
   const unsigned end_bit = min((i + 1) * (unsigned)kSeqBits, S.f.total_bits);
   const HdOut none = {};
