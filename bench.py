@@ -205,8 +205,12 @@ ALG_BYTES_PER_PX = {
     "yuv_convert": 3.0,                 # in place: 1.5 read + 1.5 written
     "tonemap": 4.5,
     "apply_gainmap": 13.5,              # YUV420 1.5 + RGBA8888 map 4 read, RGBA-F16 8 written
-    "fdct_quant": (4.5 + 9.0) / 2,      # avg of the two launches: 4:2:0 image 1.5 in + 3 out; RGB map 3 in + 6 out
-    "huff_encode": (3.0 + 6.0) / 2,     # coefficient read (2 B/sample); stream writes are O(stream size)
+    # FDCT+quant = 1 B/sample in + 2 B/sample out (4.5 B/px for 4:2:0, 9 B/px for 3-comp 4:4:4), avg of
+    # the two launches.  The kernel is fused with the entropy coder's front end and writes 16 B per block instead
+    # of 128 B of coefficients, so its real DRAM traffic (roofline.traffic, ncu) is far below this figure.
+    "fdct_quant": (4.5 + 9.0) / 2,
+    # entropy coding proper: 16 B of block meta in (0.25 B/sample: 0.375 / 0.75 B/px) + the stream out (~0.28 B/px)
+    "huff_encode": (0.375 + 0.75) / 2 + 0.28,
 }
 DATA_KERNELS = ("gainmap_pass1", "gainmap_affine", "fdct_quant", "huff_encode", "yuv_convert")
 
@@ -269,6 +273,9 @@ def bench_b200(args, rank, world):
     affinity = bind_to_gpu_numa_node(nvh, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        every = [None] * world
+        dist.all_gather_object(every, affinity)
+        affinity = every   # one entry per rank
     so = os.path.join(ROOT, "libultrahdr_b200", "libuhdr_b200.so")
     if not os.path.exists(so):
         G.build()
