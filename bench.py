@@ -426,6 +426,42 @@ def bench_b200(args, rank, world):
     for d in decs:
         lib.uhdr_release_decoder(d)
 
+    # what the link itself gives on this box: plain pinned<->device copies of 256 MB, CUDA events
+    def pcie_probe():
+        try:
+            n = 256 << 20
+            hbuf = torch.empty(n, dtype=torch.uint8).pin_memory()
+            dbuf = torch.empty(n, dtype=torch.uint8, device="cuda")
+            res = {}
+            for name, (dst, src) in (("h2d_gbs", (dbuf, hbuf)), ("d2h_gbs", (hbuf, dbuf))):
+                for _ in range(2):
+                    dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    dst.copy_(src, non_blocking=True)
+                b.record()
+                torch.cuda.synchronize()
+                res[name] = round(5 * n / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+            return res
+        except Exception as e:  # noqa: BLE001
+            return {"error": repr(e)}
+    # every rank probes its own link AT THE SAME TIME (barrier first), so that the N-GPU end-to-end number can
+    # be read against what the host (sockets' DRAM, PCIe root complexes) gives N GPUs together
+    barrier()
+    pcie = pcie_probe()
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, pcie)
+        pcie = {"concurrent_per_rank": every,
+                "h2d_gbs_sum": round(sum(e.get("h2d_gbs", 0.0) for e in every), 1),
+                "d2h_gbs_sum": round(sum(e.get("d2h_gbs", 0.0) for e in every), 1)}
+        barrier()
+        solo = pcie_probe() if rank == 0 else None     # rank 0 alone, the other ranks idle at the next barrier
+        barrier()
+        pcie["rank0_alone"] = solo
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -461,28 +497,6 @@ def bench_b200(args, rank, world):
     extra = extra_measurements(lib, api, hbm) if world == 1 else {"note": "side measurements run at N=1 only"}
 
     # ---------------- CPU baseline: the reference's own code on this box's host cores --------------
-    # what the link itself gives on this box: plain pinned<->device copies of 256 MB, CUDA events
-    def pcie_probe():
-        try:
-            n = 256 << 20
-            hbuf = torch.empty(n, dtype=torch.uint8).pin_memory()
-            dbuf = torch.empty(n, dtype=torch.uint8, device="cuda")
-            res = {}
-            for name, (dst, src) in (("h2d_gbs", (dbuf, hbuf)), ("d2h_gbs", (hbuf, dbuf))):
-                for _ in range(2):
-                    dst.copy_(src, non_blocking=True)
-                torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(5):
-                    dst.copy_(src, non_blocking=True)
-                b.record()
-                torch.cuda.synchronize()
-                res[name] = round(5 * n / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
-            return res
-        except Exception as e:  # noqa: BLE001
-            return {"error": repr(e)}
-    pcie = pcie_probe() if rank == 0 else {}
 
     # reference on the host: all cores of the box (the GPU arm's NUMA binding is lifted for it), one
     # frame per concurrent call, the same concurrency rule as `--impl reference`
@@ -508,7 +522,11 @@ def bench_b200(args, rank, world):
                              "per-kernel times from CUDA events on the launching streams"},
         "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": int(in_bytes),
                 "d2h_bytes_per_step": int(sum(e2e_out)), "ms_per_step": round(t_e2e / args.steps * 1e3, 3),
-                "h2d_achieved_gbs": round(in_bytes / (t_e2e / args.steps) / 1e9, 1), "pcie_probe": pcie,
+                "h2d_achieved_gbs": round(world * in_bytes / (t_e2e / args.steps) / 1e9, 1),
+                "h2d_achieved_gbs_per_gpu": round(in_bytes / (t_e2e / args.steps) / 1e9, 1), "pcie_probe": pcie,
+                "frac_of_concurrent_h2d_probe": (round(world * in_bytes / (t_e2e / args.steps) / 1e9 / pcie["h2d_gbs_sum"], 3)
+                                                 if world > 1 and pcie.get("h2d_gbs_sum") else
+                                                 (round(in_bytes / (t_e2e / args.steps) / 1e9 / pcie["h2d_gbs"], 3) if pcie.get("h2d_gbs") else None)),
                 "bound": "pcie h2d: 37.3 MB of raw pixels enter per 4K frame, 2.3 MB of JPEG/R leave"},
         "decode": {"metric": "MPix/s decode 8K JPEG/R -> RGBA half float", "e2e": {"value": round(dec_value, 1), "unit": "MPix/s",
                    "h2d_bytes_per_image": len(data8), "d2h_bytes_per_image": W8K * H8K * 8,
@@ -614,7 +632,7 @@ def extra_measurements(lib, api, hbm):
             h8, s8, _k8 = frame_descs(p8, y8, w, h)
             data = api.encode(h8, s8)
 
-            def timed_decode(L, n, data=data, w=w):
+            def timed_decode(L, n, data=data, w=w, sdr_out=False):
                 buf = np.frombuffer(data, np.uint8).copy()
                 ci = A.CompressedImage(buf.ctypes.data, len(data), len(data), -1, -1, -1)
                 ts = []
@@ -622,6 +640,11 @@ def extra_measurements(lib, api, hbm):
                     dec = C.c_void_p(L.uhdr_create_decoder())
                     t0 = time.perf_counter()
                     assert L.uhdr_dec_set_image(dec, C.byref(ci)).error_code == 0
+                    if sdr_out:   # the decoder's UHDR_CT_SRGB leg: base image only, 32bppRGBA8888
+                        L.uhdr_dec_set_out_img_format.restype = A.ErrorInfo
+                        L.uhdr_dec_set_out_color_transfer.restype = A.ErrorInfo
+                        assert L.uhdr_dec_set_out_img_format(dec, A.FMT_RGBA8888).error_code == 0
+                        assert L.uhdr_dec_set_out_color_transfer(dec, A.CT_SRGB).error_code == 0
                     e = L.uhdr_decode(dec)
                     assert e.error_code == 0, e.detail
                     assert L.uhdr_get_decoded_image(dec).contents.w == w
@@ -640,6 +663,9 @@ def extra_measurements(lib, api, hbm):
                                             "relaxation_rounds_last": int(st1[2])},
                         "note": "uhdr_dec_set_image + uhdr_decode + uhdr_get_decoded_image through the C ABI, best of 6; "
                                 "output 64bppRGBAHalfFloat in handle-owned pinned memory"}
+            dts, meds = timed_decode(lib, 4, sdr_out=True)
+            out[key]["sdr_output_ct_srgb_rgba8888"] = {"ms": round(dts * 1e3, 2), "ms_median": round(meds * 1e3, 2),
+                                                       "mpix_s": round(w * h / 1e6 / dts, 1), "d2h_bytes": w * h * 4}
             # several decoder handles in flight, one host thread each, every handle reused through
             # uhdr_reset_decoder (its arenas stay sized): stream in / pixels out of different images overlap
             nthr, per = 4, 6
@@ -683,17 +709,26 @@ def extra_measurements(lib, api, hbm):
         p010, yuv = make_frame(W4K, H4K, 11)
         sdr, _ks = A.yuv420_image(yuv, W4K, H4K, A.CG_BT709)
         lib.uhdr_b200_set_kernel_timing(1)
-        sweep = {}
-        for ct_name, ct in (("hlg", A.CT_HLG), ("pq", A.CT_PQ)):
-            for cg_name, cg in (("bt709", A.CG_BT709), ("p3", A.CG_P3), ("bt2100", A.CG_BT2100)):
-                hdr, _kh = A.p010_image(p010, W4K, H4K, cg, ct, A.CR_LIMITED)
-                gpu.generate(sdr, hdr)
-                kernel_report(lib)
-                for _ in range(3):
-                    gpu.generate(sdr, hdr)
-                kt = kernel_report(lib)
-                ms = sum(kt[k][1] / kt[k][0] for k in ("gainmap_pass1", "gainmap_affine") if k in kt)
-                sweep[ct_name + "_" + cg_name] = {"kernels_ms": round(ms, 4), "mpix_s": round(MPIX_4K / (ms * 1e-3), 1)}
+        def sweep_over(cfg, names):
+            res = {}
+            for ct_name, ct in (("hlg", A.CT_HLG), ("pq", A.CT_PQ), ("srgb", A.CT_SRGB)):
+                for cg_name, cg in (("bt709", A.CG_BT709), ("p3", A.CG_P3), ("bt2100", A.CG_BT2100)):
+                    hdr, _kh = A.p010_image(p010, W4K, H4K, cg, ct, A.CR_LIMITED)
+                    gpu.generate(sdr, hdr, cfg)
+                    kernel_report(lib)
+                    for _ in range(3):
+                        gpu.generate(sdr, hdr, cfg)
+                    kt = kernel_report(lib)
+                    ms = sum(kt[k][1] / kt[k][0] for k in names if k in kt)
+                    res[ct_name + "_" + cg_name] = {"kernels_ms": round(ms, 4), "mpix_s": round(MPIX_4K / (ms * 1e-3), 1)}
+            return res
+        # sRGB: not an encoder input (uhdr_enc_set_raw_image refuses it) but a valid JpegR::generateGainMap transfer
+        sweep = sweep_over(None, ("gainmap_pass1", "gainmap_affine"))
+        # JpegR's own defaults (ultrahdrcommon.h:450-457): map scale 4, one channel; both presets
+        out["config5_generate_gainmap_4k_scale4_1ch_twopass"] = sweep_over(
+            A.default_gm_config(scale_factor=4, multichannel=0, preset=1), ("gainmap_pass1", "gainmap_affine"))
+        out["config5_generate_gainmap_4k_scale4_1ch_realtime"] = sweep_over(
+            A.default_gm_config(scale_factor=4, multichannel=0, preset=0), ("gainmap_onepass",))
         lib.uhdr_b200_set_kernel_timing(0)
         out["config5_generate_gainmap_4k"] = sweep
     except Exception as e:  # noqa: BLE001

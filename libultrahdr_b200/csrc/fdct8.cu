@@ -4,10 +4,12 @@
 //           bank-padded shared-memory tile
 //   pass 2: lane (b, c) reads column c, runs the 1-D DCT, quantises with the exact reciprocal
 //           (floor(a/d) == umulhi(a, ceil(2^32/d)) while a*d < 2^32), scatters the 8 coefficients
-//           to their (zigzag) positions in the tile
-//   store : lane (b, j) writes 16 bytes; a warp writes 4 blocks = 512 contiguous bytes
-// A warp owns 4 horizontally adjacent blocks, a CTA 32; all planes of an image go in ONE launch
-// (grid.z), the three components of an RGB888 gain map are produced from one read of the pixels.
+//           to their (zigzag) positions
+//   k_fdct8 (coefficient output): lane (b, j) writes 16 bytes; a warp writes 4 blocks = 512 contiguous bytes
+//   k_fdct8_code (device entropy coder follows): the quantised blocks stay in shared memory, one LANE per
+//           block turns them into finished AC bit strings (see code_block_lane)
+// All planes of an image go in ONE launch, the three components of an RGB888 gain map are produced
+// from one read of the pixels.
 // Arithmetic is libjpeg-turbo's jccolor.c / jfdctint.c / jcdctmgr.c integer arithmetic: bit-exact.
 #include <cstring>
 #include <mutex>
@@ -61,138 +63,110 @@ __device__ __forceinline__ int unzig_rt(int n) { return kUnzigTab[n]; }
 
 constexpr int kTileStride = 72;  // ints per block tile: 64 + 8 padding (4 blocks of a warp on distinct banks)
 
-// Entropy-coder front end (jchuff.c encode_one_block), run while the quantised block is still in the
-// warp's shared-memory tile (zigzag order).  Per block it leaves
+// Entropy-coder front end (jchuff.c encode_one_block).  Per block it leaves
 //   * "meta", one uint4: x = number of code bits of its AC part (run/size Huffman codes, magnitude
 //     bits, a ZRL per 16 zeros, EOB unless coefficient 63 is non-zero) << 16 | the DC value; y, z, w =
 //     the first 96 bits of the AC part's finished bit string (EOB included), MSB first;
 //   * bit strings longer than 96 bits: all their words in the block's slot.
 // huffman.cu then only prepends the DC code (which needs the neighbouring block) and concatenates bit
 // strings; coefficients are never stored for the device path.
-// Step 1, lane j of the block's 8 lanes takes zigzag positions j, j+8, ... (the few non-zeros of a
-// typical block sit at the lowest positions: they spread over the lanes): code word of each non-zero
-// coefficient -> ent[rank].  Step 2, lane j takes entries j, j+8, ...: prefix sum of the lengths over
-// the 8 lanes -> bit offset -> OR into the block's bit-string image.
-__device__ __forceinline__ void bs_place(uint32_t* bs, unsigned off, unsigned long long pat, unsigned plen) {
-  const unsigned long long v = pat << (64 - plen);  // left aligned
-  const unsigned A = (unsigned)(v >> 32), B = (unsigned)v;
-  const unsigned w = off >> 5, sh = off & 31;
-  const unsigned x0 = A >> sh;
-  const unsigned x1 = sh ? (A << (32 - sh)) | (B >> sh) : B;
-  const unsigned x2 = sh ? B << (32 - sh) : 0u;
-  if (x0) atomicOr(bs + w, x0);
-  if (x1) atomicOr(bs + w + 1, x1);
-  if (x2) atomicOr(bs + w + 2, x2);
+// One LANE codes one block, 32 blocks of a warp at a time: the transform needs 8 lanes per block, but a
+// typical block has a handful of non-zero coefficients, and cooperating lanes spend their instructions on
+// shuffles and on work that is uniform over the group.  So a warp first transforms and quantises 32 blocks
+// (8 rounds of 4) into a staging area (zigzag order, 16 bit, 144-byte pitch: the 128-bit reads of the mask
+// scan are conflict free), then every lane walks the non-zero mask of its own block and shifts code words
+// into a 64-bit register; the trip count of a warp is the largest non-zero count of its 32 blocks.
+constexpr int kStagePitch = 72;   // int16 per staged block
+
+struct BitSink {
+  unsigned long long acc = 0;   // low `nacc` bits pending
+  unsigned nacc = 0, w = 0, bits = 0, c0 = 0, c1 = 0, c2 = 0;
+  uint32_t* slot;               // global: the block's 64-word slot (null: dead block)
+  __device__ __forceinline__ void emit(unsigned word) {
+    if (w == 0) c0 = word;
+    else if (w == 1) c1 = word;
+    else if (w == 2) c2 = word;
+    else if (slot) slot[w] = word;
+    w++;
+  }
+  __device__ __forceinline__ void put(unsigned code, unsigned len) {   // len <= 26
+    acc = (acc << len) | code;
+    nacc += len;
+    bits += len;
+    if (nacc >= 32) {
+      nacc -= 32;
+      emit((unsigned)(acc >> nacc));
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (nacc) emit((unsigned)(acc << (32 - nacc)));
+    if (bits > 96 && slot) { slot[0] = c0; slot[1] = c1; slot[2] = c2; }
+  }
+};
+
+__device__ __forceinline__ void code_block_lane(const int16_t* t16, const uint32_t* acb, uint32_t* slot, uint4* meta_out) {
+  auto nz2 = [](unsigned w) { return ((w & 0xffffu) ? 1u : 0u) | ((w >> 16) ? 2u : 0u); };
+  unsigned lo = 0, hi = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint4 q = *(const uint4*)(t16 + 8 * j);
+    const unsigned m8 = nz2(q.x) | (nz2(q.y) << 2) | (nz2(q.z) << 4) | (nz2(q.w) << 6);
+    if (j < 4) lo |= m8 << (8 * j);
+    else hi |= m8 << (8 * (j - 4));
+  }
+  BitSink S;
+  S.slot = slot;
+  const unsigned zrl = acb[0xF0] & 0xff, zcode = acb[0xF0] >> 8;
+  int prev = 0;
+  unsigned long long m = (((unsigned long long)hi << 32) | lo) & ~1ull;
+  while (m) {
+    const int k = __ffsll((long long)m) - 1;
+    m &= m - 1;
+    int run = k - prev - 1;
+    prev = k;
+    while (run >= 16) {
+      S.put(zcode, zrl);
+      run -= 16;
+    }
+    const int v = t16[k];
+    const int nb = 32 - __clz(abs(v));
+    const uint32_t e = acb[(run << 4) | nb];
+    const unsigned low = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
+    S.put(((e >> 8) << nb) | low, (e & 0xff) + nb);
+  }
+  if (!(hi >> 31)) S.put(acb[0] >> 8, acb[0] & 0xff);
+  S.finish();
+  if (meta_out) *meta_out = make_uint4((S.bits << 16) | ((unsigned)(int)t16[0] & 0xffffu), S.c0, S.c1, S.c2);
 }
 
-constexpr int kBsWords = 56;  // bit-string image per block: 63 x 26 bits = 52 words at most, padded to whole uint4
-
-__device__ __forceinline__ void block_code(const int16_t* t16, const uint4 q, int lane_r, const uint32_t* acb, uint32_t* ent,
-                                           uint32_t* bs, uint32_t* gout_words, uint4* meta_out) {
-  auto nz2 = [](unsigned w) { return ((w & 0xffffu) ? 1u : 0u) | ((w >> 16) ? 2u : 0u); };
-  const unsigned m8 = nz2(q.x) | (nz2(q.y) << 2) | (nz2(q.z) << 4) | (nz2(q.w) << 6);  // positions 8r .. 8r+7
-  unsigned lo = lane_r < 4 ? m8 << (8 * lane_r) : 0u, hi = lane_r >= 4 ? m8 << (8 * (lane_r - 4)) : 0u;
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {  // OR over the 8 lanes of the block (aligned group: xor stays inside)
-    lo |= __shfl_xor_sync(0xffffffffu, lo, o);
-    hi |= __shfl_xor_sync(0xffffffffu, hi, o);
-  }
-  const unsigned long long mask = ((unsigned long long)hi << 32) | lo;
-  const unsigned long long anchored = mask | 1ull;  // runs are counted from the DC position
-  const unsigned long long mask_ac = mask & ~1ull;
-  unsigned bits = 0;
-  const unsigned zrl = acb[0xF0] & 0xff, zcode = acb[0xF0] >> 8;
-  // step 1: code words.  entry = [24:0] Huffman code followed by the magnitude bits (bit 25 of a 26-bit
-  // word is always 1: only the 16-bit codes, which all start with a one, can reach 26 bits), [29:25] its
-  // length, [31:30] the number of ZRL codes in front of it
-#pragma unroll
-  for (int half = 0; half < 2; half++) {
-    unsigned mj = ((half ? hi : lo) >> lane_r) & 0x01010101u;
-    if (half == 0 && lane_r == 0) mj &= ~1u;  // the DC coefficient is not part of the AC code
-    while (mj) {
-      const int k = lane_r + (__ffs(mj) - 1) + 32 * half;
-      mj &= mj - 1;
-      const unsigned long long below = (1ull << k) - 1ull;
-      const int prev = 63 - __clzll((long long)(anchored & below));
-      const int run = k - prev - 1;
-      const int v = t16[k];
-      const int nb = 32 - __clz(abs(v));
-      const uint32_t e = acb[((run & 15) << 4) | nb];
-      const unsigned low = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
-      const unsigned len = (e & 0xff) + nb;
-      bits += len + (run >> 4) * zrl;
-      ent[__popcll(mask_ac & below)] = ((((e >> 8) << nb) | low) & 0x1ffffffu) | (len << 25) | ((unsigned)(run >> 4) << 30);
-    }
-  }
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
-  const bool eob = !(hi >> 31);
-  if (eob) bits += acb[0] & 0xff;
-  // step 2: bit string.  Items = the entries plus, if needed, EOB.  Strings of up to 96 bits (nearly all
-  // blocks of natural images) are assembled in three registers per lane and ORed over the 8 lanes; they
-  // travel inside the meta word.  Longer strings are built in the shared-memory image and go to the slot.
-  const int n = __popcll(mask_ac);
-  const int items = n + (eob ? 1 : 0);
-  int imax = items;  // rounds are warp-uniform (shuffles): the longest of the warp's 4 blocks decides
-  imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, 8));
-  imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, 16));
-  const unsigned nw = (bits + 31) >> 5;
-  const bool longb = bits > 96;
-  if (longb)
-    for (unsigned w = lane_r; w < nw; w += 8) bs[w] = 0;
+// transform + quantise the block whose row this lane holds; the quantised block goes to `st` (16 bit,
+// zigzag order) -- the staging entry of the device-coder kernel
+__device__ __forceinline__ void block_to_stage(int d[8], int* tile, int lane_b, int lane_r, const unsigned* sdiv,
+                                               const unsigned* smag, const uint8_t* sunzig, int16_t* st) {
+  dct1d<0>(d);
+  int* t = tile + lane_b * kTileStride;
+  *(int4*)(t + lane_r * 8) = make_int4(d[0], d[1], d[2], d[3]);
+  *(int4*)(t + lane_r * 8 + 4) = make_int4(d[4], d[5], d[6], d[7]);
   __syncwarp();
-  const unsigned eob_ent = ((acb[0] >> 8) & 0x1ffffffu) | ((acb[0] & 0xff) << 25);
-  unsigned base = 0, c0 = 0, c1 = 0, c2 = 0;
-  for (int t = 0; t * 8 < imax; t++) {
-    const int idx = t * 8 + lane_r;
-    const unsigned e = idx < n ? ent[idx] : (idx == n && eob ? eob_ent : 0u);
-    const unsigned zr = e >> 30, len = (e >> 25) & 31u;
-    const unsigned tl = len + zr * zrl;
-    unsigned incl = tl;
+  const int c = lane_r;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      const unsigned y = __shfl_up_sync(0xffffffffu, incl, o, 8);
-      if (lane_r >= o) incl += y;
-    }
-    const unsigned off = base + incl - tl;
-    base += __shfl_sync(0xffffffffu, incl, 7, 8);
-    if (tl) {
-      unsigned long long pat = (e & 0x1ffffffu) | (len == 26 ? 1u << 25 : 0u);
-      for (unsigned z = 0; z < zr; z++) pat |= (unsigned long long)zcode << (len + z * zrl);
-      if (longb) {
-        bs_place(bs, off, pat, tl);
-      } else {
-        const unsigned long long v = pat << (64 - tl);  // left aligned
-        const unsigned A = (unsigned)(v >> 32), B = (unsigned)v;
-        const unsigned w = off >> 5, sh = off & 31;
-        const unsigned x0 = A >> sh;
-        const unsigned x1 = sh ? (A << (32 - sh)) | (B >> sh) : B;
-        const unsigned x2 = sh ? B << (32 - sh) : 0u;
-        if (w == 0) { c0 |= x0; c1 |= x1; c2 |= x2; }
-        else if (w == 1) { c1 |= x0; c2 |= x1; }
-        else c2 |= x0;
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    c0 |= __shfl_xor_sync(0xffffffffu, c0, o);
-    c1 |= __shfl_xor_sync(0xffffffffu, c1, o);
-    c2 |= __shfl_xor_sync(0xffffffffu, c2, o);
-  }
+  for (int k = 0; k < 8; k++) d[k] = t[k * 8 + c];
+  dct1d<1>(d);
   __syncwarp();
-  if (longb) {
-    c0 = bs[0]; c1 = bs[1]; c2 = bs[2];
-    if (gout_words)  // 16 bytes per lane and round; the tail of the last vector is don't-care
-      for (unsigned w4 = 4 * lane_r; w4 < nw; w4 += 32) *(uint4*)(gout_words + w4) = *(const uint4*)(bs + w4);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int n = k * 8 + c;
+    const unsigned dv = sdiv[n];
+    const unsigned a = (unsigned)abs(d[k]) + (dv >> 1);
+    int q = (int)__umulhi(a, smag[n]);
+    q = d[k] < 0 ? -q : q;
+    st[sunzig[n]] = (int16_t)q;
   }
-  if (lane_r == 0 && meta_out) *meta_out = make_uint4((bits << 16) | ((unsigned)(int)t16[0] & 0xffffu), c0, c1, c2);
 }
 
 template <bool ZIGZAG>
 __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int lane_r, const unsigned* sdiv,
-                                            const unsigned* smag, const uint8_t* sunzig, int16_t* gout_block_base,
-                                            const uint32_t* acb, uint32_t* ent, uint32_t* bs, uint4* meta_out) {
+                                            const unsigned* smag, const uint8_t* sunzig, int16_t* gout_block_base) {
   // pass 1 on this lane's row, park it
   dct1d<0>(d);
   int* t = tile + lane_b * kTileStride;
@@ -220,29 +194,67 @@ __device__ __forceinline__ void block_stage(int d[8], int* tile, int lane_b, int
   __syncwarp();
   // 16 bytes per lane: coefficients [8*lane_r, 8*lane_r + 8) of block lane_b
   const uint4 q = *(const uint4*)(t16 + lane_r * 8);
-  if (ZIGZAG) {
-    // device entropy coder follows: the AC bit string instead of coefficients (all 32 lanes take part in
-    // the shuffles; dead lanes store nothing).  The block's slot holds 64 words.
-    block_code(t16, q, lane_r, acb, ent + lane_b * 64, bs + lane_b * kBsWords,
-               gout_block_base ? reinterpret_cast<uint32_t*>(gout_block_base) : nullptr, meta_out);
-  } else if (gout_block_base) {
-    *(uint4*)(gout_block_base + lane_r * 8) = q;
-  }
+  if (gout_block_base) *(uint4*)(gout_block_base + lane_r * 8) = q;
   __syncwarp();
 }
 
+// row `lane_r` of block (by, bx) of a plane, level shifted; rows past the plane: the encoder helper's pad row
+// (jpegencoderhelper.cpp:254-296)
+__device__ __forceinline__ void load_plane_row(const Fdct8Plane& pl, int by, int bx, int lane_r, int d[8]) {
+  const int y = by * 8 + lane_r;
+  if (y >= pl.h) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) d[k] = pl.fill - 128;
+  } else {
+    const uint2 v = __ldg((const uint2*)(pl.src + (size_t)y * pl.stride + bx * 8));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      d[k] = (int)((v.x >> (8 * k)) & 0xff) - 128;
+      d[4 + k] = (int)((v.y >> (8 * k)) & 0xff) - 128;
+    }
+  }
+}
+// RGB888: libjpeg's scanline path replicates the last column / row (jcsample.c, jcprepct.c)
+__device__ __forceinline__ void load_rgb_row(const Fdct8Plane& pl, int by, int bx, int lane_r, int r[8], int g[8], int b[8]) {
+  const int y = min(by * 8 + lane_r, pl.h - 1);
+  const uint8_t* row = pl.src + (size_t)y * pl.stride * 3;
+  if (bx * 8 + 8 <= pl.w) {
+    const uint2* p = (const uint2*)(row + (size_t)bx * 24);
+    const uint2 a = __ldg(p), bb = __ldg(p + 1), cc = __ldg(p + 2);
+    const unsigned w[6] = {a.x, a.y, bb.x, bb.y, cc.x, cc.y};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int o = 3 * k;
+      r[k] = (w[o >> 2] >> (8 * (o & 3))) & 0xff;
+      g[k] = (w[(o + 1) >> 2] >> (8 * ((o + 1) & 3))) & 0xff;
+      b[k] = (w[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 0xff;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint8_t* px = row + (size_t)min(bx * 8 + k, pl.w - 1) * 3;
+      r[k] = __ldg(px); g[k] = __ldg(px + 1); b[k] = __ldg(px + 2);
+    }
+  }
+}
+template <int COMP>
+__device__ __forceinline__ void rgb_to_ycc_row(const int r[8], const int g[8], const int b[8], int d[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; k++) {  // jccolor.c rgb_ycc_convert, SCALEBITS 16
+    int v;
+    if (COMP == 0) v = (19595 * r[k] + 38470 * g[k] + 7471 * b[k] + 32768) >> 16;
+    else if (COMP == 1) v = (-11059 * r[k] - 21709 * g[k] + 32768 * b[k] + (128 << 16) + 32767) >> 16;
+    else v = (32768 * r[k] - 27439 * g[k] - 5329 * b[k] + (128 << 16) + 32767) >> 16;
+    d[k] = v - 128;
+  }
+}
+
+// coefficient output (natural order: the parity hook and the host entropy coder's input; zigzag order on request)
 template <bool ZIGZAG>
 __global__ void __launch_bounds__(256, 4) k_fdct8(const Fdct8Params P) {
   __shared__ unsigned sdiv[2][64], smag[2][64];
   __shared__ int tiles[8][4 * kTileStride];
   __shared__ uint8_t sunzig[64];
-  __shared__ uint32_t sacb[ZIGZAG ? 2 : 1][ZIGZAG ? 256 : 1];       // AC code books (code << 8 | length)
-  __shared__ uint32_t sent[ZIGZAG ? 8 : 1][ZIGZAG ? 4 * 64 : 1];      // per warp: code-word entries of its 4 blocks
-  __shared__ __align__(16) uint32_t sbs[ZIGZAG ? 8 : 1][ZIGZAG ? 4 * kBsWords : 4];  // per warp: their bit-string images
-  if (ZIGZAG) {
-    sacb[0][threadIdx.x] = __ldg(P.acbooks + threadIdx.x);
-    sacb[1][threadIdx.x] = __ldg(P.acbooks + 256 + threadIdx.x);
-  }
   if (threadIdx.x >= 128 && threadIdx.x < 192) sunzig[threadIdx.x - 128] = (uint8_t)unzig_rt(threadIdx.x - 128);
   if (threadIdx.x < 128) {
     const int t = threadIdx.x >> 6, i = threadIdx.x & 63;
@@ -256,72 +268,109 @@ __global__ void __launch_bounds__(256, 4) k_fdct8(const Fdct8Params P) {
   // persistent CTAs: tiles of 32 horizontally adjacent blocks, all planes in one flat index space
 #pragma unroll 1
   for (int tidx = blockIdx.x; tidx < total_tiles; tidx += gridDim.x) {
-  const int pi = tidx < P.tile_end[0] ? 0 : (tidx < P.tile_end[1] ? 1 : 2);
-  const Fdct8Plane& pl = P.plane[pi];
-  const int local = tidx - (pi ? P.tile_end[pi - 1] : 0);
-  const int tiles_x = (pl.wblocks + 31) >> 5;
-  const int by = local / tiles_x, tx = local - by * tiles_x;
-  const int bx = tx * 32 + warp * 4 + lane_b;
-  const bool live = bx < pl.wblocks;
-  const int bxc = live ? bx : pl.wblocks - 1;  // dead lanes compute on a valid block, store nothing
-  int* tile = tiles[warp];
-  int d[8];
-  if (!pl.rgb) {
-    int y = by * 8 + lane_r;
-    if (y >= pl.h) {  // rows past the plane: the encoder helper's pad row (jpegencoderhelper.cpp:254-296)
-#pragma unroll
-      for (int k = 0; k < 8; k++) d[k] = pl.fill - 128;
-    } else {
-      const uint2 v = __ldg((const uint2*)(pl.src + (size_t)y * pl.stride + bxc * 8));
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        d[k] = (int)((v.x >> (8 * k)) & 0xff) - 128;
-        d[4 + k] = (int)((v.y >> (8 * k)) & 0xff) - 128;
-      }
-    }
+    const int pi = tidx < P.tile_end[0] ? 0 : (tidx < P.tile_end[1] ? 1 : 2);
+    const Fdct8Plane& pl = P.plane[pi];
+    const int local = tidx - (pi ? P.tile_end[pi - 1] : 0);
+    const int tiles_x = (pl.wblocks + 31) >> 5;
+    const int by = local / tiles_x, tx = local - by * tiles_x;
+    const int bx = tx * 32 + warp * 4 + lane_b;
+    const bool live = bx < pl.wblocks;
+    const int bxc = live ? bx : pl.wblocks - 1;  // dead lanes compute on a valid block, store nothing
+    int* tile = tiles[warp];
     const size_t bidx = (size_t)by * pl.wblocks + bx;
-    int16_t* out = live ? pl.coefs[0] + bidx * (ZIGZAG ? 128 : 64) : nullptr;
-    block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, out, sacb[ZIGZAG ? pl.hsel[0] : 0],
-                        sent[ZIGZAG ? warp : 0], sbs[ZIGZAG ? warp : 0], live && pl.meta[0] ? pl.meta[0] + bidx : nullptr);
-  } else {
-    // RGB888: libjpeg's scanline path replicates the last column / row (jcsample.c, jcprepct.c)
-    const int y = min(by * 8 + lane_r, pl.h - 1);
-    const uint8_t* row = pl.src + (size_t)y * pl.stride * 3;
-    int r[8], g[8], b[8];
-    if (bxc * 8 + 8 <= pl.w) {
-      const uint2* p = (const uint2*)(row + (size_t)bxc * 24);
-      const uint2 a = __ldg(p), bb = __ldg(p + 1), cc = __ldg(p + 2);
-      const unsigned w[6] = {a.x, a.y, bb.x, bb.y, cc.x, cc.y};
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int o = 3 * k;
-        r[k] = (w[o >> 2] >> (8 * (o & 3))) & 0xff;
-        g[k] = (w[(o + 1) >> 2] >> (8 * ((o + 1) & 3))) & 0xff;
-        b[k] = (w[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 0xff;
-      }
+    int d[8];
+    if (!pl.rgb) {
+      load_plane_row(pl, by, bxc, lane_r, d);
+      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, live ? pl.coefs[0] + bidx * 64 : nullptr);
     } else {
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const uint8_t* px = row + (size_t)min(bxc * 8 + k, pl.w - 1) * 3;
-        r[k] = __ldg(px); g[k] = __ldg(px + 1); b[k] = __ldg(px + 2);
-      }
-    }
-#pragma unroll
-    for (int comp = 0; comp < 3; comp++) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) {  // jccolor.c rgb_ycc_convert, SCALEBITS 16
-        int v;
-        if (comp == 0) v = (19595 * r[k] + 38470 * g[k] + 7471 * b[k] + 32768) >> 16;
-        else if (comp == 1) v = (-11059 * r[k] - 21709 * g[k] + 32768 * b[k] + (128 << 16) + 32767) >> 16;
-        else v = (32768 * r[k] - 27439 * g[k] - 5329 * b[k] + (128 << 16) + 32767) >> 16;
-        d[k] = v - 128;
-      }
-      const size_t bidx = (size_t)by * pl.wblocks + bx;
-      int16_t* out = live ? pl.coefs[comp] + bidx * (ZIGZAG ? 128 : 64) : nullptr;
-      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[comp]], smag[pl.tq[comp]], sunzig, out, sacb[ZIGZAG ? pl.hsel[comp] : 0],
-                          sent[ZIGZAG ? warp : 0], sbs[ZIGZAG ? warp : 0], live && pl.meta[comp] ? pl.meta[comp] + bidx : nullptr);
+      int r[8], g[8], b[8];
+      load_rgb_row(pl, by, bxc, lane_r, r, g, b);
+      rgb_to_ycc_row<0>(r, g, b, d);
+      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[0]], smag[pl.tq[0]], sunzig, live ? pl.coefs[0] + bidx * 64 : nullptr);
+      rgb_to_ycc_row<1>(r, g, b, d);
+      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[1]], smag[pl.tq[1]], sunzig, live ? pl.coefs[1] + bidx * 64 : nullptr);
+      rgb_to_ycc_row<2>(r, g, b, d);
+      block_stage<ZIGZAG>(d, tile, lane_b, lane_r, sdiv[pl.tq[2]], smag[pl.tq[2]], sunzig, live ? pl.coefs[2] + bidx * 64 : nullptr);
     }
   }
+}
+
+// device entropy coder follows: per block the AC bit string (meta word, long strings in the slot) instead of
+// coefficients.  Work item of a WARP = 32 consecutive blocks (raster order) of a plane, or 8 consecutive
+// pixel blocks x 3 components of an RGB888 image (24 of the 32 lanes code).
+struct CodeSmem {
+  unsigned sdiv[2][64], smag[2][64];
+  uint32_t acb[2][256];                 // AC code books (code << 8 | length)
+  int tiles[8][4 * kTileStride];
+  alignas(16) int16_t stage[8][32 * kStagePitch];
+  uint8_t unzig[64];
+};
+
+__global__ void __launch_bounds__(256, 4) k_fdct8_code(const __grid_constant__ Fdct8Params P) {
+  extern __shared__ uint4 smem_u4[];
+  CodeSmem& S = *reinterpret_cast<CodeSmem*>(smem_u4);
+  S.acb[0][threadIdx.x] = __ldg(P.acbooks + threadIdx.x);
+  S.acb[1][threadIdx.x] = __ldg(P.acbooks + 256 + threadIdx.x);
+  if (threadIdx.x >= 128 && threadIdx.x < 192) S.unzig[threadIdx.x - 128] = (uint8_t)unzig_rt(threadIdx.x - 128);
+  if (threadIdx.x < 128) {
+    const int t = threadIdx.x >> 6, i = threadIdx.x & 63;
+    S.sdiv[t][i] = (unsigned)P.q[t][i] << 3;
+    S.smag[t][i] = P.mag[t][i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane_b = lane >> 3, lane_r = lane & 7;
+  const int total_items = P.tile_end[P.nplanes - 1];
+  int* tile = S.tiles[warp];
+  int16_t* stage = S.stage[warp];
+#pragma unroll 1
+  for (int it = blockIdx.x * 8 + warp; it < total_items; it += gridDim.x * 8) {
+    const int pi = it < P.tile_end[0] ? 0 : (it < P.tile_end[1] ? 1 : 2);
+    const Fdct8Plane& pl = P.plane[pi];
+    const int local = it - (pi ? P.tile_end[pi - 1] : 0);
+    const int nb = pl.wblocks * pl.hblocks;
+    int d[8];
+    if (!pl.rgb) {
+      const int base = local * 32;
+#pragma unroll 1
+      for (int s = 0; s < 8; s++) {
+        const int f = min(base + s * 4 + lane_b, nb - 1);   // past the end: a valid block, nothing stored later
+        const int by = f / pl.wblocks, bx = f - by * pl.wblocks;
+        load_plane_row(pl, by, bx, lane_r, d);
+        block_to_stage(d, tile, lane_b, lane_r, S.sdiv[pl.tq[0]], S.smag[pl.tq[0]], S.unzig, stage + (s * 4 + lane_b) * kStagePitch);
+      }
+      __syncwarp();
+      const int f = base + lane;
+      const bool live = f < nb;
+      code_block_lane(stage + lane * kStagePitch, S.acb[pl.hsel[0]], live ? reinterpret_cast<uint32_t*>(pl.coefs[0] + (size_t)f * 128) : nullptr,
+                      live && pl.meta[0] ? pl.meta[0] + f : nullptr);
+      __syncwarp();
+    } else {
+      const int base = local * 8;
+#pragma unroll 1
+      for (int s = 0; s < 2; s++) {
+        const int f = min(base + s * 4 + lane_b, nb - 1);
+        const int by = f / pl.wblocks, bx = f - by * pl.wblocks;
+        int r[8], g[8], b[8];
+        load_rgb_row(pl, by, bx, lane_r, r, g, b);
+        int16_t* st = stage + (s * 12 + lane_b) * kStagePitch;
+        rgb_to_ycc_row<0>(r, g, b, d);
+        block_to_stage(d, tile, lane_b, lane_r, S.sdiv[pl.tq[0]], S.smag[pl.tq[0]], S.unzig, st);
+        rgb_to_ycc_row<1>(r, g, b, d);
+        block_to_stage(d, tile, lane_b, lane_r, S.sdiv[pl.tq[1]], S.smag[pl.tq[1]], S.unzig, st + 4 * kStagePitch);
+        rgb_to_ycc_row<2>(r, g, b, d);
+        block_to_stage(d, tile, lane_b, lane_r, S.sdiv[pl.tq[2]], S.smag[pl.tq[2]], S.unzig, st + 8 * kStagePitch);
+      }
+      __syncwarp();
+      if (lane < 24) {
+        const int s = lane / 12, comp = (lane - s * 12) >> 2;
+        const int f = base + s * 4 + (lane & 3);
+        const bool live = f < nb;
+        code_block_lane(stage + lane * kStagePitch, S.acb[pl.hsel[comp]],
+                        live ? reinterpret_cast<uint32_t*>(pl.coefs[comp] + (size_t)f * 128) : nullptr, live && pl.meta[comp] ? pl.meta[comp] + f : nullptr);
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -353,7 +402,8 @@ static int fdct_device_books(const uint32_t** out) {
 cudaError_t launch_fdct8(const Fdct8Params& Pin, cudaStream_t s) {
   count_launches(1);
   Fdct8Params P = Pin;
-  if (P.zigzag) {
+  const bool code = P.zigzag != 0;   // zigzag launches feed the device entropy coder
+  if (code) {
     int rc = fdct_device_books(&P.acbooks);
     if (rc) return cudaErrorUnknown;
   }
@@ -364,24 +414,44 @@ cudaError_t launch_fdct8(const Fdct8Params& Pin, cudaStream_t s) {
     }
   int total = 0;
   for (int i = 0; i < 3; i++) {
-    if (i < P.nplanes) total += ((P.plane[i].wblocks + 31) / 32) * P.plane[i].hblocks;
+    if (i < P.nplanes) {
+      const Fdct8Plane& pl = P.plane[i];
+      if (code) {
+        if (pl.wblocks > 0 && pl.hblocks > 0) {
+          const int per = pl.rgb ? 8 : 32;   // blocks of the plane per warp item
+          total += (pl.wblocks * pl.hblocks + per - 1) / per;
+        }
+      } else {
+        total += ((pl.wblocks + 31) / 32) * pl.hblocks;
+      }
+    }
     P.tile_end[i] = total;
   }
   if (total == 0) return cudaSuccess;
-  static int resident_tab[2] = {0, 0};  // CTAs of one wave, per instantiation
-  int& resident = resident_tab[P.zigzag ? 1 : 0];
+  static int resident_tab[2] = {0, 0};  // CTAs of one wave, per kernel
+  int& resident = resident_tab[code ? 1 : 0];
   if (!resident) {
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const cudaError_t oe = P.zigzag ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fdct8<true>, 256, 0)
-                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fdct8<false>, 256, 0);
+    cudaError_t oe;
+    if (code) {
+      cudaFuncSetAttribute(k_fdct8_code, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CodeSmem));
+      oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fdct8_code, 256, sizeof(CodeSmem));
+    } else {
+      oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fdct8<false>, 256, 0);
+    }
     if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
     resident = per_sm * (sms > 0 ? sms : 148);
   }
-  const int ctas = total < resident ? total : resident;
-  if (P.zigzag) k_fdct8<true><<<ctas, 256, 0, s>>>(P);
-  else k_fdct8<false><<<ctas, 256, 0, s>>>(P);
+  if (code) {
+    const int need = (total + 7) / 8;
+    const int ctas = need < resident ? need : resident;
+    k_fdct8_code<<<ctas, 256, sizeof(CodeSmem), s>>>(P);
+  } else {
+    const int ctas = total < resident ? total : resident;
+    k_fdct8<false><<<ctas, 256, 0, s>>>(P);
+  }
   return cudaGetLastError();
 }
 

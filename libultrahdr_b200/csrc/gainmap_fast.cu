@@ -1,6 +1,6 @@
-// generateGainMap fast path (jpegr.cpp:753-817 one-pass, :866-931 pass 1 of two-pass) for the
-// configuration the API-0/API-1 benchmarks exercise: P010 HDR intent (HLG or PQ) + YUV 4:2:0 SDR
-// intent, map scale 1.  Arithmetic, operand order and tables are those of the generic kernels in
+// generateGainMap fast path (jpegr.cpp:753-817 one-pass, :866-931 pass 1 of two-pass) for P010 HDR intent
+// (HLG or PQ) + YUV 4:2:0 SDR intent: map scale 1 (the configuration the API-0/API-1 benchmarks exercise,
+// k_gainmap_fast) and map scales 2 / 4 (JpegR's own default is 4, k_gainmap_scaled further down).  Arithmetic, operand order and tables are those of the generic kernels in
 // kernels.cu; what changes is the instruction count:
 //   * persistent CTAs, 256x8-pixel tiles handed out through an atomic ticket; one thread = a 4x2
 //     pixel tile (chroma terms of both images computed once per 2x2)
@@ -96,6 +96,37 @@ __device__ __forceinline__ float fetch_off(const float* t, unsigned mant) {  // 
   return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(t) + (mant & 0x7ffffc));
 }
 
+// order-independent min / max reduction of a CTA into the pass-1 keys (same as k_gainmap_pass1)
+template <int NCH>
+__device__ __forceinline__ void reduce_minmax(const float mn[3], const float mx[3], unsigned* __restrict__ minmax, int tid, int nt) {
+  __shared__ unsigned s_mn[3][8], s_mx[3][8];
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    unsigned a = __float_as_uint(mn[c]), b = __float_as_uint(mx[c]);
+    a = (a & 0x80000000u) ? ~a : (a | 0x80000000u);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    for (int o = 16; o; o >>= 1) {
+      a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (lane == 0) { s_mn[c][warp] = a; s_mx[c][warp] = b; }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = nt >> 5;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      unsigned a = lane < nw ? s_mn[c][lane] : 0xffffffffu, b = lane < nw ? s_mx[c][lane] : 0u;
+      for (int o = 4; o; o >>= 1) {
+        a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+      }
+      if (lane == 0) { atomicMin(minmax + c, a); atomicMax(minmax + 3 + c, b); }
+    }
+  }
+}
+
 template <bool ONEPASS, int NCH, int GAMUT /*0 none, 1 on sdr, 2 on hdr*/, bool LIMITED>
 __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g, const int tiles_x,
                                                          const int ntiles, unsigned* __restrict__ sched, const unsigned long long nz) {
@@ -105,14 +136,18 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
   for (int i = tid; i < 128; i += nt) sm.log2tab[i] = make_double2(log2tab_g[i], log2tab_g[128 + i]);
   for (int i = tid; i < 2048; i += nt) sm.srgb2[i] = __ldg(p.luts + kLutSrgbInv + min((i + 1) >> 1, 1023));
-  const float* hsrc = p.luts + (p.hdr_ct == CT_HLG ? kLutHlgInvOotf : kLutPqInv);
-  for (int i = tid; i < 8192; i += nt) sm.hdr2[i] = __ldg(hsrc + min((i + 1) >> 1, 4095));
+  // hdr inverse OETF table: 4096 entries for HLG (OOTF folded in) / PQ, the 1024-entry sRGB one for an sRGB
+  // "hdr" intent (reachable through JpegR::generateGainMap, getInverseOetfFn gainmapmath.cpp:1175-1180)
+  const int hN = p.hdr_ct == CT_SRGB ? 1024 : 4096;
+  const float* hsrc = p.luts + (p.hdr_ct == CT_HLG ? kLutHlgInvOotf : (p.hdr_ct == CT_PQ ? kLutPqInv : kLutSrgbInv));
+  for (int i = tid; i < 2 * hN; i += nt) sm.hdr2[i] = __ldg(hsrc + min((i + 1) >> 1, hN - 1));
+  const float hscale8 = (float)(8 * (hN - 1));
   // persistent CTAs; 256x8-pixel tiles handed out through a ticket counter (zeroed by the caller)
   if (tid == 0) s_tile[0] = (int)atomicAdd(sched, 1u);
   __syncthreads();
 
   float mn[3] = {127.0f, 127.0f, 127.0f}, mx[3] = {-128.0f, -128.0f, -128.0f};
-  const V2 k8184 = bc(8184.0f), k32760 = bc(32760.0f), keps = bc(1e-7f);
+  const V2 k8184 = bc(8184.0f), k32760 = bc(hscale8), keps = bc(1e-7f);
   const V2 snits = bc(p.sdr_nits), hnits = bc(p.hdr_nits);
 #pragma unroll 1
   for (int it = 0;; it++) {
@@ -264,35 +299,130 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
     }
     __syncthreads();
   }
-  if (!ONEPASS) {
-    // same order-independent reduction as k_gainmap_pass1
-    __shared__ unsigned s_mn[3][8], s_mx[3][8];
-    const int lane = tid & 31, warp = tid >> 5;
+  if (!ONEPASS) reduce_minmax<NCH>(mn, mx, p.minmax, tid, nt);
+}
+
+// ---- map scale 2 / 4 (the reference's JpegR default is scale 4, one channel, ultrahdrcommon.h:450-457) ----
+// samplePixels (gainmapmath.cpp:494-504): the S x S source pixels of a map pixel are fetched as normalised
+// YUV floats, summed in raster order (three sequential chains, starting from 0) and divided by S*S; the rest
+// of the pixel is the scale-1 arithmetic once per map pixel.  The sampling is the work here (16 source
+// pixels of each image per map pixel at S = 4): one thread = one map pixel, each source row arrives with
+// one load per plane (8 / 8 / 4 / 2 / 2 bytes at S = 4), the adds stay in the reference's order.
+template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, int S>
+__global__ void __launch_bounds__(256) k_gainmap_scaled(const GainmapGenParams p, const double* __restrict__ log2tab_g) {
+  extern __shared__ double2 smem_d[];
+  GmSmem& sm = *reinterpret_cast<GmSmem*>(smem_d);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  for (int i = tid; i < 128; i += nt) sm.log2tab[i] = make_double2(log2tab_g[i], log2tab_g[128 + i]);
+  for (int i = tid; i < 2048; i += nt) sm.srgb2[i] = __ldg(p.luts + kLutSrgbInv + min((i + 1) >> 1, 1023));
+  // hdr inverse OETF table: 4096 entries for HLG (OOTF folded in) / PQ, the 1024-entry sRGB one for an sRGB
+  // "hdr" intent (reachable through JpegR::generateGainMap, getInverseOetfFn gainmapmath.cpp:1175-1180)
+  const int hN = p.hdr_ct == CT_SRGB ? 1024 : 4096;
+  const float* hsrc = p.luts + (p.hdr_ct == CT_HLG ? kLutHlgInvOotf : (p.hdr_ct == CT_PQ ? kLutPqInv : kLutSrgbInv));
+  for (int i = tid; i < 2 * hN; i += nt) sm.hdr2[i] = __ldg(hsrc + min((i + 1) >> 1, hN - 1));
+  const float hscale8 = (float)(8 * (hN - 1));
+  __syncthreads();
+  float mn[3] = {127.0f, 127.0f, 127.0f}, mx[3] = {-128.0f, -128.0f, -128.0f};
+  const int tiles_x = (p.map_w + 63) / 64, ntiles = tiles_x * ((p.map_h + 3) / 4);
+#pragma unroll 1
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int x = tx * 64 + threadIdx.x, y = ty * 4 + threadIdx.y;
+    if (x >= p.map_w || y >= p.map_h) continue;
+    // ---- sampling
+    float sy = 0.f, su = 0.f, sv = 0.f, hy = 0.f, hu = 0.f, hv = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < S; dy++) {
+      const int yy = y * S + dy;
+      unsigned long long hyw, huvw;   // S luma words of 16 bit, S/2 chroma pairs
+      unsigned syw, suw, svw;
+      const uint16_t* hyp = (const uint16_t*)p.hdr.p[0] + (size_t)yy * p.hdr.stride[0] + x * S;
+      const uint16_t* hcp = (const uint16_t*)p.hdr.p[1] + (size_t)(yy >> 1) * p.hdr.stride[1] + x * S;
+      const uint8_t* syp = (const uint8_t*)p.sdr.p[0] + (size_t)yy * p.sdr.stride[0] + x * S;
+      const uint8_t* sup = (const uint8_t*)p.sdr.p[1] + (size_t)(yy >> 1) * p.sdr.stride[1] + x * (S / 2);
+      const uint8_t* svp = (const uint8_t*)p.sdr.p[2] + (size_t)(yy >> 1) * p.sdr.stride[2] + x * (S / 2);
+      if (S == 4) {
+        const uint2 a = __ldg((const uint2*)hyp), b = __ldg((const uint2*)hcp);
+        hyw = ((unsigned long long)a.y << 32) | a.x;
+        huvw = ((unsigned long long)b.y << 32) | b.x;
+        syw = __ldg((const unsigned*)syp);
+        suw = __ldg((const uint16_t*)sup);
+        svw = __ldg((const uint16_t*)svp);
+      } else {
+        hyw = __ldg((const unsigned*)hyp);
+        huvw = __ldg((const unsigned*)hcp);
+        syw = __ldg((const uint16_t*)syp);
+        suw = __ldg(sup);
+        svw = __ldg(svp);
+      }
+#pragma unroll
+      for (int dx = 0; dx < S; dx++) {
+        // getYuv420Pixel (gainmapmath.cpp:354-372)
+        sy += (float)((syw >> (8 * dx)) & 0xff) * (1 / 255.0f);
+        su += (float)((int)((suw >> (8 * (dx >> 1))) & 0xff) - 128) * (1 / 255.0f);
+        sv += (float)((int)((svw >> (8 * (dx >> 1))) & 0xff) - 128) * (1 / 255.0f);
+        // getP010Pixel (:412-445)
+        const int y10 = (int)((hyw >> (16 * dx + 6)) & 0x3ff);
+        const int u10 = (int)((huvw >> (32 * (dx >> 1) + 6)) & 0x3ff), v10 = (int)((huvw >> (32 * (dx >> 1) + 22)) & 0x3ff);
+        if (LIMITED) {
+          hy += (float)(y10 - 64) * (1 / 876.0f);
+          hu += (float)(u10 - 64) * (1 / 896.0f) - 0.5f;
+          hv += (float)(v10 - 64) * (1 / 896.0f) - 0.5f;
+        } else {
+          hy += (float)y10 / 1023.0f;
+          hu += (float)u10 / 1023.0f - 0.5f;
+          hv += (float)v10 / 1023.0f - 0.5f;
+        }
+      }
+    }
+    const float inv = 1.0f / (float)(S * S);   // a power of two: the product equals the reference's quotient
+    sy *= inv; su *= inv; sv *= inv; hy *= inv; hu *= inv; hv *= inv;
+    // ---- yuvToRgb -> inverse OETF tables [-> gamut] -> clipNegatives: the scale-1 expressions on scalars
+    float sr = fetch2(sm.srgb2, __saturatef(sy + p.sdr_y2r[0] * sv), 8184.0f);
+    float sg = fetch2(sm.srgb2, __saturatef((sy - p.sdr_y2r[2] * su) - p.sdr_y2r[3] * sv), 8184.0f);
+    float sb = fetch2(sm.srgb2, __saturatef(sy + p.sdr_y2r[1] * su), 8184.0f);
+    float hr = fetch2(sm.hdr2, __saturatef(hy + p.hdr_y2r[0] * hv), hscale8);
+    float hg = fetch2(sm.hdr2, __saturatef((hy - p.hdr_y2r[2] * hu) - p.hdr_y2r[3] * hv), hscale8);
+    float hb = fetch2(sm.hdr2, __saturatef(hy + p.hdr_y2r[1] * hu), hscale8);
+    if (GAMUT != 0) {
+      float& xr = GAMUT == 1 ? sr : hr;
+      float& xg = GAMUT == 1 ? sg : hg;
+      float& xb = GAMUT == 1 ? sb : hb;
+      const float a = (p.gamut[0] * xr + p.gamut[1] * xg) + p.gamut[2] * xb;
+      const float b = (p.gamut[3] * xr + p.gamut[4] * xg) + p.gamut[5] * xb;
+      const float c = (p.gamut[6] * xr + p.gamut[7] * xg) + p.gamut[8] * xb;
+      xr = fmaxf(a, 0.0f); xg = fmaxf(b, 0.0f); xb = fmaxf(c, 0.0f);
+    }
+    float s3[3], h3[3];
+    if (NCH == 3) {
+      s3[0] = sr * p.sdr_nits; s3[1] = sg * p.sdr_nits; s3[2] = sb * p.sdr_nits;
+      h3[0] = hr * p.hdr_nits; h3[1] = hg * p.hdr_nits; h3[2] = hb * p.hdr_nits;
+    } else if (p.use_luminance) {
+      s3[0] = ((p.lum[0] * sr + p.lum[1] * sg) + p.lum[2] * sb) * p.sdr_nits;
+      h3[0] = ((p.lum[0] * hr + p.lum[1] * hg) + p.lum[2] * hb) * p.hdr_nits;
+    } else {
+      s3[0] = fmaxf(sr, fmaxf(sg, sb)) * p.sdr_nits;
+      h3[0] = fmaxf(hr, fmaxf(hg, hb)) * p.hdr_nits;
+    }
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
-      unsigned a = __float_as_uint(mn[c]), b = __float_as_uint(mx[c]);
-      a = (a & 0x80000000u) ? ~a : (a | 0x80000000u);
-      b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-      for (int o = 16; o; o >>= 1) {
-        a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
-        b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
-      }
-      if (lane == 0) { s_mn[c][warp] = a; s_mx[c][warp] = b; }
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int nw = nt >> 5;
-#pragma unroll
-      for (int c = 0; c < NCH; c++) {
-        unsigned a = lane < nw ? s_mn[c][lane] : 0xffffffffu, b = lane < nw ? s_mx[c][lane] : 0u;
-        for (int o = 4; o; o >>= 1) {
-          a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
-          b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
-        }
-        if (lane == 0) { atomicMin(p.minmax + c, a); atomicMax(p.minmax + 3 + c, b); }
+      if (ONEPASS) {   // encodeGain gainmapmath.cpp:758-771, gamma 1
+        float gain = 1.0f;
+        if (s3[c] > 0.0f) gain = div_pos(h3[c], s3[c]);
+        if (gain < p.min_boost) gain = p.min_boost;
+        if (gain > p.max_boost) gain = p.max_boost;
+        const float gn = (float)((log2_core(gain, sm.log2tab) - (double)p.log2_min) / (double)(p.log2_max - p.log2_min));
+        p.dst[((size_t)y * p.dst_stride + x) * NCH + c] = (uint8_t)((unsigned)__float2int_rz(gn * 255.0f) & 0xff);
+      } else {         // computeGain :773-782
+        float g = (float)log2_core(div_pos(h3[c] + 1e-7f, s3[c] + 1e-7f), sm.log2tab);
+        if (s3[c] < 2.f / 255.0f) g = fminf(g, 2.3f);
+        p.gains[((size_t)y * p.map_w + x) * NCH + c] = g;
+        mn[c] = fminf(mn[c], g);
+        mx[c] = fmaxf(mx[c], g);
       }
     }
   }
+  if (!ONEPASS) reduce_minmax<NCH>(mn, mx, p.minmax, tid, nt);
 }
 
 // ---- pass 2 (jpegr.cpp:988-1013, affineMapGain gainmapmath.cpp:784-789), gamma 1, tight rows ------
@@ -460,8 +590,32 @@ cudaError_t launch_kernel(const GainmapGenParams& p, const FastLaunch& L) {
   fn<<<ctas, dim3(64, 4), L.smem, L.s>>>(p, L.tab, L.tiles_x, L.ntiles, L.sched, kNegZero2);
   return cudaGetLastError();
 }
+template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, int S>
+cudaError_t launch_scaled(const GainmapGenParams& p, const FastLaunch& L) {
+  static int resident[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto fn = k_gainmap_scaled<ONEPASS, NCH, GAMUT, LIMITED, S>;
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!resident[dev]) {
+    int per_sm = 0, sms = 0;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, L.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    resident[dev] = per_sm * (sms > 0 ? sms : 148);
+  }
+  const int ntiles = ((p.map_w + 63) / 64) * ((p.map_h + 3) / 4);
+  const int ctas = resident[dev] < ntiles ? resident[dev] : ntiles;
+  count_launches(1);
+  fn<<<ctas, dim3(64, 4), L.smem, L.s>>>(p, L.tab);
+  return cudaGetLastError();
+}
 template <bool ONEPASS, int NCH, int GAMUT>
 cudaError_t launch_range(const GainmapGenParams& p, const FastLaunch& L) {
+  if (p.scale == 4)
+    return p.hdr.full_range ? launch_scaled<ONEPASS, NCH, GAMUT, false, 4>(p, L) : launch_scaled<ONEPASS, NCH, GAMUT, true, 4>(p, L);
+  if (p.scale == 2)
+    return p.hdr.full_range ? launch_scaled<ONEPASS, NCH, GAMUT, false, 2>(p, L) : launch_scaled<ONEPASS, NCH, GAMUT, true, 2>(p, L);
   return p.hdr.full_range ? launch_kernel<ONEPASS, NCH, GAMUT, false>(p, L) : launch_kernel<ONEPASS, NCH, GAMUT, true>(p, L);
 }
 template <bool ONEPASS, int NCH>
@@ -503,8 +657,21 @@ cudaError_t launch_yuv420_fast(const YuvConvParams& p, cudaStream_t s) {
 }
 
 bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass) {
-  if (p.hdr.fmt != F_P010 || p.sdr.fmt != F_YUV420 || p.scale != 1) return false;
-  if (p.hdr_ct != CT_HLG && p.hdr_ct != CT_PQ) return false;
+  if (p.hdr.fmt != F_P010 || p.sdr.fmt != F_YUV420) return false;
+  if (p.hdr_ct != CT_HLG && p.hdr_ct != CT_PQ && p.hdr_ct != CT_SRGB) return false;
+  if (p.scale == 2 || p.scale == 4) {
+    // k_gainmap_scaled: one load per source row and plane -> S luma samples / S/2 chroma pairs must be aligned
+    const int S = p.scale;
+    if (p.map_w != p.hdr.w / S || p.map_h != p.hdr.h / S || p.map_w < 1 || p.map_h < 1) return false;
+    if (p.sdr.w < p.map_w * S || p.sdr.h < p.map_h * S) return false;
+    const size_t am = (size_t)S * 2 - 1;   // bytes of a P010 row fragment - 1
+    if ((p.hdr.stride[0] * 2 & am) || (p.hdr.stride[1] * 2 & am) || ((size_t)p.hdr.p[0] & am) || ((size_t)p.hdr.p[1] & am)) return false;
+    if ((p.sdr.stride[0] & (S - 1)) || ((size_t)p.sdr.p[0] & (S - 1))) return false;
+    if ((p.sdr.stride[1] & (S / 2 - 1)) || (p.sdr.stride[2] & (S / 2 - 1)) || ((size_t)p.sdr.p[1] & (S / 2 - 1)) || ((size_t)p.sdr.p[2] & (S / 2 - 1))) return false;
+    if (onepass) return p.gamma == 1.0f;
+    return true;
+  }
+  if (p.scale != 1) return false;
   if ((p.map_w & 3) || (p.map_h & 1) || p.map_w != p.hdr.w || p.map_h != p.hdr.h) return false;
   if ((p.hdr.stride[0] & 3) || (p.hdr.stride[1] & 3) || (p.sdr.stride[0] & 3) || (p.sdr.stride[1] & 1) || (p.sdr.stride[2] & 1)) return false;
   if (((size_t)p.hdr.p[0] & 7) || ((size_t)p.hdr.p[1] & 7) || ((size_t)p.sdr.p[0] & 3) || ((size_t)p.sdr.p[1] & 1) || ((size_t)p.sdr.p[2] & 1)) return false;

@@ -53,6 +53,21 @@ def test_generate_matrix(gpu, checker):
     assert not bad, bad[:10]
 
 
+def test_generate_srgb_transfer_leg(gpu, checker):
+    """config 5's sRGB leg: an sRGB-transfer P010 "hdr" intent is refused by uhdr_enc_set_raw_image but is a
+    valid JpegR::generateGainMap input (getInverseOetfFn, gainmapmath.cpp:1175-1180)."""
+    bad = []
+    for hcg, scg, multi, scale, preset in itertools.product([0, 1, 2], [0, 2], [0, 1], [1, 2, 4], [0, 1]):
+        hdr, k1 = _hdr("noise", "p010", hcg, A.CT_SRGB)
+        sdr, k2 = _sdr("noise", scg)
+        cfg = A.default_gm_config(scale_factor=scale, multichannel=multi, preset=preset)
+        g1, m1 = gpu.generate(sdr, hdr, cfg)
+        g2, m2 = checker.generate(sdr, hdr, cfg)
+        if not ((g1 == g2).all() and T.md_equal(m1, m2)):
+            bad.append((hcg, scg, multi, scale, preset, int((g1 != g2).sum())))
+    assert not bad, bad[:10]
+
+
 @pytest.mark.parametrize("fmt,ct", [("p010full", A.CT_HLG), ("1010102", A.CT_PQ), ("1010102", A.CT_HLG),
                                     ("f16", A.CT_LINEAR)])
 @pytest.mark.parametrize("multi,preset", [(1, 1), (1, 0), (0, 1), (0, 0)])
@@ -238,6 +253,23 @@ def test_api1_stages_full_size(gpu, checker, w, h):
     a = gpu.convert_yuv(sb, w, h, 0, 1)
     b = checker.convert_yuv(sb, w, h, 0, 1)
     assert (a == b).all()
+
+
+@pytest.mark.parametrize("w,h,scale,multi,preset", [(3840, 2160, 4, 0, 0), (3840, 2160, 4, 0, 1), (3840, 2160, 4, 1, 1),
+                                                    (1920, 1080, 2, 1, 1), (1920, 1080, 2, 0, 0), (1284, 724, 4, 0, 1)])
+def test_generate_scaled_full_size(gpu, checker, w, h, scale, multi, preset):
+    """JpegR's own defaults (map scale 4, one channel, ultrahdrcommon.h:450-457) and scale 2 at full
+    size: k_gainmap_scaled against the reference's samplePixels path, bit exact."""
+    hb = T.make_p010(w, h, "noise")
+    sb = T.make_yuv420(w, h, "noise")
+    hdr, k1 = A.p010_image(hb, w, h, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+    sdr, k2 = A.yuv420_image(sb, w, h, A.CG_BT709)
+    cfg = A.default_gm_config(scale_factor=scale, multichannel=multi, preset=preset)
+    g1, m1 = gpu.generate(sdr, hdr, cfg)
+    g2, m2 = checker.generate(sdr, hdr, cfg)
+    assert g1.shape == g2.shape == (h // scale, w // scale, 3 if multi else 1) or g1.shape == g2.shape
+    assert T.md_equal(m1, m2), (m1.as_dict(), m2.as_dict())
+    assert (g1 == g2).all(), int((g1 != g2).sum())
 
 
 def test_apply_8k(gpu, checker):
