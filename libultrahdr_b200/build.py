@@ -63,9 +63,14 @@ def build(force=False, verbose=False):
         ok &= p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-lcudart", "-lpthread"])
-    with open(STAMP, "w") as f:
+    # link next to the target and swap it in atomically: a snapshot of the tree (gpurun) taken during a build sees
+    # either the previous library or the new one, never a half-written file
+    tmp = OUT + ".link"
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs + ["-lcudart", "-lpthread"])
+    os.replace(tmp, OUT)
+    with open(STAMP + ".tmp", "w") as f:
         f.write(source_digest())
+    os.replace(STAMP + ".tmp", STAMP)
     return OUT
 
 

@@ -67,10 +67,11 @@ uhdr_error_info_t from_rc(int rc) {
 }
 
 struct Encoder : uhdr_codec_private {
-  std::map<int, DevImage> raw;         // UHDR_HDR_IMG / UHDR_SDR_IMG, device resident
-  std::map<int, int> quality;
-  struct Compressed { std::vector<uint8_t> bytes; int cg, ct, range; };
-  std::map<int, Compressed> compressed;  // UHDR_SDR_IMG / UHDR_BASE_IMG / UHDR_GAIN_MAP_IMG (encode API-2/3/4)
+  // keyed by uhdr_img_label_t (0..3); fixed slots: configuring / resetting a handle does not touch the heap
+  SlotMap<DevImage, 4> raw;            // UHDR_HDR_IMG / UHDR_SDR_IMG, device resident
+  SlotMap<int, 4> quality;
+  struct Compressed { std::vector<uint8_t> bytes; int cg = 0, ct = 0, range = 0; };
+  SlotMap<Compressed, 4> compressed;   // UHDR_SDR_IMG / UHDR_BASE_IMG / UHDR_GAIN_MAP_IMG (encode API-2/3/4)
   uhdr_gainmap_metadata_t metadata{};
   std::vector<uint8_t> exif;
   int scale = 1, multichannel = 1, preset = UHDR_USAGE_BEST_QUALITY, output_format = UHDR_CODEC_JPG;
@@ -82,7 +83,7 @@ struct Encoder : uhdr_codec_private {
   uhdr_error_info_t status = ok();
   void defaults() {
     raw.clear();
-    compressed.clear();
+    compressed.clear([](Compressed& c) { c.bytes.clear(); });   // keeps the capacity
     memset(&metadata, 0, sizeof metadata);
     quality.clear();
     quality[UHDR_BASE_IMG] = 95;
@@ -230,10 +231,9 @@ static uhdr_error_info_t set_compressed(uhdr_codec_private_t* enc, uhdr_compress
   if (n < 0) return err(UHDR_CODEC_INVALID_PARAM, "received bad/corrupted jpeg image as part of input configuration");
   if (n == 0) return err(UHDR_CODEC_INVALID_PARAM, "compressed image received as part of input config contains no valid jpeg images");
   // several images: the first one is taken, the rest ignored (:572-584)
-  Encoder::Compressed c;
+  Encoder::Compressed& c = h->compressed[intent];   // the slot's buffer is reused across resets
   c.bytes.assign((const uint8_t*)img->data + off, (const uint8_t*)img->data + off + len);
   c.cg = img->cg; c.ct = img->ct; c.range = img->range;
-  h->compressed[intent] = std::move(c);
   return ok();
 }
 UHDR_API uhdr_error_info_t uhdr_enc_set_compressed_image(uhdr_codec_private_t* enc, uhdr_compressed_image_t* img, uhdr_img_label_t intent) {
@@ -464,7 +464,7 @@ UHDR_API uhdr_error_info_t uhdr_dec_probe(uhdr_codec_private_t* dec) {
   int rc = h->codec.probe(h->stream.data(), h->stream.size(), &h->info);
   h->probe_status = from_rc(rc);
   if (rc == E_OK) {
-    auto blk = [](std::vector<uint8_t>& v, uhdr_mem_block_t* b) { b->data = v.data(); b->data_sz = b->capacity = v.size(); };
+    auto blk = [](const ByteView& v, uhdr_mem_block_t* b) { b->data = const_cast<uint8_t*>(v.data); b->data_sz = b->capacity = v.size; };
     blk(h->info.exif, &h->exif_blk);
     blk(h->info.icc, &h->icc_blk);
     // the compressed base / gain-map images are views into the handle's copy of the stream

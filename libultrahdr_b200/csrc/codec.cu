@@ -10,7 +10,7 @@
 
 namespace uhdr_b200 {
 
-static void grab_marker(const uint8_t* d, const JpegHeader& h, uint8_t id, const char* sig, size_t sig_len, std::vector<uint8_t>* out);
+static ByteView find_marker(const uint8_t* d, const JpegHeader& h, uint8_t id, const char* sig, size_t sig_len);
 
 // ------------------------------------------------------------------------------------------------
 // encode
@@ -81,14 +81,18 @@ int JpegRCodec::encode(const DevImage& hdr, const DevImage* sdr_in, const uhdr_b
   size_t icc_gm_n = 0, icc_base_n = 0;
   const uint8_t* icc_gm = icc_profile(gm.map.ct, gm.map.cg, &icc_gm_n);  // compressGainMap :520-528
   const uint8_t* icc_base = icc_profile(UHDR_CT_SRGB, sdr_cg, &icc_base_n);
-  std::vector<uint8_t> gm_head, base_head, gm_hs, base_hs;
+  // the two JPEG heads are written into the workspace's host arena: no heap on this path
   JpegPieces pg, pb;
-  rc = jpeg_stream_pieces(gm_jpeg, icc_gm, icc_gm_n, jpeg_gainmap_comment(), &gm_head, &gm_hs, &pg.scan, &pg.scan_len);
+  const size_t gm_cap = jpeg_head_capacity(icc_gm_n, jpeg_gainmap_comment()), base_cap = jpeg_head_capacity(icc_base_n, nullptr);
+  uint8_t* gm_head = (uint8_t*)ws_.halloc(gm_cap);
+  uint8_t* base_head = (uint8_t*)ws_.halloc(base_cap);
+  if (!gm_head || !base_head) return E_MEM;
+  rc = jpeg_stream_pieces(gm_jpeg, icc_gm, icc_gm_n, jpeg_gainmap_comment(), gm_head, gm_cap, &pg.head_len, &pg.scan, &pg.scan_len);
   if (rc) return rc;
-  rc = jpeg_stream_pieces(base_jpeg, icc_base, icc_base_n, nullptr, &base_head, &base_hs, &pb.scan, &pb.scan_len);
+  rc = jpeg_stream_pieces(base_jpeg, icc_base, icc_base_n, nullptr, base_head, base_cap, &pb.head_len, &pb.scan, &pb.scan_len);
   if (rc) return rc;
-  pg.head = gm_head.data(); pg.head_len = gm_head.size();
-  pb.head = base_head.data(); pb.head_len = base_head.size();
+  pg.head = gm_head;
+  pb.head = base_head;
   return assemble_jpegr(pb, pg, exif, exif_size, md, out, cap, out_size);
 }
 
@@ -97,17 +101,17 @@ int JpegRCodec::encode_from_compressed(const uint8_t* base, size_t base_size, in
   JpegHeader bh;
   int rc = jpeg_read_header(base, base_size, &bh);  // parseImage :392
   if (rc) return rc;
-  std::vector<uint8_t> blob;
+  ByteView blob;
   if (!md.use_base_cg) {
     JpegHeader gh;
     rc = jpeg_read_header(gainmap, gainmap_size, &gh);
     if (rc) return rc;
-    grab_marker(gainmap, gh, 0xE2, "ICC_PROFILE", 12, &blob);
+    blob = find_marker(gainmap, gh, 0xE2, "ICC_PROFILE", 12);
     if (blob.empty())
       return fail(E_UNSUPPORTED, "For gainmap application space to be alternate image space, gainmap image is expected to "
                   "contain alternate image color space in the form of ICC. The ICC marker in gainmap jpeg is missing.");
   }
-  grab_marker(base, bh, 0xE2, "ICC_PROFILE", 12, &blob);
+  blob = find_marker(base, bh, 0xE2, "ICC_PROFILE", 12);
   const uint8_t* icc = nullptr;
   size_t icc_n = 0;
   if (blob.empty()) {  // add ICC if not already present
@@ -139,10 +143,9 @@ int JpegRCodec::encode_with_compressed_sdr(const DevImage& hdr, const DevImage* 
     JpegHeader h;
     rc = decode_jpeg_dev(ws_, sdr_jpg, sdr_jpg_size, 0, &sdr, &h);
     if (rc) return rc;
-    std::vector<uint8_t> blob;
-    grab_marker(sdr_jpg, h, 0xE2, "ICC_PROFILE", 12, &blob);
+    const ByteView blob = find_marker(sdr_jpg, h, 0xE2, "ICC_PROFILE", 12);
     if (!blob.empty()) {
-      const int cg = icc_read_gamut(blob.data(), blob.size());
+      const int cg = icc_read_gamut(blob.data, blob.size);
       if (cg == UHDR_CG_UNSPECIFIED || (sdr_jpg_cg != UHDR_CG_UNSPECIFIED && sdr_jpg_cg != cg))
         return fail(E_INVALID_PARAM, "configured color gamut %d does not match with color gamut specified in icc box %d", sdr_jpg_cg, cg);
       sdr.cg = cg;
@@ -171,10 +174,13 @@ int JpegRCodec::encode_with_compressed_sdr(const DevImage& hdr, const DevImage* 
   finish_gainmap_metadata(gm, &md);
   size_t icc_gm_n = 0;
   const uint8_t* icc_gm = icc_profile(gm.map.ct, gm.map.cg, &icc_gm_n);
-  std::vector<uint8_t> gm_file;
-  rc = jpeg_finish_stream(gm_jpeg, icc_gm, icc_gm_n, jpeg_gainmap_comment(), &gm_file);
+  const size_t gm_cap = jpeg_head_capacity(icc_gm_n, jpeg_gainmap_comment()) + gm_jpeg.h_scan_bytes[3] + 2;
+  uint8_t* gm_file = (uint8_t*)ws_.halloc(gm_cap);
+  if (!gm_file) return E_MEM;
+  size_t gm_file_n = 0;
+  rc = jpeg_finish_stream_into(gm_jpeg, icc_gm, icc_gm_n, jpeg_gainmap_comment(), gm_file, gm_cap, &gm_file_n);
   if (rc) return rc;
-  return encode_from_compressed(sdr_jpg, sdr_jpg_size, sdr_jpg_cg, gm_file.data(), gm_file.size(), md, out, cap, out_size);
+  return encode_from_compressed(sdr_jpg, sdr_jpg_size, sdr_jpg_cg, gm_file, gm_file_n, md, out, cap, out_size);
 }
 
 int JpegRCodec::encode_host(const uhdr_raw_image_t& hdr, const uhdr_raw_image_t* sdr,
@@ -238,14 +244,53 @@ static int validate_header(const JpegHeader& h) {  // jpegdecoderhelper.cpp:244-
   return E_OK;
 }
 
-static void grab_marker(const uint8_t* d, const JpegHeader& h, uint8_t id, const char* sig, size_t sig_len,
-                        std::vector<uint8_t>* out) {  // jpegdecoderhelper.cpp:119-139
-  out->clear();
+// first marker `id` whose payload starts with `sig`, as a view into the stream (jpegdecoderhelper.cpp:119-139 copies it)
+static ByteView find_marker(const uint8_t* d, const JpegHeader& h, uint8_t id, const char* sig, size_t sig_len) {
+  ByteView v;
   for (const JpegMarker& m : h.markers)
     if (m.id == id && m.length > sig_len && !memcmp(d + m.offset, sig, sig_len)) {
-      out->assign(d + m.offset, d + m.offset + m.length);
-      return;
+      v.data = d + m.offset;
+      v.size = m.length;
+      break;
     }
+  return v;
+}
+
+ParkedThread::~ParkedThread() {
+  if (!th_.joinable()) return;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    quit_ = true;
+  }
+  cv_.notify_all();
+  th_.join();
+}
+void ParkedThread::loop() {
+  std::unique_lock<std::mutex> lk(mu_);
+  for (;;) {
+    cv_.wait(lk, [&] { return quit_ || (busy_ && fn_); });
+    if (quit_) return;
+    void (*fn)(void*) = fn_;
+    void* arg = arg_;
+    fn_ = nullptr;
+    lk.unlock();
+    fn(arg);
+    lk.lock();
+    busy_ = false;
+    cv_.notify_all();
+  }
+}
+void ParkedThread::start(void (*fn)(void*), void* arg) {
+  std::unique_lock<std::mutex> lk(mu_);
+  if (!th_.joinable()) th_ = std::thread([this] { loop(); });
+  fn_ = fn;
+  arg_ = arg;
+  busy_ = true;
+  cv_.notify_all();
+}
+void ParkedThread::wait() {
+  std::unique_lock<std::mutex> lk(mu_);
+  cv_.wait(lk, [&] { return !busy_; });
 }
 
 JpegRCodec::~JpegRCodec() {
@@ -355,12 +400,11 @@ int JpegRCodec::probe(const uint8_t* data, size_t size, DecodedInfo* info) {
   info->gm_height = gh.frame.height;
   info->base_off = po; info->base_len = pl;
   info->gainmap_off = go; info->gainmap_len = gl;
-  grab_marker(data + po, ph, 0xE1, "Exif\0\0", 6, &info->exif);
-  grab_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12, &info->icc);
-  std::vector<uint8_t> iso, xmp;
-  grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &iso);
-  grab_marker(data + go, gh, 0xE1, "http://ns.adobe.com/xap/1.0/", 29, &xmp);
-  rc = parse_gainmap_metadata(iso.data(), iso.size(), xmp.data(), xmp.size(), info->exif.data(), info->exif.size(), &info->metadata);
+  info->exif = find_marker(data + po, ph, 0xE1, "Exif\0\0", 6);   // views into the caller's stream
+  info->icc = find_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12);
+  const ByteView iso = find_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28);
+  const ByteView xmp = find_marker(data + go, gh, 0xE1, "http://ns.adobe.com/xap/1.0/", 29);
+  rc = parse_gainmap_metadata(iso.data, iso.size, xmp.data, xmp.size, info->exif.data, info->exif.size, &info->metadata);
   if (rc) return rc;
   info->has_metadata = true;
   return E_OK;
@@ -380,9 +424,15 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
   const bool want_map = gainmap_out || !sdr_only;  // :1484-1495
   // both images sizeable: the gain-map JPEG goes to a helper thread with its own stream
   const bool overlap = want_map && pl >= (256u << 10) && gl >= (256u << 10);
-  int rc2 = E_OK;
-  std::string err2;
-  std::thread helper;
+  struct MapJob {   // lives on this frame until helper_.wait() below
+    JpegRCodec* self;
+    const uint8_t* data;
+    size_t len;
+    DevImage* map;
+    JpegHeader* gh;
+    int dev, rc;
+    char err[256];
+  } mj{this, data + go, gl, &map, &gh, 0, E_OK, {0}};
   if (overlap) {
     if (!ws2_) {
       ws2_.reset(new Workspace());
@@ -391,46 +441,45 @@ int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt
       CUDA_TRY(cudaEventCreateWithFlags(&map_ready_, cudaEventDisableTiming));
     }
     ws2_->rewind();
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    helper = std::thread([&, dev]() {
-      if (cudaSetDevice(dev) != cudaSuccess) { rc2 = E_ERROR; err2 = "cudaSetDevice failed in the gain-map decode thread"; return; }
-      rc2 = decode_jpeg_dev(*ws2_, data + go, gl, 2, &map, &gh);  // DECODE_STREAM :1486
-      if (rc2) err2 = last_error();
-      else if (cudaEventRecord(map_ready_, ws2_->stream()) != cudaSuccess) { rc2 = E_ERROR; err2 = "cudaEventRecord failed"; }
-    });
+    CUDA_TRY(cudaGetDevice(&mj.dev));
+    helper_.start([](void* a) {
+      MapJob& j = *static_cast<MapJob*>(a);
+      auto fail_with = [&](int rc, const char* what) { j.rc = rc; snprintf(j.err, sizeof j.err, "%s", what); };
+      if (cudaSetDevice(j.dev) != cudaSuccess) return fail_with(E_ERROR, "cudaSetDevice failed in the gain-map decode thread");
+      j.rc = j.self->decode_jpeg_dev(*j.self->ws2_, j.data, j.len, 2, j.map, j.gh);  // DECODE_STREAM :1486
+      if (j.rc) snprintf(j.err, sizeof j.err, "%s", last_error());
+      else if (cudaEventRecord(j.self->map_ready_, j.self->ws2_->stream()) != cudaSuccess) fail_with(E_ERROR, "cudaEventRecord failed");
+    }, &mj);
   }
   rc = decode_jpeg_dev(ws_, data + po, pl, sdr_only ? 1 : 0, &sdr, &ph);  // DECODE_TO_RGB_CS / DECODE_TO_YCBCR_CS
-  if (helper.joinable()) helper.join();
+  if (overlap) helper_.wait();
   if (rc) return rc;
   tr.mark("primary jpeg enqueued");
-  std::vector<uint8_t> blob;
-  grab_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12, &blob);
-  sdr.cg = icc_read_gamut(blob.data(), blob.size());
+  ByteView blob = find_marker(data + po, ph, 0xE2, "ICC_PROFILE", 12);
+  sdr.cg = icc_read_gamut(blob.data, blob.size);
   map_pending_ = false;
   uhdr_gainmap_metadata_t md{};
   if (want_map) {
     if (overlap) {
-      if (rc2) { set_last_error(err2); return rc2; }
+      if (mj.rc) { set_last_error(mj.err); return mj.rc; }
       CUDA_TRY(cudaStreamWaitEvent(ws_.stream(), map_ready_, 0));
       if (kernel_timing_enabled()) ws2_->sync();
     } else {
       rc = decode_jpeg_dev(ws_, data + go, gl, 2, &map, &gh);  // DECODE_STREAM :1486
       if (rc) return rc;
     }
-    grab_marker(data + go, gh, 0xE2, "ICC_PROFILE", 12, &blob);
-    map.cg = icc_read_gamut(blob.data(), blob.size());
+    blob = find_marker(data + go, gh, 0xE2, "ICC_PROFILE", 12);
+    map.cg = icc_read_gamut(blob.data, blob.size);
     tr.mark("gainmap jpeg enqueued");
   }
   if (md_out || !sdr_only) {  // :1497-1518
     // the reference reads the gain-map image's markers only when it decodes that image (:1484-1495):
     // metadata alone with SDR output finds no buffer to parse
     if (!want_map) return fail(E_INVALID_PARAM, "received no valid buffer to parse gainmap metadata");
-    std::vector<uint8_t> xmp, exif;
-    grab_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28, &blob);
-    grab_marker(data + go, gh, 0xE1, "http://ns.adobe.com/xap/1.0/", 29, &xmp);
-    grab_marker(data + po, ph, 0xE1, "Exif\0\0", 6, &exif);
-    rc = parse_gainmap_metadata(blob.data(), blob.size(), xmp.data(), xmp.size(), exif.data(), exif.size(), &md);
+    blob = find_marker(data + go, gh, 0xE2, "urn:iso:std:iso:ts:21496:-1", 28);
+    const ByteView xmp = find_marker(data + go, gh, 0xE1, "http://ns.adobe.com/xap/1.0/", 29);
+    const ByteView exif = find_marker(data + po, ph, 0xE1, "Exif\0\0", 6);
+    rc = parse_gainmap_metadata(blob.data, blob.size, xmp.data, xmp.size, exif.data, exif.size, &md);
     if (rc) return rc;
     if (md_out) *md_out = md;
   }

@@ -2,7 +2,10 @@
 // encodeJPEGR API-0 / API-1 and decodeJPEGR run their pixel and block stages on the device;
 // the marker/container layer is host code.
 #pragma once
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "container.h"
@@ -13,10 +16,27 @@ namespace uhdr_b200 {
 
 struct DecodedInfo {
   int width = 0, height = 0, gm_width = 0, gm_height = 0;
-  std::vector<uint8_t> exif, icc;
+  ByteView exif, icc;   // views into the probed stream (the caller keeps it alive: the C API handle owns a copy)
   size_t base_off = 0, base_len = 0, gainmap_off = 0, gainmap_len = 0;  // the two JPEGs inside the probed stream
   uhdr_gainmap_metadata_t metadata{};
   bool has_metadata = false;
+};
+
+// One parked host thread per codec (spawned on first use, kept until the codec dies): runs the gain-map JPEG of a
+// decode next to the primary one without creating a thread per call.
+class ParkedThread {
+ public:
+  ~ParkedThread();
+  void start(void (*fn)(void*), void* arg);   // fn(arg) on the parked thread
+  void wait();                                // until that call has returned
+ private:
+  void loop();
+  std::thread th_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  void (*fn_)(void*) = nullptr;
+  void* arg_ = nullptr;
+  bool busy_ = false, quit_ = false;
 };
 
 class JpegRCodec {
@@ -67,6 +87,7 @@ class JpegRCodec {
   // second stream + arenas: the gain-map JPEG of a decode is processed by a helper thread while the
   // calling thread handles the primary image (both entropy decoders alternate host and device phases)
   std::unique_ptr<Workspace> ws2_;
+  ParkedThread helper_;
   cudaEvent_t map_ready_ = nullptr;
   bool lazy_gainmap_ = false, map_pending_ = false;
   DevImage last_map_{};

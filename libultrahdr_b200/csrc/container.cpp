@@ -50,8 +50,8 @@ struct Frac {
   uint32_t base_headroom_n, base_headroom_d, alt_headroom_n, alt_headroom_d;
   bool backward, use_base;
 };
-void be16(std::vector<uint8_t>& o, unsigned v) { o.push_back(v >> 8); o.push_back(v & 0xff); }
-void be32(std::vector<uint8_t>& o, uint32_t v) { for (int s = 24; s >= 0; s -= 8) o.push_back((v >> s) & 0xff); }
+void be16(ByteSink& o, unsigned v) { o.u16(v); }
+void be32(ByteSink& o, uint32_t v) { o.u32(v); }
 bool md_single(const uhdr_gainmap_metadata_t& m) {
   auto same = [](const float* a) { return a[0] == a[1] && a[0] == a[2]; };
   return same(m.max_content_boost) && same(m.min_content_boost) && same(m.gamma) && same(m.offset_sdr) && same(m.offset_hdr);
@@ -85,7 +85,7 @@ int validate_metadata(const uhdr_gainmap_metadata_t& m) {  // ultrahdr_api.cpp:4
   return rc;
 }
 
-int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, std::vector<uint8_t>* out) {
+int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size) {
   Frac f;
   memset(&f, 0, sizeof f);
   f.backward = false;
@@ -116,8 +116,7 @@ int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, std::vector<uint8_t>*
   const bool one = ident(f.min_n) && ident(f.min_d) && ident(f.max_n) && ident(f.max_d) && ident(f.gamma_n) &&
                    ident(f.gamma_d) && ident(f.base_off_n) && ident(f.base_off_d) && ident(f.alt_off_n) && ident(f.alt_off_d);
   const int channels = one ? 1 : 3;
-  std::vector<uint8_t>& o = *out;
-  o.clear();
+  ByteSink o(out, cap);
   be16(o, 0);
   be16(o, 0);
   uint8_t flags = 0;
@@ -130,7 +129,7 @@ int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, std::vector<uint8_t>*
     if (f.min_d[c] != denom || f.max_d[c] != denom || f.gamma_d[c] != denom || f.base_off_d[c] != denom || f.alt_off_d[c] != denom)
       common = false;
   if (common) flags |= 8;
-  o.push_back(flags);
+  o.u8(flags);
   if (common) {
     be32(o, denom);
     be32(o, f.base_headroom_n);
@@ -147,6 +146,8 @@ int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, std::vector<uint8_t>*
       be32(o, (uint32_t)f.alt_off_n[c]); be32(o, f.alt_off_d[c]);
     }
   }
+  if (!o.ok()) return fail(E_MEM, "gain map metadata block of %zu bytes does not fit the %zu-byte buffer", o.size(), cap);
+  *out_size = o.size();
   return E_OK;
 }
 
@@ -514,19 +515,20 @@ int icc_read_gamut(const uint8_t* d, size_t n) {
 }
 
 // ---- MPF (multipictureformat.cpp) ---------------------------------------------------------------
-static void make_mpf(size_t primary_size, size_t secondary_size, size_t secondary_offset, std::vector<uint8_t>* o) {
-  o->clear();
+constexpr size_t kMpfBytes = 86;   // MPF signature + TIFF header + index IFD (3 tags) + two 16-byte MP entries
+static void make_mpf(size_t primary_size, size_t secondary_size, size_t secondary_offset, uint8_t out[kMpfBytes]) {
+  ByteSink o(out, kMpfBytes);
   static const uint8_t head[8] = {'M', 'P', 'F', 0, 0x4D, 0x4D, 0x00, 0x2A};
-  o->insert(o->end(), head, head + 8);
-  be32(*o, 8);            // index IFD offset
-  be16(*o, 3);            // tag count
-  be16(*o, 0xB000); be16(*o, 7); be32(*o, 4); o->insert(o->end(), {'0', '1', '0', '0'});
-  be16(*o, 0xB001); be16(*o, 4); be32(*o, 1); be32(*o, 2);
-  be16(*o, 0xB002); be16(*o, 7); be32(*o, 32);
-  be32(*o, (uint32_t)(o->size() - 4 + 4 + 4));  // MP entry offset
-  be32(*o, 0);                                   // attribute IFD offset
-  be32(*o, 0x030000); be32(*o, (uint32_t)primary_size); be32(*o, 0); be16(*o, 0); be16(*o, 0);
-  be32(*o, 0); be32(*o, (uint32_t)secondary_size); be32(*o, (uint32_t)secondary_offset); be16(*o, 0); be16(*o, 0);
+  o.raw(head, 8);
+  be32(o, 8);            // index IFD offset
+  be16(o, 3);            // tag count
+  be16(o, 0xB000); be16(o, 7); be32(o, 4); o.raw("0100", 4);
+  be16(o, 0xB001); be16(o, 4); be32(o, 1); be32(o, 2);
+  be16(o, 0xB002); be16(o, 7); be32(o, 32);
+  be32(o, (uint32_t)(o.size() - 4 + 4 + 4));  // MP entry offset
+  be32(o, 0);                                  // attribute IFD offset
+  be32(o, 0x030000); be32(o, (uint32_t)primary_size); be32(o, 0); be16(o, 0); be16(o, 0);
+  be32(o, 0); be32(o, (uint32_t)secondary_size); be32(o, (uint32_t)secondary_offset); be16(o, 0); be16(o, 0);
 }
 
 int assemble_jpegr(const JpegPieces& base, const JpegPieces& gm, const uint8_t* exif, size_t exif_size,
@@ -534,10 +536,11 @@ int assemble_jpegr(const JpegPieces& base, const JpegPieces& gm, const uint8_t* 
                    const uint8_t* icc_arg, size_t icc_arg_size) {
   static const char kIsoNs[] = "urn:iso:std:iso:ts:21496:-1";  // 27 chars + NUL
   const size_t ns_len = sizeof kIsoNs;
-  std::vector<uint8_t> iso;
-  int rc = iso_encode_metadata(md, &iso);
+  uint8_t iso[kIsoMetadataMaxBytes];   // no heap on this path: fixed-size blocks, everything else goes straight to `out`
+  size_t iso_n = 0;
+  int rc = iso_encode_metadata(md, iso, sizeof iso, &iso_n);
   if (rc) return rc;
-  const size_t iso_secondary_len = 2 + ns_len + iso.size();
+  const size_t iso_secondary_len = 2 + ns_len + iso_n;
   const size_t secondary_size = gm.total() + 2 + iso_secondary_len;
   size_t pos = 0;
   auto put = [&](const void* p, size_t n) {
@@ -600,19 +603,19 @@ int assemble_jpegr(const JpegPieces& base, const JpegPieces& gm, const uint8_t* 
   }
   if (!sos) return fail(E_INVALID_PARAM, "SOS marker not found while reordering base jpeg segments, unable to append gainmap");
   {
-    const size_t mpf_len = 2 + 86;
+    const size_t mpf_len = 2 + kMpfBytes;
     const size_t tail = (bn - sos) + base.scan_len + (base.whole ? 0 : 2);  // SOS header + entropy-coded data + EOI
     const size_t primary_size = pos + 2 + mpf_len + tail;
     const size_t secondary_offset = primary_size - pos - 8;
-    std::vector<uint8_t> mpf;
-    make_mpf(primary_size, secondary_size, secondary_offset, &mpf);
-    W(put_marker(0xE2, mpf.size())); W(put(mpf.data(), mpf.size()));
+    uint8_t mpf[kMpfBytes];
+    make_mpf(primary_size, secondary_size, secondary_offset, mpf);
+    W(put_marker(0xE2, sizeof mpf)); W(put(mpf, sizeof mpf));
   }
   W(put(b + sos, bn - sos));
   if (base.scan_len) W(put(base.scan, base.scan_len));
   if (!base.whole) W(put(eoi, 2));
   W(put(soi, 2));
-  W(put_marker(0xE2, ns_len + iso.size())); W(put(kIsoNs, ns_len)); W(put(iso.data(), iso.size()));
+  W(put_marker(0xE2, ns_len + iso_n)); W(put(kIsoNs, ns_len)); W(put(iso, iso_n));
   W(put(gm.head + 2, gm.head_len - 2));
   if (gm.scan_len) W(put(gm.scan, gm.scan_len));
   if (!gm.whole) W(put(eoi, 2));

@@ -8,13 +8,18 @@
 #include <cstdint>
 #include <vector>
 
+#include "bytes.h"
+
 #include "../../include/ultrahdr_api.h"
 
 namespace uhdr_b200 {
 
 // ISO 21496-1 payload for the gain-map image (gainmapmetadata.cpp:113-193 after
 // gainmapMetadataFloatToFraction :349-425). Returns uhdr_codec_err_t.
-int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, std::vector<uint8_t>* out);
+// Writes into caller storage (no heap): kIsoMetadataMaxBytes always suffices (2+2+1 bytes of versions and flags,
+// 4 header fractions of 8 bytes, 3 channels x 5 fractions of 8 bytes).
+constexpr size_t kIsoMetadataMaxBytes = 160;
+int iso_encode_metadata(const uhdr_gainmap_metadata_t& md, uint8_t* out, size_t cap, size_t* out_size);
 // inverse (:195-347); validates like uhdr_validate_gainmap_metadata_descriptor
 int iso_decode_metadata(const uint8_t* data, size_t size, uhdr_gainmap_metadata_t* md);
 int validate_metadata(const uhdr_gainmap_metadata_t& md);

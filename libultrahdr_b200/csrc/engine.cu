@@ -355,9 +355,7 @@ int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map_in
       }
   }
   if (idw_floats) {
-    std::vector<float> idw;
-    build_idw_tables(p.scale_int, idw);
-    memcpy(h_tab + 3 * 1024, idw.data(), sizeof(float) * idw_floats);
+    build_idw_tables(p.scale_int, h_tab + 3 * 1024);   // straight into the pinned staging block
   }
   CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, sizeof(float) * tab_floats, cudaMemcpyHostToDevice, ws.stream()));
   p.gain_lut = d_tab;

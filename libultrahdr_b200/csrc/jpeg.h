@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "bytes.h"
 #include "engine.h"
 
 namespace uhdr_b200 {
@@ -66,22 +67,38 @@ int jpeg_fetch_coefs(Workspace& ws, JpegEncodeJob* job);
 // writes for gain-map images (jpegencoderhelper.cpp:205-211).
 int jpeg_finish_stream(const JpegEncodeJob& job, const void* icc, size_t icc_size,
                        const char* comment, std::vector<uint8_t>* out);
-// Head (SOI .. SOS header) only, and the entropy-coded segment as a pointer: device path = the
-// pinned buffer, host path = `host_scan` filled here.  No copy of the segment is made.
-int jpeg_stream_pieces(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment,
-                       std::vector<uint8_t>* head, std::vector<uint8_t>* host_scan, const uint8_t** scan,
-                       size_t* scan_len);
+// The same for the device entropy path into storage the caller owns (no heap): `cap` >= jpeg_head_capacity() +
+// the segment's bytes + 2.
+size_t jpeg_head_capacity(size_t icc_size, const char* comment);
+int jpeg_finish_stream_into(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment, uint8_t* out,
+                            size_t cap, size_t* out_size);
+// Head (SOI .. SOS header) only, into `head` (capacity jpeg_head_capacity()), and the entropy-coded segment as a
+// pointer into the pinned buffer the device wrote it to.  No copy of the segment is made.
+int jpeg_stream_pieces(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment, uint8_t* head,
+                       size_t head_cap, size_t* head_len, const uint8_t** scan, size_t* scan_len);
 // host Huffman coder over [block][64] coefficient arrays
 void jpeg_host_entropy(const JpegFrame& f, const int16_t* const coefs[3], std::vector<uint8_t>* scan);
 
 // ---- decoder -----------------------------------------------------------------------------------
 struct JpegMarker { uint8_t id; size_t offset, length; };
+// APPn markers of a header in stream order; fixed capacity (no heap): the first kMax are kept, which is more than
+// any writer emits ahead of SOS (the look-ups below want the first EXIF / ICC / XMP / ISO / MPF marker)
+struct JpegMarkerList {
+  static constexpr int kMax = 48;
+  JpegMarker v[kMax];
+  int n = 0;
+  void push_back(const JpegMarker& m) { if (n < kMax) v[n++] = m; }
+  void clear() { n = 0; }
+  const JpegMarker* begin() const { return v; }
+  const JpegMarker* end() const { return v + n; }
+  size_t size() const { return (size_t)n; }
+};
 struct JpegHeader {
   JpegFrame frame;
   int comp_id[3] = {0, 0, 0};
   int restart_interval = 0;
   size_t scan_offset = 0;
-  std::vector<JpegMarker> markers;  // APP0..APP2 in stream order
+  JpegMarkerList markers;  // APP0..APP2 in stream order
   uint8_t bits[2][2][17];
   uint8_t vals[2][2][256];
   bool have_tbl[2][2] = {{false, false}, {false, false}};

@@ -143,12 +143,6 @@ const char* jpeg_gainmap_comment() {
 
 // ---- marker layer (jcmarker.c order: SOI, JFIF, [APP2], [COM], DQT.., SOF0, DHT.., SOS) ----------
 namespace {
-struct ByteSink {
-  std::vector<uint8_t>& v;
-  void u8(unsigned b) { v.push_back((uint8_t)b); }
-  void u16(unsigned w) { u8(w >> 8); u8(w & 0xff); }
-  void raw(const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; v.insert(v.end(), b, b + n); }
-};
 void put_dht(ByteSink& o, int cls_id, const HuffSpec& s) {
   o.u16(0xFFC4);
   o.u16(2 + 1 + 16 + s.nsym);
@@ -158,9 +152,12 @@ void put_dht(ByteSink& o, int cls_id, const HuffSpec& s) {
 }
 }  // namespace
 
-static void write_headers(const JpegFrame& f, const void* icc, size_t icc_size, const char* comment,
-                          std::vector<uint8_t>* out) {
-  ByteSink o{*out};
+// upper bound of what write_headers emits next to the ICC payload and the comment text: SOI 2, JFIF 18, APP2 and
+// COM marker headers 8, two DQT 138, SOF0 19, four DHT 432, SOS 14
+constexpr size_t kJpegHeadFixedBytes = 640;
+size_t jpeg_head_capacity(size_t icc_size, const char* comment) { return kJpegHeadFixedBytes + icc_size + (comment ? strlen(comment) : 0); }
+
+static void write_headers(const JpegFrame& f, const void* icc, size_t icc_size, const char* comment, ByteSink& o) {
   o.u16(0xFFD8);
   static const uint8_t jfif[16] = {0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0};
   o.u16(0xFFE0);
@@ -290,10 +287,15 @@ void jpeg_host_entropy(const JpegFrame& f, const int16_t* const coefs[3], std::v
 
 int jpeg_finish_stream(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment,
                        std::vector<uint8_t>* out) {
-  out->clear();
   const JpegFrame& f = job.frame;
-  out->reserve(1024 + icc_size + (job.h_scan_bytes ? job.h_scan_bytes[3] : f.total_blocks() * 24));
-  write_headers(f, icc, icc_size, comment, out);
+  const size_t head_cap = jpeg_head_capacity(icc_size, comment);
+  out->clear();
+  out->reserve(head_cap + 2 + (job.h_scan_bytes ? job.h_scan_bytes[3] : f.total_blocks() * 24));
+  out->resize(head_cap);
+  ByteSink head(out->data(), head_cap);
+  write_headers(f, icc, icc_size, comment, head);
+  if (!head.ok()) return fail(E_ERROR, "JPEG header of %zu bytes exceeds its bound of %zu", head.size(), head_cap);
+  out->resize(head.size());
   if (job.h_scan_bytes) {
     if (job.h_scan_bytes[4] || !job.h_scan)
       return fail(E_MEM, "entropy-coded segment exceeds the device scan buffer (%zu bytes)", job.scan_capacity);
@@ -307,23 +309,30 @@ int jpeg_finish_stream(const JpegEncodeJob& job, const void* icc, size_t icc_siz
   return E_OK;
 }
 
-int jpeg_stream_pieces(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment,
-                       std::vector<uint8_t>* head, std::vector<uint8_t>* host_scan, const uint8_t** scan,
-                       size_t* scan_len) {
-  head->clear();
-  write_headers(job.frame, icc, icc_size, comment, head);
-  if (job.h_scan_bytes) {
-    if (job.h_scan_bytes[4] || !job.h_scan)
-      return fail(E_MEM, "entropy-coded segment exceeds the device scan buffer (%zu bytes)", job.scan_capacity);
-    *scan = job.h_scan;
-    *scan_len = job.h_scan_bytes[3];
-  } else {
-    host_scan->clear();
-    const int16_t* c[3] = {job.h_coefs[0], job.h_coefs[1], job.h_coefs[2]};
-    jpeg_host_entropy(job.frame, c, host_scan);
-    *scan = host_scan->data();
-    *scan_len = host_scan->size();
-  }
+// device entropy path, caller storage (workspace arena): SOI .. EOI into `out`
+int jpeg_finish_stream_into(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment, uint8_t* out,
+                            size_t cap, size_t* out_size) {
+  if (!job.h_scan_bytes || job.h_scan_bytes[4] || !job.h_scan)
+    return fail(E_MEM, "entropy-coded segment exceeds the device scan buffer (%zu bytes)", job.scan_capacity);
+  ByteSink o(out, cap);
+  write_headers(job.frame, icc, icc_size, comment, o);
+  o.raw(job.h_scan, job.h_scan_bytes[3]);
+  o.u16(0xFFD9);
+  if (!o.ok()) return fail(E_MEM, "JPEG stream of %zu bytes does not fit its %zu-byte buffer", o.size(), cap);
+  *out_size = o.size();
+  return E_OK;
+}
+
+int jpeg_stream_pieces(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment, uint8_t* head,
+                       size_t head_cap, size_t* head_len, const uint8_t** scan, size_t* scan_len) {
+  if (!job.h_scan_bytes || job.h_scan_bytes[4] || !job.h_scan)
+    return fail(E_MEM, "entropy-coded segment exceeds the device scan buffer (%zu bytes)", job.scan_capacity);
+  ByteSink o(head, head_cap);
+  write_headers(job.frame, icc, icc_size, comment, o);
+  if (!o.ok()) return fail(E_ERROR, "JPEG header of %zu bytes exceeds its bound of %zu", o.size(), head_cap);
+  *head_len = o.size();
+  *scan = job.h_scan;
+  *scan_len = job.h_scan_bytes[3];
   return E_OK;
 }
 

@@ -78,12 +78,12 @@ void build_lut_blob(float* out) {
 static float idw_dist(float x1, float x2, float y1, float y2) {
   return (float)std::sqrt((double)(((y2 - y1) * (y2 - y1)) + (x2 - x1) * (x2 - x1)));
 }
-void build_idw_tables(int scale, std::vector<float>& out) {
+void build_idw_tables(int scale, float* out) {
   static const int inc[4][2] = {{1, 1}, {0, 1}, {1, 0}, {0, 0}};
   const size_t per = (size_t)scale * scale * 4;
-  out.assign(per * 4, 0.0f);
+  for (size_t i = 0; i < per * 4; i++) out[i] = 0.0f;
   for (int v = 0; v < 4; v++) {
-    float* w = out.data() + per * v;
+    float* w = out + per * v;
     for (int y = 0; y < scale; y++)
       for (int x = 0; x < scale; x++) {
         float px = ((float)x) / scale, py = ((float)y) / scale;

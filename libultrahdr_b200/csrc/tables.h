@@ -27,7 +27,7 @@ enum : int {
 void build_lut_blob(float* out);
 
 // ShepardsIDW: 4 variants (default, no-right, no-bottom, corner) x scale*scale*4 floats.
-void build_idw_tables(int scale, std::vector<float>& out);
+void build_idw_tables(int scale, float* out);   // 16 * scale * scale floats, caller storage
 
 struct GainmapMetadata {  // == uhdr_gainmap_metadata_t
   float max_content_boost[3], min_content_boost[3], gamma[3], offset_sdr[3], offset_hdr[3];
