@@ -126,3 +126,95 @@ def test_color_to_rgba1010102_and_f16_through_apply(oracle_libs):
             assert (pq >> 30 == 3).all()
             if name == "black":
                 assert (pq == np.uint32(0x3 << 30)).all()
+
+
+# ---- stage-level restatements of further gainmapmath_test.cpp vectors --------------------------------------------
+_YUV_COEFFS = {  # gainmapmath.cpp:638-674, keyed (src_cg, dst_cg) with BT.709 = 0, P3 (BT.601 matrix) = 1, BT.2100 = 2
+    (0, 1): [1.0, 0.101579, 0.196076, 0.0, 0.989854, -0.110653, 0.0, -0.072453, 0.983398],
+    (0, 2): [1.0, -0.016969, 0.096312, 0.0, 0.995306, -0.051192, 0.0, 0.011507, 1.002637],
+    (1, 0): [1.0, -0.118188, -0.212685, 0.0, 1.018640, 0.114618, 0.0, 0.075049, 1.025327],
+    (1, 2): [1.0, -0.128245, -0.115879, 0.0, 1.010016, 0.061592, 0.0, 0.086969, 1.029350],
+    (2, 0): [1.0, 0.018149, -0.095132, 0.0, 1.004123, 0.051267, 0.0, -0.011524, 0.996782],
+    (2, 1): [1.0, 0.117887, 0.105521, 0.0, 0.995211, -0.059549, 0.0, -0.084085, 0.976518],
+}
+
+
+def _stage_impls(oracle_libs):
+    return [oracle_libs.Oracle()] + ([oracle_libs.Ref()] if oracle_libs.have_ref() else [])
+
+
+def test_transform_yuv420_fixture(oracle_libs):
+    """gainmapmath_test.cpp:897-971 on the 4x4 fixture of :154-197: every output sample within 1 of the value the
+    test computes from yuvColorGamutConversion of the four covered pixels (chroma: their mean), for all six matrices."""
+    y = np.array([0x00, 0x10, 0x20, 0x30, 0x01, 0x11, 0x21, 0x31, 0x02, 0x12, 0x22, 0x32, 0x03, 0x13, 0x23, 0x33], np.uint8)
+    u = np.array([0xA0, 0xA1, 0xA2, 0xA3], np.uint8)
+    v = np.array([0xB0, 0xB1, 0xB2, 0xB3], np.uint8)
+    buf = np.concatenate([y, u, v])
+    f32 = np.float32
+    for (src, dst), m in _YUV_COEFFS.items():
+        m = np.array(m, f32)
+        outs = [impl.convert_yuv(buf, 4, 4, src, dst) for impl in _stage_impls(oracle_libs)]
+        for o in outs[1:]:
+            assert (o == outs[0]).all(), (src, dst)
+        o = outs[0]
+        oy, ou, ov = o[:16].reshape(4, 4), o[16:20].reshape(2, 2), o[20:].reshape(2, 2)
+        for cy in range(2):
+            for cx in range(2):
+                uu = (f32(int(u[cy * 2 + cx]) - 128)) / f32(255)
+                vv = (f32(int(v[cy * 2 + cx]) - 128)) / f32(255)
+                su = sv = f32(0)
+                for dy in range(2):
+                    for dx in range(2):
+                        yy = f32(int(y[(2 * cy + dy) * 4 + 2 * cx + dx])) / f32(255)
+                        ny = yy * m[0] + uu * m[1] + vv * m[2]
+                        su += yy * m[3] + uu * m[4] + vv * m[5]
+                        sv += yy * m[6] + uu * m[7] + vv * m[8]
+                        want = int(min(max(float(ny) * 255.0 + 0.5, 0), 255))
+                        assert abs(int(oy[2 * cy + dy, 2 * cx + dx]) - want) <= 1, (src, dst, cy, cx, dy, dx)
+                want_u = int(min(max(float(su) / 4 * 255.0 + 128.0 + 0.5, 0), 255))
+                want_v = int(min(max(float(sv) / 4 * 255.0 + 128.0 + 0.5, 0), 255))
+                assert abs(int(ou[cy, cx]) - want_u) <= 1 and abs(int(ov[cy, cx]) - want_v) <= 1, (src, dst, cy, cx)
+
+
+def test_yuv_gamut_conversion_of_primaries(oracle_libs):
+    """gainmapmath_test.cpp:738-773: the YUV of a gamut's primaries maps to the YUV of the target gamut's primaries
+    (fixture values :84-97), here through the 4:2:0 image transform on uniform 4x4 images, 8-bit quantised (+-2)."""
+    prim = {0: [(0.2126, -0.11457, 0.5), (0.7152, -0.38543, -0.45415), (0.0722, 0.5, -0.04585)],
+            1: [(0.299, -0.16874, 0.5), (0.587, -0.33126, -0.41869), (0.114, 0.5, -0.08131)],
+            2: [(0.2627, -0.13963, 0.5), (0.6780, -0.36037, -0.45979), (0.0593, 0.5, -0.04021)]}
+    for cg in prim:
+        prim[cg] = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0)] + prim[cg]   # YuvBlack, YuvWhite
+    q = lambda c: (int(round(c[0] * 255)), int(min(255, round(c[1] * 255 + 128))), int(min(255, round(c[2] * 255 + 128))))  # noqa: E731
+    for impl in _stage_impls(oracle_libs):
+        for (src, dst) in _YUV_COEFFS:
+            for i in range(5):
+                a, want = q(prim[src][i]), q(prim[dst][i])
+                buf = np.concatenate([np.full(16, a[0]), np.full(4, a[1]), np.full(4, a[2])]).astype(np.uint8)
+                o = impl.convert_yuv(buf, 4, 4, src, dst)
+                got = (int(o[0]), int(o[16]), int(o[20]))
+                assert all(abs(g - w) <= 2 for g, w in zip(got, want)), (src, dst, i, got, want)
+
+
+def test_apply_gain_table(oracle_libs):
+    """gainmapmath_test.cpp:1353-1429 (applyGain) through the applyGainMap stage: a white SDR pixel under a gain-map
+    byte b comes out as min_boost^(1-b/255) * max_boost^(b/255) in every channel (the reference's table rows at
+    g = 0, .25, .5, .75, 1), within the GainLUT's 1/1023 index step and half-float precision."""
+    from libultrahdr_b200 import ctypes_api as A
+    w, h = 16, 8
+    buf = np.concatenate([np.full(w * h, 255), np.full(w * h // 2, 128)]).astype(np.uint8)
+    sdr, _k = A.yuv420_image(buf, w, h, A.CG_BT709)
+    for mn, mx in ((0.25, 4.0), (0.5, 2.0), (0.125, 8.0), (1.0, 8.0), (0.5, 8.0)):
+        md = A.GainmapMetadata()
+        for i in range(3):
+            md.max_content_boost[i], md.min_content_boost[i], md.gamma[i] = mx, mn, 1.0
+            md.offset_sdr[i] = md.offset_hdr[i] = 0.0
+        md.hdr_capacity_min, md.hdr_capacity_max, md.use_base_cg = mn, mx, 1
+        if mn < 1.0:
+            md.hdr_capacity_min = 1.0   # the C API's validation wants capacity_min >= 1; the weight stays 1 at full boost
+        for b in (0, 64, 128, 191, 255):
+            gm = np.full((h, w, 1), b, np.uint8)
+            gi = T.gm_image(gm, A.CG_BT709)
+            want = math.exp2(math.log2(mn) + (b / 255.0) * (math.log2(mx) - math.log2(mn)))
+            for impl in _stage_impls(oracle_libs):
+                f16 = impl.apply(sdr, gi, md, A.CT_LINEAR).reshape(-1, 4)[:, :3].copy().view(np.float16).astype(np.float64)
+                assert np.allclose(f16, want, rtol=1.5e-2), (mn, mx, b, float(f16[0, 0]), want)
