@@ -98,8 +98,9 @@ UHDR_EXTERN int uhdr_b200_enc_rearm(uhdr_codec_private_t* enc);
  * does not pay cudaHostAlloc every time.  This returns the cache to the driver; result = bytes freed. */
 UHDR_EXTERN size_t uhdr_b200_trim_cache(void);
 /* Where JpegDecoderHelper's entropy decoding (libjpeg-turbo jdhuff.c behind jpegdecoderhelper.cpp:397-411)
- * runs: 0 = automatic (device for scans of 64 KiB and more), 1 = host, 2 = device whenever the stream
- * allows it.  Process-wide; returns the previous setting.  Results are identical either way. */
+ * runs: 0 (default) and 2 = on the device for every stream the parallel decoder accepts, whatever its size (the
+ * host decoder only takes the streams it declines: restart markers, no fixed point, inconsistent data);
+ * 1 = host, for tests and triage.  Process-wide; returns the previous setting.  Results are identical either way. */
 UHDR_EXTERN int uhdr_b200_set_entropy_decoder(int mode);
 /* out[0] = scans entropy-decoded on the device so far, out[1] = scans the device decoder handed back to
  * the host decoder, out[2] = relaxation rounds the last device decode needed */

@@ -322,10 +322,11 @@ int JpegRCodec::decode_jpeg_dev(Workspace& ws, const uint8_t* data, size_t size,
     planes[c] = (uint8_t*)ws.dalloc((size_t)strides[c] * f.comp[c].hblocks * 8);
     if (!planes[c]) return E_MEM;
   }
-  // entropy decoding: on the device (huffdec.cu) for anything sizeable, else -- or when the device
-  // decoder declines the stream -- on the host
+  // entropy decoding: on the device (huffdec.cu).  The host decoder is not a size-based alternative: it runs only
+  // for streams the parallel decoder declines (restart markers, no fixed point, inconsistent data -- it also
+  // produces the reference's error texts for those) or when a test / triage session selects it (mode 1).
   const int dec_mode = jpeg_get_entropy_decoder();
-  bool on_device = dec_mode == 2 || (dec_mode == 0 && size - h->scan_offset >= (64u << 10));
+  bool on_device = dec_mode != 1;
   if (on_device) {
     int16_t* d_coefs[3] = {nullptr, nullptr, nullptr};
     rc = jpeg_entropy_decode_dev(ws, data, size, *h, d_coefs);

@@ -119,7 +119,7 @@ int jpeg_idct_dev(Workspace& ws, const JpegHeader& h, int16_t* const d_coefs[3],
 // runs jpeg_host_decode_coefs, which also produces the reference's error texts.
 constexpr int kHuffDecFallback = -1000;
 int jpeg_entropy_decode_dev(Workspace& ws, const uint8_t* data, size_t size, const JpegHeader& h, int16_t* d_coefs[3]);
-// 0 = automatic (device for scans of at least 64 KiB), 1 = host, 2 = device whenever possible
+// 0 = default = 2 = device whenever the stream allows (host only for streams the device decoder declines), 1 = host (tests, triage)
 // [0] scans decoded on the device, [1] scans handed back to the host decoder, [2] relaxation rounds of the last one
 void jpeg_entropy_decoder_stats(unsigned long long out[3]);
 void jpeg_set_entropy_decoder(int mode);

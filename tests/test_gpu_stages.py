@@ -2,6 +2,7 @@
 else the C restatement), called through the C ABI with host buffers.  Bit-exact bar for the packed
 integer outputs and for the RGBA-F16 / metadata floats (tolerance 0 ULP is asserted; the tests that
 involve float powf with a continuous argument state their own bound)."""
+import ctypes as C
 import itertools
 
 import numpy as np
@@ -222,6 +223,31 @@ def test_convert_yuv(gpu, checker):
         a = gpu.convert_yuv(sb, W, H, s, d)
         b = checker.convert_yuv(sb, W, H, s, d)
         assert (a == b).all(), (s, d)
+
+
+def test_convert_yuv_444_and_unsupported_formats(gpu, checker):
+    """convertYuv at stage level on a 4:4:4 image (transformYuv444, jpegr.cpp:504-507) for all six gamut pairs, and the
+    reference's refusal of every other layout (:508-514), e.g. 4:2:2."""
+    rs = np.random.RandomState(5)
+    w, h = 98, 54
+    for s, d in itertools.permutations([0, 1, 2], 2):
+        outs = []
+        for impl in (gpu, checker):
+            planes = [rs_plane.copy() for rs_plane in _planes444(w, h)]
+            img = A.raw_image(A.FMT_YUV444, s, A.CT_SRGB, A.CR_FULL, w, h, planes, [w, w, w])
+            assert impl.f("convert_yuv")(C.byref(img), s, d) == 0
+            outs.append(np.stack(planes))
+        assert (outs[0] == outs[1]).all(), (s, d, int((outs[0] != outs[1]).sum()))
+    planes = [rs.randint(0, 256, (h, w)).astype(np.uint8), rs.randint(0, 256, (h, w // 2)).astype(np.uint8),
+              rs.randint(0, 256, (h, w // 2)).astype(np.uint8)]
+    for impl in (gpu, checker):
+        img = A.raw_image(A.FMT_YUV422, 0, A.CT_SRGB, A.CR_FULL, w, h, planes, [w, w // 2, w // 2])
+        assert impl.f("convert_yuv")(C.byref(img), 0, 1) != 0
+
+
+def _planes444(w, h):
+    rs = np.random.RandomState(17)
+    return [rs.randint(0, 256, (h, w)).astype(np.uint8) for _ in range(3)]
 
 
 def test_lut_blob_matches_checker(gpu, checker):
