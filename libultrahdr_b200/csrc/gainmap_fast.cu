@@ -602,6 +602,9 @@ cudaError_t launch_scaled(const GainmapGenParams& p, const FastLaunch& L) {
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, L.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    // two CTAs per SM: every CTA stages 42 KB of tables, and a 4K frame at scale 4 is only 2025 tiles -- with all
+    // the co-resident CTAs the table fill (31 MB out of L2) would weigh as much as the 37 MB of pixels
+    if (per_sm > 2) per_sm = 2;
     resident[dev] = per_sm * (sms > 0 ? sms : 148);
   }
   const int ntiles = ((p.map_w + 63) / 64) * ((p.map_h + 3) / 4);

@@ -43,4 +43,7 @@ if what in ("encode", "all"):
         api.encode(hdr, sdr)
     if what == "all":
         api.encode(hdr, None)
+        # JpegR's own defaults: map scale 4, one channel (k_gainmap_scaled), two-pass and realtime
+        api.encode(hdr, sdr, scale=4, multichannel=0)
+        api.encode(hdr, sdr, scale=4, multichannel=0, preset=A.USAGE_REALTIME)
 print("done")
