@@ -194,6 +194,11 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
     p.log2_min = std::log2(p.min_boost);  // float overloads: jpegr.cpp has `using namespace std`
     p.log2_max = std::log2(p.max_boost);
     p.gamma = cfg.gamma;
+    {
+      const double range = (double)(p.log2_max - p.log2_min);
+      const double inv = 1.0 / range;   // IEEE division on the host: correctly rounded
+      p.inv_log2_range = (range != 0.0 && std::isfinite(range) && std::isfinite(inv)) ? inv : 0.0;
+    }
     if (gainmap_fast_eligible(p, true)) {
       unsigned* sched = (unsigned*)ws.dalloc(64);
       if (!sched) return E_MEM;

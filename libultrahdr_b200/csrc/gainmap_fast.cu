@@ -65,6 +65,22 @@ __device__ __forceinline__ double log2_core(float q, const double2* __restrict__
 }
 
 
+// encodeGain's normalisation (gainmapmath.cpp:766): float((log2(gain) - log2_min) / double(log2_max - log2_min)), an fp64
+// division per channel and pixel in the reference.  The divisor b is the same for every pixel and is a float widened
+// to double, so the quotient comes out of three fp64 operations with y = RN(1/b) from the host (IEEE division):
+//   q = RN(a*y);  r = a - b*q (exact in the fma);  q' = RN(q + r*y)
+// q is within one ulp of a/b, so q + r*y differs from a/b by less than 2^-51 ulp before rounding; with a 24-bit
+// divisor a/b stays at least 2^-25 ulp away from every rounding boundary of a double (|A*2^k - B*(2n+1)| >= 1 for
+// integers A < 2^53, B < 2^24), hence q' = RN(a/b): the same double the division returns, bit for bit.
+__device__ __forceinline__ float encode_gain_norm(double log2_gain, const GainmapGenParams& p) {
+  const double a = log2_gain - (double)p.log2_min;
+  const double b = (double)(p.log2_max - p.log2_min);
+  if (p.inv_log2_range == 0.0) return (float)(a / b);   // degenerate range: the reference's own division (inf / NaN)
+  const double q = a * p.inv_log2_range;
+  const double r = fma(-q, b, a);
+  return (float)fma(r, p.inv_log2_range, q);
+}
+
 // ---- shared memory ------------------------------------------------------------------------------
 struct GmSmem {
   double2 log2tab[128];  // {invc, logc}
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
                 if (sv2[e] > 0.0f) gain = div_pos(hv2[e], sv2[e]);
                 if (gain < p.min_boost) gain = p.min_boost;
                 if (gain > p.max_boost) gain = p.max_boost;
-                const float gn = (float)((log2_core(gain, sm.log2tab) - (double)p.log2_min) / (double)(p.log2_max - p.log2_min));
+                const float gn = encode_gain_norm(log2_core(gain, sm.log2tab), p);
                 const unsigned code = (unsigned)__float2int_rz(gn * 255.0f) & 0xff;
                 const int bi = (2 * k + e) * NCH + c;
                 bout[bi >> 2] |= code << (8 * (bi & 3));
@@ -308,8 +324,31 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
 // of the pixel is the scale-1 arithmetic once per map pixel.  The sampling is the work here (16 source
 // pixels of each image per map pixel at S = 4): one thread = one map pixel, each source row arrives with
 // one load per plane (8 / 8 / 4 / 2 / 2 bytes at S = 4), the adds stay in the reference's order.
+// read-only loads that stay where they are written (ptxas keeps volatile instructions in program order): the scaled
+// kernel wants every source row of a thread in flight before the first dependent instruction
+__device__ __forceinline__ unsigned long long ldv_u64(const void* p) {
+  unsigned long long v;
+  asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ldv_u32(const void* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ldv_u16(const void* p) {
+  unsigned short v;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ldv_u8(const void* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, int S>
-__global__ void __launch_bounds__(256) k_gainmap_scaled(const GainmapGenParams p, const double* __restrict__ log2tab_g) {
+__global__ void __launch_bounds__(256, 4) k_gainmap_scaled(const GainmapGenParams p, const double* __restrict__ log2tab_g) {
   extern __shared__ double2 smem_d[];
   GmSmem& sm = *reinterpret_cast<GmSmem*>(smem_d);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
@@ -329,41 +368,52 @@ __global__ void __launch_bounds__(256) k_gainmap_scaled(const GainmapGenParams p
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int x = tx * 64 + threadIdx.x, y = ty * 4 + threadIdx.y;
     if (x >= p.map_w || y >= p.map_h) continue;
-    // ---- sampling
-    float sy = 0.f, su = 0.f, sv = 0.f, hy = 0.f, hu = 0.f, hv = 0.f;
+    // ---- sampling.  All S source rows are requested before the first sum: a thread's rows are S independent
+    // DRAM round trips, and with 42 KB of tables per CTA occupancy alone does not hide them.
+    unsigned long long hyw[S], huvw[S];   // per row: S luma words of 16 bit, S/2 chroma pairs
+    unsigned syw[S], suw[S], svw[S];
 #pragma unroll
     for (int dy = 0; dy < S; dy++) {
       const int yy = y * S + dy;
-      unsigned long long hyw, huvw;   // S luma words of 16 bit, S/2 chroma pairs
-      unsigned syw, suw, svw;
       const uint16_t* hyp = (const uint16_t*)p.hdr.p[0] + (size_t)yy * p.hdr.stride[0] + x * S;
       const uint16_t* hcp = (const uint16_t*)p.hdr.p[1] + (size_t)(yy >> 1) * p.hdr.stride[1] + x * S;
       const uint8_t* syp = (const uint8_t*)p.sdr.p[0] + (size_t)yy * p.sdr.stride[0] + x * S;
       const uint8_t* sup = (const uint8_t*)p.sdr.p[1] + (size_t)(yy >> 1) * p.sdr.stride[1] + x * (S / 2);
       const uint8_t* svp = (const uint8_t*)p.sdr.p[2] + (size_t)(yy >> 1) * p.sdr.stride[2] + x * (S / 2);
       if (S == 4) {
-        const uint2 a = __ldg((const uint2*)hyp), b = __ldg((const uint2*)hcp);
-        hyw = ((unsigned long long)a.y << 32) | a.x;
-        huvw = ((unsigned long long)b.y << 32) | b.x;
-        syw = __ldg((const unsigned*)syp);
-        suw = __ldg((const uint16_t*)sup);
-        svw = __ldg((const uint16_t*)svp);
+        hyw[dy] = ldv_u64(hyp);
+        syw[dy] = ldv_u32(syp);
+        if (!(dy & 1)) {   // rows 2k and 2k+1 share their chroma row
+          huvw[dy] = ldv_u64(hcp);
+          suw[dy] = ldv_u16(sup);
+          svw[dy] = ldv_u16(svp);
+        } else {
+          huvw[dy] = huvw[dy - 1]; suw[dy] = suw[dy - 1]; svw[dy] = svw[dy - 1];
+        }
       } else {
-        hyw = __ldg((const unsigned*)hyp);
-        huvw = __ldg((const unsigned*)hcp);
-        syw = __ldg((const uint16_t*)syp);
-        suw = __ldg(sup);
-        svw = __ldg(svp);
+        hyw[dy] = ldv_u32(hyp);
+        syw[dy] = ldv_u16(syp);
+        if (!(dy & 1)) {
+          huvw[dy] = ldv_u32(hcp);
+          suw[dy] = ldv_u8(sup);
+          svw[dy] = ldv_u8(svp);
+        } else {
+          huvw[dy] = huvw[dy - 1]; suw[dy] = suw[dy - 1]; svw[dy] = svw[dy - 1];
+        }
       }
+    }
+    float sy = 0.f, su = 0.f, sv = 0.f, hy = 0.f, hu = 0.f, hv = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < S; dy++) {
 #pragma unroll
       for (int dx = 0; dx < S; dx++) {
         // getYuv420Pixel (gainmapmath.cpp:354-372)
-        sy += (float)((syw >> (8 * dx)) & 0xff) * (1 / 255.0f);
-        su += (float)((int)((suw >> (8 * (dx >> 1))) & 0xff) - 128) * (1 / 255.0f);
-        sv += (float)((int)((svw >> (8 * (dx >> 1))) & 0xff) - 128) * (1 / 255.0f);
+        sy += (float)((syw[dy] >> (8 * dx)) & 0xff) * (1 / 255.0f);
+        su += (float)((int)((suw[dy] >> (8 * (dx >> 1))) & 0xff) - 128) * (1 / 255.0f);
+        sv += (float)((int)((svw[dy] >> (8 * (dx >> 1))) & 0xff) - 128) * (1 / 255.0f);
         // getP010Pixel (:412-445)
-        const int y10 = (int)((hyw >> (16 * dx + 6)) & 0x3ff);
-        const int u10 = (int)((huvw >> (32 * (dx >> 1) + 6)) & 0x3ff), v10 = (int)((huvw >> (32 * (dx >> 1) + 22)) & 0x3ff);
+        const int y10 = (int)((hyw[dy] >> (16 * dx + 6)) & 0x3ff);
+        const int u10 = (int)((huvw[dy] >> (32 * (dx >> 1) + 6)) & 0x3ff), v10 = (int)((huvw[dy] >> (32 * (dx >> 1) + 22)) & 0x3ff);
         if (LIMITED) {
           hy += (float)(y10 - 64) * (1 / 876.0f);
           hu += (float)(u10 - 64) * (1 / 896.0f) - 0.5f;
@@ -411,7 +461,7 @@ __global__ void __launch_bounds__(256) k_gainmap_scaled(const GainmapGenParams p
         if (s3[c] > 0.0f) gain = div_pos(h3[c], s3[c]);
         if (gain < p.min_boost) gain = p.min_boost;
         if (gain > p.max_boost) gain = p.max_boost;
-        const float gn = (float)((log2_core(gain, sm.log2tab) - (double)p.log2_min) / (double)(p.log2_max - p.log2_min));
+        const float gn = encode_gain_norm(log2_core(gain, sm.log2tab), p);
         p.dst[((size_t)y * p.dst_stride + x) * NCH + c] = (uint8_t)((unsigned)__float2int_rz(gn * 255.0f) & 0xff);
       } else {         // computeGain :773-782
         float g = (float)log2_core(div_pos(h3[c] + 1e-7f, s3[c] + 1e-7f), sm.log2tab);
@@ -602,9 +652,6 @@ cudaError_t launch_scaled(const GainmapGenParams& p, const FastLaunch& L) {
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, L.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    // two CTAs per SM: every CTA stages 42 KB of tables, and a 4K frame at scale 4 is only 2025 tiles -- with all
-    // the co-resident CTAs the table fill (31 MB out of L2) would weigh as much as the 37 MB of pixels
-    if (per_sm > 2) per_sm = 2;
     resident[dev] = per_sm * (sms > 0 ? sms : 148);
   }
   const int ntiles = ((p.map_w + 63) / 64) * ((p.map_h + 3) / 4);

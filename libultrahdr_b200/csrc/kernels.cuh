@@ -33,6 +33,9 @@ struct GainmapGenParams {  // generateGainMap, lib/src/jpegr.cpp:530-1058
   unsigned* minmax;                 // 6 order-preserving keys: min[3], max[3]
   // one-pass (REALTIME) :724-737, encodeGain gainmapmath.cpp:758-771
   float min_boost, max_boost, log2_min, log2_max, gamma;
+  // one-pass fast kernels: correctly rounded 1 / double(log2_max - log2_min), or 0 when that range is zero / not finite
+  // (then the kernels divide); see encode_gain_norm in gainmap_fast.cu
+  double inv_log2_range;
   uint8_t* dst;                     // RGB888 / Y400
   int dst_stride;                   // pixels
 };
