@@ -105,6 +105,14 @@ UHDR_EXTERN int uhdr_b200_set_entropy_decoder(int mode);
 /* out[0] = scans entropy-decoded on the device so far, out[1] = scans the device decoder handed back to
  * the host decoder, out[2] = relaxation rounds the last device decode needed */
 UHDR_EXTERN void uhdr_b200_entropy_decoder_stats(unsigned long long out[3]);
+/* Two-pass generateGainMap on the fast kernels keeps the quotient (hdr+eps)/(sdr+eps) in its float plane and takes the
+ * log2 in pass 2, in fp32 (lg2.approx) wherever the output byte provably does not depend on more, in fp64 otherwise.
+ * out[0] = gain values quantised that way since process start, out[1] = how many of them took the fp64 path. */
+UHDR_EXTERN void uhdr_b200_generate_stats(unsigned long long out[2]);
+/* diagnostic: worst[0] = max over the `count` floats whose bit patterns start at first_bits of
+ * |lg2.approx(x) - float(log2(double(x)))| / bound(x), the bound being the one pass 2 relies on (must stay <= 0.5:
+ * a factor 2 to spare); host pointer. */
+UHDR_EXTERN int uhdr_b200_probe_log2_fast(unsigned first_bits, unsigned count, float* worst);
 /* diagnostic: out[i] = float(log2(double(in[i]))) exactly as the gain-map kernels evaluate computeGain's
  * log2 (gainmapmath.cpp:773-782); host pointers. */
 UHDR_EXTERN int uhdr_b200_probe_log2(const float* in, float* out, int n);

@@ -57,6 +57,21 @@ UHDR_API int uhdr_b200_probe_log2(const float* in, float* out, int n) {
   return ws->sync();
 }
 
+UHDR_API void uhdr_b200_generate_stats(unsigned long long out[2]) {
+  if (out) gainmap_affine_stats(out);
+}
+
+UHDR_API int uhdr_b200_probe_log2_fast(unsigned first_bits, unsigned count, float* worst) {
+  Workspace* ws = tls_workspace();
+  if (!ws || !worst) return E_ERROR;
+  float* d_w = (float*)ws->dalloc(64);
+  if (!d_w) return E_MEM;
+  CUDA_TRY(cudaMemsetAsync(d_w, 0, 4, ws->stream()));
+  CUDA_TRY(launch_log2_fast_probe(first_bits, count, d_w, ws->stream()));
+  CUDA_TRY(cudaMemcpyAsync(worst, d_w, 4, cudaMemcpyDeviceToHost, ws->stream()));
+  return ws->sync();
+}
+
 UHDR_API int uhdr_b200_probe_powf(const float* in, float y, float* out, int n) {
   Workspace* ws = tls_workspace();
   if (!ws) return E_ERROR;

@@ -1,7 +1,9 @@
 #include "engine.h"
 
+#include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace uhdr_b200 {
@@ -209,15 +211,10 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
     return E_OK;
   }
   p.gains = (float*)ws.dalloc(sizeof(float) * (size_t)mw * mh * p.nch);
-  p.minmax = (unsigned*)ws.dalloc(64);
+  p.minmax = (unsigned*)ws.dalloc(128);
   float* d_minmax_f = (float*)ws.dalloc(64);
   job->h_minmax = (float*)ws.halloc(64);
   if (!p.gains || !p.minmax || !d_minmax_f || !job->h_minmax) return E_MEM;
-  CUDA_TRY(launch_gainmap_init_minmax(p.minmax, ws.stream()));
-  if (gainmap_fast_eligible(p, false))
-    TIMED(ws, "gainmap_pass1", launch_gainmap_fast(p, false, p.minmax + 8, ws.stream()));  // word 8: tile tickets, zeroed by init_minmax
-  else
-    TIMED(ws, "gainmap_pass1", launch_gainmap_pass1(p, ws.stream()));
   GainmapFinalizeParams f;
   f.minmax = p.minmax;
   f.minmax_f = d_minmax_f;
@@ -235,19 +232,52 @@ int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr
   a.nch = p.nch;
   a.dst_stride = p.dst_stride;
   a.gamma = cfg.gamma;
-  if (affine_fast_eligible(a)) {  // clamp / hints folded into the affine pass
+  // Both passes on their fast kernels: the float plane carries the quotient (sign = dark pixel) and pass 2 takes the
+  // log2 -- in fp32 wherever the byte provably does not depend on more (k_affine_q).  UHDR_B200_GAINS_PLANE=1 keeps
+  // the log2 in pass 1 (measurement / triage).
+  static const bool keep_gains_plane = getenv("UHDR_B200_GAINS_PLANE") != nullptr;
+  const bool pass1_fast = gainmap_fast_eligible(p, false), affine_fast = affine_fast_eligible(a);
+  const bool q_mode = pass1_fast && affine_fast && !keep_gains_plane;
+  job->exact_word = nullptr;
+  if (q_mode) {
+    p.store_q = 1;
+    CUDA_TRY(launch_init_q_keys(p.minmax, ws.stream()));
+    TIMED(ws, "gainmap_pass1", launch_gainmap_fast(p, false, p.minmax + 8, ws.stream()));
     count_launches(1);
-    TIMED(ws, "gainmap_affine", launch_affine_fast(a, f, ws.stream()));
+    TIMED(ws, "gainmap_affine", launch_affine_q(a, f, p.minmax + 9, ws.stream()));
+    job->exact_word = reinterpret_cast<unsigned*>(job->h_minmax + 8);
+    job->values = (unsigned long long)mw * mh * p.nch;
+    CUDA_TRY(cudaMemcpyAsync(job->exact_word, p.minmax + 9, sizeof(unsigned), cudaMemcpyDeviceToHost, ws.stream()));
   } else {
-    TIMED(ws, "gainmap_finalize", launch_gainmap_finalize(f, ws.stream()));
-    TIMED(ws, "gainmap_affine", launch_gainmap_affine(a, ws.stream()));
+    CUDA_TRY(launch_gainmap_init_minmax(p.minmax, ws.stream()));
+    if (pass1_fast)
+      TIMED(ws, "gainmap_pass1", launch_gainmap_fast(p, false, p.minmax + 8, ws.stream()));  // word 8: tile tickets, zeroed by init_minmax
+    else
+      TIMED(ws, "gainmap_pass1", launch_gainmap_pass1(p, ws.stream()));
+    if (affine_fast) {  // clamp / hints folded into the affine pass
+      count_launches(1);
+      TIMED(ws, "gainmap_affine", launch_affine_fast(a, f, ws.stream()));
+    } else {
+      TIMED(ws, "gainmap_finalize", launch_gainmap_finalize(f, ws.stream()));
+      TIMED(ws, "gainmap_affine", launch_gainmap_affine(a, ws.stream()));
+    }
   }
   CUDA_TRY(cudaMemcpyAsync(job->h_minmax, d_minmax_f, 6 * sizeof(float), cudaMemcpyDeviceToHost, ws.stream()));
   return E_OK;
 }
 
+static std::atomic<unsigned long long> g_affine_values{0}, g_affine_exact{0};
+void gainmap_affine_stats(unsigned long long out[2]) {
+  out[0] = g_affine_values.load();
+  out[1] = g_affine_exact.load();
+}
+
 void finish_gainmap_metadata(const GainmapJob& job, uhdr_gainmap_metadata_t* md) {
   const float kSdrWhiteNits = 203.0f;
+  if (job.exact_word) {   // k_affine_q ran: how many values needed the fp64 log2
+    g_affine_values.fetch_add(job.values);
+    g_affine_exact.fetch_add(*job.exact_word);
+  }
   if (job.onepass) {  // jpegr.cpp:724-734
     for (int i = 0; i < 3; i++) {
       md->max_content_boost[i] = job.hdr_white_nits / kSdrWhiteNits;

@@ -31,12 +31,16 @@ struct GainmapJob {      // state between enqueue and metadata finish
   float target_nits = -1;
   int use_base_cg = 1;
   float* h_minmax = nullptr;  // pinned, 6 floats (two-pass)
+  unsigned* exact_word = nullptr;      // pinned; k_affine_q: values that took the fp64 log2 (null: other kernels ran)
+  unsigned long long values = 0;       // map_w * map_h * channels of that run
 };
 // map_align: stride alignment of the produced map in pixels (reference allocates with 64)
 int generate_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& hdr,
                          const uhdr_b200_gm_config_t& cfg, int map_align, GainmapJob* job);
 // after the stream has been synchronised: fill the metadata (jpegr.cpp:724-734, 1031-1048)
 void finish_gainmap_metadata(const GainmapJob& job, uhdr_gainmap_metadata_t* md);
+// two-pass fast path since process start: [0] gain values quantised by k_affine_q, [1] of those through the fp64 log2
+void gainmap_affine_stats(unsigned long long out[2]);
 
 int apply_gainmap_dev(Workspace& ws, const DevImage& sdr, const DevImage& map,
                       const uhdr_gainmap_metadata_t& md, int out_ct, float max_display_boost,

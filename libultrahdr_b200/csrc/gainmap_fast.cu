@@ -81,6 +81,10 @@ __device__ __forceinline__ float encode_gain_norm(double log2_gain, const Gainma
   return (float)fma(r, p.inv_log2_range, q);
 }
 
+// q mode of the two-pass kernels: key slots and start values (a quotient is a positive finite float)
+constexpr float kQMinInit = 3.0e38f;
+constexpr int kQDarkKeys = 16;   // minmax[16..18] min q of dark pixels, [19..21] max q of dark pixels ([0..5]: the others)
+
 // ---- shared memory ------------------------------------------------------------------------------
 struct GmSmem {
   double2 log2tab[128];  // {invc, logc}
@@ -143,7 +147,7 @@ __device__ __forceinline__ void reduce_minmax(const float mn[3], const float mx[
   }
 }
 
-template <bool ONEPASS, int NCH, int GAMUT /*0 none, 1 on sdr, 2 on hdr*/, bool LIMITED>
+template <bool ONEPASS, int NCH, int GAMUT /*0 none, 1 on sdr, 2 on hdr*/, bool LIMITED, bool QMODE /*two-pass: quotient plane*/>
 __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams p, const double* __restrict__ log2tab_g, const int tiles_x,
                                                          const int ntiles, unsigned* __restrict__ sched, const unsigned long long nz) {
   extern __shared__ double2 smem_d[];
@@ -162,7 +166,10 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
   if (tid == 0) s_tile[0] = (int)atomicAdd(sched, 1u);
   __syncthreads();
 
-  float mn[3] = {127.0f, 127.0f, 127.0f}, mx[3] = {-128.0f, -128.0f, -128.0f};
+  // gains mode: extremes of the gains; q mode (store_q): extremes of the quotient, non-dark and dark pixels apart
+  const float mn0 = QMODE ? kQMinInit : 127.0f, mx0 = QMODE ? 0.0f : -128.0f;
+  float mn[3] = {mn0, mn0, mn0}, mx[3] = {mx0, mx0, mx0};
+  float dmn[3] = {kQMinInit, kQMinInit, kQMinInit}, dmx[3] = {0.0f, 0.0f, 0.0f};
   const V2 k8184 = bc(8184.0f), k32760 = bc(hscale8), keps = bc(1e-7f);
   const V2 snits = bc(p.sdr_nits), hnits = bc(p.hdr_nits);
 #pragma unroll 1
@@ -286,13 +293,23 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
               }
             } else {        // computeGain :773-782
               un(div_pos2(vadd(hv3[c], keps), vadd(sv3[c], keps), nz), q0, q1);
-              float g0 = (float)log2_core(q0, sm.log2tab), g1 = (float)log2_core(q1, sm.log2tab);
-              if (s0 < 2.f / 255.0f) g0 = fminf(g0, 2.3f);
-              if (s1 < 2.f / 255.0f) g1 = fminf(g1, 2.3f);
-              gout[(2 * k) * NCH + c] = g0;
-              gout[(2 * k + 1) * NCH + c] = g1;
-              mn[c] = fminf(mn[c], fminf(g0, g1));
-              mx[c] = fmaxf(mx[c], fmaxf(g0, g1));
+              if (QMODE) {
+                // the log2 waits for pass 2 (k_affine_q): log2, its narrowing to float and the dark-pixel cap are
+                // monotone, so the extremes of the gains are the images of the extremes of q per class
+                const bool d0 = s0 < 2.f / 255.0f, d1 = s1 < 2.f / 255.0f;
+                gout[(2 * k) * NCH + c] = d0 ? -q0 : q0;
+                gout[(2 * k + 1) * NCH + c] = d1 ? -q1 : q1;
+                if (d0) { dmn[c] = fminf(dmn[c], q0); dmx[c] = fmaxf(dmx[c], q0); } else { mn[c] = fminf(mn[c], q0); mx[c] = fmaxf(mx[c], q0); }
+                if (d1) { dmn[c] = fminf(dmn[c], q1); dmx[c] = fmaxf(dmx[c], q1); } else { mn[c] = fminf(mn[c], q1); mx[c] = fmaxf(mx[c], q1); }
+              } else {
+                float g0 = (float)log2_core(q0, sm.log2tab), g1 = (float)log2_core(q1, sm.log2tab);
+                if (s0 < 2.f / 255.0f) g0 = fminf(g0, 2.3f);
+                if (s1 < 2.f / 255.0f) g1 = fminf(g1, 2.3f);
+                gout[(2 * k) * NCH + c] = g0;
+                gout[(2 * k + 1) * NCH + c] = g1;
+                mn[c] = fminf(mn[c], fminf(g0, g1));
+                mx[c] = fmaxf(mx[c], fmaxf(g0, g1));
+              }
             }
           }
         }
@@ -315,7 +332,13 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
     }
     __syncthreads();
   }
-  if (!ONEPASS) reduce_minmax<NCH>(mn, mx, p.minmax, tid, nt);
+  if (!ONEPASS) {
+    reduce_minmax<NCH>(mn, mx, p.minmax, tid, nt);
+    if (QMODE) {
+      __syncthreads();
+      reduce_minmax<NCH>(dmn, dmx, p.minmax + kQDarkKeys, tid, nt);
+    }
+  }
 }
 
 // ---- map scale 2 / 4 (the reference's JpegR default is scale 4, one channel, ultrahdrcommon.h:450-457) ----
@@ -347,7 +370,7 @@ __device__ __forceinline__ unsigned ldv_u8(const void* p) {
   return v;
 }
 
-template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, int S>
+template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, int S, bool QMODE>
 __global__ void __launch_bounds__(256, 4) k_gainmap_scaled(const GainmapGenParams p, const double* __restrict__ log2tab_g) {
   extern __shared__ double2 smem_d[];
   GmSmem& sm = *reinterpret_cast<GmSmem*>(smem_d);
@@ -361,7 +384,10 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_scaled(const GainmapGenParam
   for (int i = tid; i < 2 * hN; i += nt) sm.hdr2[i] = __ldg(hsrc + min((i + 1) >> 1, hN - 1));
   const float hscale8 = (float)(8 * (hN - 1));
   __syncthreads();
-  float mn[3] = {127.0f, 127.0f, 127.0f}, mx[3] = {-128.0f, -128.0f, -128.0f};
+  // gains mode: extremes of the gains; q mode (store_q): extremes of the quotient, non-dark and dark pixels apart
+  const float mn0 = QMODE ? kQMinInit : 127.0f, mx0 = QMODE ? 0.0f : -128.0f;
+  float mn[3] = {mn0, mn0, mn0}, mx[3] = {mx0, mx0, mx0};
+  float dmn[3] = {kQMinInit, kQMinInit, kQMinInit}, dmx[3] = {0.0f, 0.0f, 0.0f};
   const int tiles_x = (p.map_w + 63) / 64, ntiles = tiles_x * ((p.map_h + 3) / 4);
 #pragma unroll 1
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -464,15 +490,28 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_scaled(const GainmapGenParam
         const float gn = encode_gain_norm(log2_core(gain, sm.log2tab), p);
         p.dst[((size_t)y * p.dst_stride + x) * NCH + c] = (uint8_t)((unsigned)__float2int_rz(gn * 255.0f) & 0xff);
       } else {         // computeGain :773-782
-        float g = (float)log2_core(div_pos(h3[c] + 1e-7f, s3[c] + 1e-7f), sm.log2tab);
-        if (s3[c] < 2.f / 255.0f) g = fminf(g, 2.3f);
-        p.gains[((size_t)y * p.map_w + x) * NCH + c] = g;
-        mn[c] = fminf(mn[c], g);
-        mx[c] = fmaxf(mx[c], g);
+        const float q = div_pos(h3[c] + 1e-7f, s3[c] + 1e-7f);
+        const bool dark = s3[c] < 2.f / 255.0f;
+        if (QMODE) {
+          p.gains[((size_t)y * p.map_w + x) * NCH + c] = dark ? -q : q;
+          if (dark) { dmn[c] = fminf(dmn[c], q); dmx[c] = fmaxf(dmx[c], q); } else { mn[c] = fminf(mn[c], q); mx[c] = fmaxf(mx[c], q); }
+        } else {
+          float g = (float)log2_core(q, sm.log2tab);
+          if (dark) g = fminf(g, 2.3f);
+          p.gains[((size_t)y * p.map_w + x) * NCH + c] = g;
+          mn[c] = fminf(mn[c], g);
+          mx[c] = fmaxf(mx[c], g);
+        }
       }
     }
   }
-  if (!ONEPASS) reduce_minmax<NCH>(mn, mx, p.minmax, tid, nt);
+  if (!ONEPASS) {
+    reduce_minmax<NCH>(mn, mx, p.minmax, tid, nt);
+    if (QMODE) {
+      __syncthreads();
+      reduce_minmax<NCH>(dmn, dmx, p.minmax + kQDarkKeys, tid, nt);
+    }
+  }
 }
 
 // ---- pass 2 (jpegr.cpp:988-1013, affineMapGain gainmapmath.cpp:784-789), gamma 1, tight rows ------
@@ -532,6 +571,176 @@ __global__ void __launch_bounds__(192) k_affine_fast(const AffineParams p, const
     }
     o[f] = w;
   }
+}
+
+// ---- pass 2 on the quotient plane (store_q) ---------------------------------------------------------
+// gain = float(log2(double(q))) capped at 2.3 for dark pixels, then affineMapGain -> byte.  Only the byte leaves the
+// kernel, so the fp64 log2 is needed only where the byte could depend on it: every value first goes through the
+// hardware's fp32 lg2.approx, whose distance to the exact path is bounded by kLg2Abs + |g| * kLg2Rel (checked over every
+// float of the quotient's range on the device, tests/test_gpu_stages.py::test_fast_log2_error_bound, with a factor 2 to
+// spare); the affine map turns that into a bound on t = 255 * (g - min) / (max - min) + 0.5, and the byte is
+// trunc(clamp(t)).  When t is further than the bound (plus the float roundings of the map itself) from the nearest
+// integer, the exact t truncates to the same byte; otherwise the value takes the exact path.  On natural content a few
+// values in ten thousand do.
+constexpr float kLg2Abs = 6e-7f, kLg2Rel = 2.4e-7f, kAffineRound = 2e-4f;
+
+__device__ __forceinline__ float lg2_fast(float x) {
+  float r;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_fast_bound(float g) { return kLg2Abs + fabsf(g) * kLg2Rel; }
+
+// log2 with the table in global memory (a dozen evaluations per thread at kernel start)
+__device__ __forceinline__ float log2f_exact_g(float q, const double* __restrict__ tab_g) {
+  const unsigned ix = __float_as_uint(q);
+  const unsigned tmp = ix - kLogOff;
+  const int i = (tmp >> 16) & 127;
+  const int k = (int)tmp >> 23;
+  const unsigned im = ix - (tmp & 0xff800000u);
+  const double md = __hiloint2double((int)((im >> 3) + 0x38000000u), (int)(im << 29));
+  const double kd = __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)k)) - 4503601774854144.0;
+  const double invc = tab_g[i], logc = tab_g[128 + i];
+  const double r = fma(md, invc, -1.0);
+  double pp = kLog2Poly[0];
+#pragma unroll
+  for (int j = 1; j < 8; j++) pp = fma(pp, r, kLog2Poly[j]);
+  return (float)fma(pp, r, kd + logc);
+}
+
+// min / max of the gains of channel c from the images g[] of the extreme quotients (g[4*c + {0: min q, 1: max q,
+// 2: min q dark, 3: max q dark}], a class without pixels flagged by a non-positive max q): fold them like the reference
+// folds every pixel (start values 127 / -128, jpegr.cpp:866-868), then the clamps / hints of finalized_minmax
+__device__ __forceinline__ void fold_minmax_q(const GainmapFinalizeParams& f, const float* g, const bool* has, float& mn, float& mx) {
+  mn = 127.0f;
+  mx = -128.0f;
+  if (has[0]) {   // non-dark pixels
+    mn = fminf(mn, g[0]);
+    mx = fmaxf(mx, g[1]);
+  }
+  if (has[1]) {   // dark pixels: gain = min(log2, 2.3)
+    mn = fminf(mn, fminf(g[2], 2.3f));
+    mx = fmaxf(mx, fminf(g[3], 2.3f));
+  }
+  mn = mn < -14.3f ? -14.3f : (mn > 15.6f ? 15.6f : mn);
+  mx = mx < -14.3f ? -14.3f : (mx > 15.6f ? 15.6f : mx);
+  if (f.has_user_max) mx = fminf(mx, f.log2_user_max);
+  if (f.has_user_min) mn = fmaxf(mn, f.log2_user_min);
+  if (fabsf(mx - mn) < 1.1920928955078125e-07f) mx += 0.1f;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(192) k_affine_q(const AffineParams p, const GainmapFinalizeParams fin, const long long n4,
+                                                  const double* __restrict__ tab_g, unsigned* __restrict__ exact_count,
+                                                  const unsigned long long nz) {
+  __shared__ double2 tab[128];
+  __shared__ float s_mm[6];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) tab[i] = make_double2(tab_g[i], tab_g[128 + i]);
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  __shared__ float s_g[12];
+  __shared__ bool s_has[6];
+  if (threadIdx.x < 12) {   // once per CTA: the fp64 log2 of the twelve extreme quotients, one per thread
+    const int c = threadIdx.x >> 2, k = threadIdx.x & 3, cc = c < fin.nch ? c : 0;
+    const unsigned key = fin.minmax[(k >> 1) * kQDarkKeys + (k & 1) * 3 + cc];
+    const float q = __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+    if (k & 1) s_has[c * 2 + (k >> 1)] = q > 0.0f;
+    s_g[threadIdx.x] = q > 0.0f && q < 3.0e38f ? log2f_exact_g(q, tab_g) : 0.0f;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float a, b;
+    fold_minmax_q(fin, s_g + 4 * threadIdx.x, s_has + 2 * threadIdx.x, a, b);
+    s_mm[threadIdx.x] = a;
+    s_mm[3 + threadIdx.x] = b;
+    if (blockIdx.x == 0) {
+      fin.minmax_f[threadIdx.x] = a;
+      fin.minmax_f[3 + threadIdx.x] = b;
+    }
+  }
+  __syncthreads();
+  // per element of this thread's float4 (fixed channel phase, see k_affine_fast): min, -range, refined 1/range and the
+  // screen's threshold.  A value whose t lands in [-1, 257] has |g| <= max(|min|, |max|) + 1: the threshold is constant.
+  float mn[4], nd[4], rc[4], thr[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = NCH == 3 ? (int)((t0 * 4 + j) % 3) : 0;
+    mn[j] = s_mm[c];
+    const float dj = s_mm[3 + c] - mn[j];
+    nd[j] = -dj;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dj));
+    rc[j] = __fmaf_rn(r, __fmaf_rn(-dj, r, 1.0f), r);
+    const float gmax = fmaxf(fabsf(mn[j]), fabsf(s_mm[3 + c])) + 1.0f;
+    thr[j] = (kLg2Abs + gmax * kLg2Rel) * (255.0f * rc[j] * 1.0001f) + kAffineRound;
+  }
+  const V2 mnv[2] = {v2(mn[0], mn[1]), v2(mn[2], mn[3])}, ndv[2] = {v2(nd[0], nd[1]), v2(nd[2], nd[3])};
+  const V2 rcv[2] = {v2(rc[0], rc[1]), v2(rc[2], rc[3])};
+  const V2 k255 = bc(255.0f), khalf = bc(0.5f), kmagic = bc(12582912.0f);   // 1.5 * 2^23: adding it rounds to an integer
+  const float4* g4 = reinterpret_cast<const float4*>(p.gains);
+  unsigned* o = reinterpret_cast<unsigned*>(p.dst);
+  unsigned n_exact = 0;
+  // two loads ahead of the value being processed (four: 68 registers, slower): the byte stores may alias the plane as far as the compiler knows, so
+  // it would not move the next load above them by itself
+  float4 q1 = t0 < n4 ? __ldcs(g4 + t0) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 q2 = t0 + nthr < n4 ? __ldcs(g4 + t0 + nthr) : q1;
+#pragma unroll 1
+  for (long long f = t0; f < n4; f += nthr) {
+    const float4 qv = q1;
+    q1 = q2;
+    if (f + 2 * nthr < n4) q2 = __ldcs(g4 + f + 2 * nthr);
+    const float qs[4] = {qv.x, qv.y, qv.z, qv.w};
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      g[j] = lg2_fast(fabsf(qs[j]));
+      if (qs[j] < 0.0f) g[j] = fminf(g[j], 2.3f);   // dark pixel
+    }
+    unsigned w = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      // the steps of k_affine_fast on a pair: a = g - min; a / range (div_pos steps); * 255; + 0.5
+      const V2 a = vsub(v2(g[2 * h], g[2 * h + 1]), mnv[h]);
+      V2 qq = vmul(a, rcv[h], nz);
+      qq = vfma(rcv[h], vfma(ndv[h], qq, a), qq);
+      const V2 t = vadd(vmul(qq, k255, nz), khalf);
+      float tt[2], dl[2];
+      un(t, tt[0], tt[1]);
+      un(vsub(t, vsub(vadd(t, kmagic), kmagic)), dl[0], dl[1]);   // t - nearest integer
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int j = 2 * h + e;
+        if (fabsf(dl[e]) < thr[j]) {   // the byte could depend on the last bits of the log2: exact path
+          float ge = (float)log2_core(fabsf(qs[j]), tab);
+          if (qs[j] < 0.0f) ge = fminf(ge, 2.3f);
+          const float ae = ge - mn[j];
+          float qe = __fmul_rn(ae, rc[j]);
+          qe = __fmaf_rn(rc[j], __fmaf_rn(nd[j], qe, ae), qe);
+          tt[e] = qe * 255.0f + 0.5f;
+          n_exact++;
+        }
+        const float tc = fminf(fmaxf(tt[e], 0.0f), 255.0f);
+        w |= (__float_as_uint(__fadd_rz(tc, 8388608.0f)) & 0xffu) << (8 * j);
+      }
+    }
+    o[f] = w;
+  }
+  if (exact_count && n_exact) atomicAdd(exact_count, n_exact);
+}
+
+// diagnostic: out[i] = |lg2.approx(in[i]) - float(log2(double(in[i])))| / lg2_fast_bound(lg2.approx(in[i]))
+__global__ void k_log2_fast_probe(unsigned first_bits, unsigned count, float* __restrict__ worst, const double* __restrict__ tab_g) {
+  __shared__ double2 tab[128];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) tab[i] = make_double2(tab_g[i], tab_g[128 + i]);
+  __syncthreads();
+  float w = 0.0f;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const float q = __uint_as_float(first_bits + i);
+    const float a = lg2_fast(q), e = (float)log2_core(q, tab);
+    w = fmaxf(w, fabsf(a - e) / lg2_fast_bound(a));
+  }
+  for (int o = 16; o; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned*>(worst), __float_as_uint(w));   // w >= 0: bit order == value order
 }
 
 // ---- convertYuv 4:2:0 (transformYuv420, gainmapmath.cpp:686-726), in place -----------------------
@@ -620,13 +829,13 @@ struct FastLaunch {
   size_t smem;
   cudaStream_t s;
 };
-template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED>
-cudaError_t launch_kernel(const GainmapGenParams& p, const FastLaunch& L) {
+template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, bool QMODE>
+cudaError_t launch_kernel_q(const GainmapGenParams& p, const FastLaunch& L) {
   // persistent grid = the CTAs that are co-resident (asked once per instantiation and device)
   static int resident[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto fn = k_gainmap_fast<ONEPASS, NCH, GAMUT, LIMITED>;
+  auto fn = k_gainmap_fast<ONEPASS, NCH, GAMUT, LIMITED, QMODE>;
   if (dev < 0 || dev >= 64) dev = 0;
   if (!resident[dev]) {
     int per_sm = 0, sms = 0;
@@ -640,12 +849,12 @@ cudaError_t launch_kernel(const GainmapGenParams& p, const FastLaunch& L) {
   fn<<<ctas, dim3(64, 4), L.smem, L.s>>>(p, L.tab, L.tiles_x, L.ntiles, L.sched, kNegZero2);
   return cudaGetLastError();
 }
-template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, int S>
-cudaError_t launch_scaled(const GainmapGenParams& p, const FastLaunch& L) {
+template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, int S, bool QMODE>
+cudaError_t launch_scaled_q(const GainmapGenParams& p, const FastLaunch& L) {
   static int resident[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto fn = k_gainmap_scaled<ONEPASS, NCH, GAMUT, LIMITED, S>;
+  auto fn = k_gainmap_scaled<ONEPASS, NCH, GAMUT, LIMITED, S, QMODE>;
   if (dev < 0 || dev >= 64) dev = 0;
   if (!resident[dev]) {
     int per_sm = 0, sms = 0;
@@ -659,6 +868,16 @@ cudaError_t launch_scaled(const GainmapGenParams& p, const FastLaunch& L) {
   count_launches(1);
   fn<<<ctas, dim3(64, 4), L.smem, L.s>>>(p, L.tab);
   return cudaGetLastError();
+}
+template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED>
+cudaError_t launch_kernel(const GainmapGenParams& p, const FastLaunch& L) {
+  if (!ONEPASS && p.store_q) return launch_kernel_q<ONEPASS, NCH, GAMUT, LIMITED, !ONEPASS>(p, L);
+  return launch_kernel_q<ONEPASS, NCH, GAMUT, LIMITED, false>(p, L);
+}
+template <bool ONEPASS, int NCH, int GAMUT, bool LIMITED, int S>
+cudaError_t launch_scaled(const GainmapGenParams& p, const FastLaunch& L) {
+  if (!ONEPASS && p.store_q) return launch_scaled_q<ONEPASS, NCH, GAMUT, LIMITED, S, !ONEPASS>(p, L);
+  return launch_scaled_q<ONEPASS, NCH, GAMUT, LIMITED, S, false>(p, L);
 }
 template <bool ONEPASS, int NCH, int GAMUT>
 cudaError_t launch_range(const GainmapGenParams& p, const FastLaunch& L) {
@@ -683,6 +902,40 @@ bool affine_fast_eligible(const AffineParams& p) {
   if (((size_t)p.map_w * p.map_h * p.nch) & 3) return false;
   return !(((size_t)p.gains & 15) || ((size_t)p.dst & 3));
 }
+// q mode: pass 2 on the quotient plane.  exact_count (device word, may be null): how many values took the fp64 path.
+cudaError_t launch_affine_q(const AffineParams& p, const GainmapFinalizeParams& fin, unsigned* exact_count, cudaStream_t s) {
+  const double* tab = nullptr;
+  if (log2_table_dev(&tab) != E_OK) return cudaErrorUnknown;
+  const long long n4 = (long long)p.map_w * p.map_h * p.nch / 4;
+  long long ctas = (n4 + 192 * 4 - 1) / (192 * 4);
+  if (ctas > 148 * 10) ctas = 148 * 10;
+  if (ctas < 1) ctas = 1;
+  if (p.nch == 3) k_affine_q<3><<<(unsigned)ctas, 192, 0, s>>>(p, fin, n4, tab, exact_count, kNegZero2);
+  else k_affine_q<1><<<(unsigned)ctas, 192, 0, s>>>(p, fin, n4, tab, exact_count, kNegZero2);
+  return cudaGetLastError();
+}
+// start values of the q keys (and the tile-ticket word 8)
+__global__ void k_init_q_keys(unsigned* mm) {
+  const int t = threadIdx.x;
+  auto key = [](float f) { const unsigned b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); };
+  if (t < 3 || (t >= kQDarkKeys && t < kQDarkKeys + 3)) mm[t] = key(kQMinInit);
+  else if ((t >= 3 && t < 6) || (t >= kQDarkKeys + 3 && t < kQDarkKeys + 6)) mm[t] = key(0.0f);
+  else if (t == 8 || t == 9) mm[t] = 0;   // 8: tile tickets of k_gainmap_fast, 9: exact-path counter of k_affine_q
+}
+cudaError_t launch_init_q_keys(unsigned* minmax, cudaStream_t s) {
+  count_launches(1);
+  k_init_q_keys<<<1, 32, 0, s>>>(minmax);
+  return cudaGetLastError();
+}
+// worst[0] (device float, zeroed by the caller) = max over the `count` floats starting at bit pattern first_bits of
+// |lg2.approx - exact| / bound
+cudaError_t launch_log2_fast_probe(unsigned first_bits, unsigned count, float* d_worst, cudaStream_t s) {
+  const double* tab = nullptr;
+  if (log2_table_dev(&tab) != E_OK) return cudaErrorUnknown;
+  k_log2_fast_probe<<<148 * 8, 256, 0, s>>>(first_bits, count, d_worst, tab);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_affine_fast(const AffineParams& p, const GainmapFinalizeParams& fin, cudaStream_t s) {
   const long long n4 = (long long)p.map_w * p.map_h * p.nch / 4;
   long long ctas = (n4 + 192 * 4 - 1) / (192 * 4);

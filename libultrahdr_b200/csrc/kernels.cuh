@@ -36,6 +36,9 @@ struct GainmapGenParams {  // generateGainMap, lib/src/jpegr.cpp:530-1058
   // one-pass fast kernels: correctly rounded 1 / double(log2_max - log2_min), or 0 when that range is zero / not finite
   // (then the kernels divide); see encode_gain_norm in gainmap_fast.cu
   double inv_log2_range;
+  // two-pass fast kernels: the float plane receives the quotient (hdr+eps)/(sdr+eps) per value, negated when the
+  // pixel is dark (sdr < 2/255), instead of its log2; minmax holds q keys (k_affine_q finishes the job)
+  int store_q;
   uint8_t* dst;                     // RGB888 / Y400
   int dst_stride;                   // pixels
 };
@@ -170,6 +173,9 @@ cudaError_t launch_apply_fast(const ApplyParams& p, const float* gain_u8, cudaSt
 bool affine_fast_eligible(const AffineParams& p);
 // finalize (clamp / hints) + affine in one launch; also writes fin.minmax_f
 cudaError_t launch_affine_fast(const AffineParams& p, const GainmapFinalizeParams& fin, cudaStream_t s);
+cudaError_t launch_affine_q(const AffineParams& p, const GainmapFinalizeParams& fin, unsigned* exact_count, cudaStream_t s);
+cudaError_t launch_init_q_keys(unsigned* minmax, cudaStream_t s);
+cudaError_t launch_log2_fast_probe(unsigned first_bits, unsigned count, float* d_worst, cudaStream_t s);
 bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass);
 cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, unsigned* sched, cudaStream_t s);
 cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream_t s);

@@ -298,6 +298,40 @@ def test_generate_scaled_full_size(gpu, checker, w, h, scale, multi, preset):
     assert (g1 == g2).all(), int((g1 != g2).sum())
 
 
+def test_fast_log2_error_bound(gpu):
+    """Pass 2 of the two-pass fast path (k_affine_q) trusts lg2.approx to within kLg2Abs + |g| * kLg2Rel of the exact
+    float(log2(double(q))).  Checked here for EVERY float q in [2^-40, 2^40] (the quotient (hdr+1e-7)/(sdr+1e-7) lives in
+    [2^-31, 2^37]): the worst ratio error / bound must leave a factor 2."""
+    lib = gpu.lib
+    worst = C.c_float(-1.0)
+    first = (127 - 40) << 23
+    count = ((127 + 40) << 23) - first
+    assert lib.uhdr_b200_probe_log2_fast(C.c_uint(first), C.c_uint(count), C.byref(worst)) == 0, T.gpu_err(gpu)
+    assert 0.0 < worst.value <= 0.5, worst.value
+
+
+def test_two_pass_takes_the_exact_log2_only_near_byte_boundaries(gpu, checker):
+    """k_affine_q's screen: on noise (every gain value different) a small share of the values takes the fp64 path,
+    and the map is still bit exact (the other tests); on a constant image none has to."""
+    lib = gpu.lib
+
+    def stats():
+        st = (C.c_ulonglong * 2)()
+        lib.uhdr_b200_generate_stats(st)
+        return st[0], st[1]
+    w, h = 1280, 720
+    hdr, k1 = _hdr("noise", "p010", 2, A.CT_HLG, w, h)
+    sdr, k2 = _sdr("noise", 0, w, h)
+    v0, e0 = stats()
+    g1, m1 = gpu.generate(sdr, hdr)
+    v1, e1 = stats()
+    g2, m2 = checker.generate(sdr, hdr)
+    assert (g1 == g2).all() and T.md_equal(m1, m2)
+    assert v1 - v0 == w * h * 3, "the quotient-plane path did not run"
+    share = (e1 - e0) / float(v1 - v0)
+    assert 0.0 < share < 0.02, share
+
+
 def test_apply_8k(gpu, checker):
     """config 3 geometry: 7680x4320, RGBA8888 map at scale 1 -> RGBA half float, bit exact."""
     w, h = 7680, 4320
