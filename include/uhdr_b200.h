@@ -113,6 +113,13 @@ UHDR_EXTERN void uhdr_b200_generate_stats(unsigned long long out[2]);
  * |lg2.approx(x) - float(log2(double(x)))| / bound(x), the bound being the one pass 2 relies on (must stay <= 0.5:
  * a factor 2 to spare); host pointer. */
 UHDR_EXTERN int uhdr_b200_probe_log2_fast(unsigned first_bits, unsigned count, float* worst);
+/* toneMap's fast kernel screens srgbOetf's powf: a 2x2 pixel group first runs with a hardware fp32 approximation and is
+ * redone with the exact routine only if one of its six 8-bit codes could depend on the difference.
+ * out[0] = groups processed since process start, out[1] = groups redone (current device). */
+UHDR_EXTERN void uhdr_b200_tonemap_stats(unsigned long long out[2]);
+/* diagnostic: worst[0] = max |approximate pow(e, 1/2.4) - the exact one| over the `count` floats whose bit patterns
+ * start at first_bits (the screen relies on <= 3e-7 for e in (0.0031308, 1]; must measure <= 1.5e-7); host pointer. */
+UHDR_EXTERN int uhdr_b200_probe_pow_fast(unsigned first_bits, unsigned count, float* worst);
 /* diagnostic: out[i] = float(log2(double(in[i]))) exactly as the gain-map kernels evaluate computeGain's
  * log2 (gainmapmath.cpp:773-782); host pointers. */
 UHDR_EXTERN int uhdr_b200_probe_log2(const float* in, float* out, int n);

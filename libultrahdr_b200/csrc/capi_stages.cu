@@ -72,6 +72,21 @@ UHDR_API int uhdr_b200_probe_log2_fast(unsigned first_bits, unsigned count, floa
   return ws->sync();
 }
 
+UHDR_API void uhdr_b200_tonemap_stats(unsigned long long out[2]) {
+  if (out) tonemap_screen_stats(out);
+}
+
+UHDR_API int uhdr_b200_probe_pow_fast(unsigned first_bits, unsigned count, float* worst) {
+  Workspace* ws = tls_workspace();
+  if (!ws || !worst) return E_ERROR;
+  float* d_w = (float*)ws->dalloc(64);
+  if (!d_w) return E_MEM;
+  CUDA_TRY(cudaMemsetAsync(d_w, 0, 4, ws->stream()));
+  CUDA_TRY(launch_pow_fast_probe(first_bits, count, d_w, ws->stream()));
+  CUDA_TRY(cudaMemcpyAsync(worst, d_w, 4, cudaMemcpyDeviceToHost, ws->stream()));
+  return ws->sync();
+}
+
 UHDR_API int uhdr_b200_probe_powf(const float* in, float y, float* out, int n) {
   Workspace* ws = tls_workspace();
   if (!ws) return E_ERROR;

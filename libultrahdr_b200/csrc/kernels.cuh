@@ -176,6 +176,8 @@ cudaError_t launch_affine_fast(const AffineParams& p, const GainmapFinalizeParam
 cudaError_t launch_affine_q(const AffineParams& p, const GainmapFinalizeParams& fin, unsigned* exact_count, cudaStream_t s);
 cudaError_t launch_init_q_keys(unsigned* minmax, cudaStream_t s);
 cudaError_t launch_log2_fast_probe(unsigned first_bits, unsigned count, float* d_worst, cudaStream_t s);
+cudaError_t launch_pow_fast_probe(unsigned first_bits, unsigned count, float* d_worst, cudaStream_t s);
+void tonemap_screen_stats(unsigned long long out[2]);
 bool gainmap_fast_eligible(const GainmapGenParams& p, bool onepass);
 cudaError_t launch_gainmap_fast(const GainmapGenParams& p, bool onepass, unsigned* sched, cudaStream_t s);
 cudaError_t launch_log2_probe(const float* d_in, float* d_out, int n, cudaStream_t s);

@@ -298,6 +298,39 @@ def test_generate_scaled_full_size(gpu, checker, w, h, scale, multi, preset):
     assert (g1 == g2).all(), int((g1 != g2).sum())
 
 
+def test_fast_pow_error_bound(gpu):
+    """toneMap's screen (tonemap_fast.cu) trusts ex2.approx(lg2.approx(e) / 2.4) to within 3e-7 of the exact powf
+    restatement for every float e in (0.0031308, 1]: all of them are compared on the device, and the worst case must
+    leave a factor 2."""
+    import struct
+    lib = gpu.lib
+    first = struct.unpack("<I", struct.pack("<f", 0.0031308))[0]
+    last = struct.unpack("<I", struct.pack("<f", 1.0))[0]
+    worst = C.c_float(-1.0)
+    assert lib.uhdr_b200_probe_pow_fast(C.c_uint(first), C.c_uint(last - first + 1), C.byref(worst)) == 0, T.gpu_err(gpu)
+    assert 0.0 < worst.value <= 1.5e-7, worst.value
+
+
+def test_tonemap_redoes_only_groups_near_a_rounding_boundary(gpu, checker):
+    lib = gpu.lib
+
+    def stats():
+        st = (C.c_ulonglong * 2)()
+        lib.uhdr_b200_tonemap_stats(st)
+        return st[0], st[1]
+    w, h = 1280, 720
+    hb = T.make_p010(w, h, "noise")
+    hdr, k1 = A.p010_image(hb, w, h, A.CG_BT2100, A.CT_HLG, A.CR_LIMITED)
+    g0, e0 = stats()
+    a = gpu.tonemap(hdr)[0]
+    g1, e1 = stats()
+    b = checker.tonemap(hdr)[0]
+    assert (a == b).all(), int((a != b).sum())
+    assert g1 - g0 == w * h // 4, "the fast tone-map kernel did not run"
+    share = (e1 - e0) / float(g1 - g0)
+    assert 0.0 < share < 0.05, share
+
+
 def test_fast_log2_error_bound(gpu):
     """Pass 2 of the two-pass fast path (k_affine_q) trusts lg2.approx to within kLg2Abs + |g| * kLg2Rel of the exact
     float(log2(double(q))).  Checked here for EVERY float q in [2^-40, 2^40] (the quotient (hdr+1e-7)/(sdr+1e-7) lives in
