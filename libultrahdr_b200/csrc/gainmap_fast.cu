@@ -85,6 +85,40 @@ __device__ __forceinline__ float encode_gain_norm(double log2_gain, const Gainma
 constexpr float kQMinInit = 3.0e38f;
 constexpr int kQDarkKeys = 16;   // minmax[16..18] min q of dark pixels, [19..21] max q of dark pixels ([0..5]: the others)
 
+constexpr float kLg2Abs = 8e-7f, kLg2Rel = 3.2e-7f, kAffineRound = 2e-4f;   // measured worst case: 0.35 of this bound
+
+__device__ __forceinline__ float lg2_fast(float x) {
+  float r;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_fast_bound(float g) { return kLg2Abs + fabsf(g) * kLg2Rel; }
+
+// one-pass code of a gain: trunc(encode_gain_norm(log2(gain)) * 255).  Only the byte leaves the kernel: it is taken from
+// lg2.approx and float arithmetic unless t lies within `thr` of an integer, thr bounding everything the short cut can
+// differ by (lg2_fast_bound scaled by 255 / range, plus 1.5e-4 for the float roundings on either side); then the fp64
+// path decides.  thr <= 0: always exact (degenerate range).
+// Gains clamped to min_boost / max_boost (every pixel that is not brighter in the HDR rendition, for one) sit exactly
+// on t = 0 / 255: their codes come from two exact evaluations per thread (code_lo, code_hi), not from the screen.
+__device__ __forceinline__ unsigned encode_gain_code(float gain, const GainmapGenParams& p, float inv_range_f, float thr,
+                                                     unsigned code_lo, unsigned code_hi, const double2* __restrict__ tab) {
+  if (gain <= p.min_boost) return code_lo;
+  if (gain >= p.max_boost) return code_hi;
+  float t = 0.0f;
+  bool exact = !(thr > 0.0f);
+  if (!exact) {
+    t = ((lg2_fast(gain) - p.log2_min) * inv_range_f) * 255.0f;
+    exact = fabsf(t - rintf(t)) < thr;
+  }
+  if (exact) t = encode_gain_norm(log2_core(gain, tab), p) * 255.0f;
+  return (unsigned)__float2int_rz(t) & 0xff;
+}
+__device__ __forceinline__ float onepass_threshold(const GainmapGenParams& p, float inv_range_f) {
+  if (p.inv_log2_range == 0.0) return -1.0f;
+  const float gmax = fmaxf(fabsf(p.log2_min), fabsf(p.log2_max));
+  return 255.0f * (kLg2Abs + gmax * kLg2Rel) * fabsf(inv_range_f) * 1.0001f + 1.5e-4f;   // six float roundings of 6e-8 on t <= 255: 9.2e-5
+}
+
 // ---- shared memory ------------------------------------------------------------------------------
 struct GmSmem {
   double2 log2tab[128];  // {invc, logc}
@@ -172,6 +206,12 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
   float dmn[3] = {kQMinInit, kQMinInit, kQMinInit}, dmx[3] = {0.0f, 0.0f, 0.0f};
   const V2 k8184 = bc(8184.0f), k32760 = bc(hscale8), keps = bc(1e-7f);
   const V2 snits = bc(p.sdr_nits), hnits = bc(p.hdr_nits);
+  const float inv_range_f = (float)p.inv_log2_range, thr1 = onepass_threshold(p, inv_range_f);   // one-pass screen
+  unsigned code_lo = 0, code_hi = 0;
+  if (ONEPASS) {   // exact codes of the two clamp values (tables are staged: see the barrier above)
+    code_lo = (unsigned)__float2int_rz(encode_gain_norm(log2_core(p.min_boost, sm.log2tab), p) * 255.0f) & 0xff;
+    code_hi = (unsigned)__float2int_rz(encode_gain_norm(log2_core(p.max_boost, sm.log2tab), p) * 255.0f) & 0xff;
+  }
 #pragma unroll 1
   for (int it = 0;; it++) {
     const int t = s_tile[it & 1];
@@ -286,8 +326,7 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_fast(const GainmapGenParams 
                 if (sv2[e] > 0.0f) gain = div_pos(hv2[e], sv2[e]);
                 if (gain < p.min_boost) gain = p.min_boost;
                 if (gain > p.max_boost) gain = p.max_boost;
-                const float gn = encode_gain_norm(log2_core(gain, sm.log2tab), p);
-                const unsigned code = (unsigned)__float2int_rz(gn * 255.0f) & 0xff;
+                const unsigned code = encode_gain_code(gain, p, inv_range_f, thr1, code_lo, code_hi, sm.log2tab);
                 const int bi = (2 * k + e) * NCH + c;
                 bout[bi >> 2] |= code << (8 * (bi & 3));
               }
@@ -389,6 +428,12 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_scaled(const GainmapGenParam
   float mn[3] = {mn0, mn0, mn0}, mx[3] = {mx0, mx0, mx0};
   float dmn[3] = {kQMinInit, kQMinInit, kQMinInit}, dmx[3] = {0.0f, 0.0f, 0.0f};
   const int tiles_x = (p.map_w + 63) / 64, ntiles = tiles_x * ((p.map_h + 3) / 4);
+  const float inv_range_f = (float)p.inv_log2_range, thr1 = onepass_threshold(p, inv_range_f);   // one-pass screen
+  unsigned code_lo = 0, code_hi = 0;
+  if (ONEPASS) {   // exact codes of the two clamp values (tables are staged: see the barrier above)
+    code_lo = (unsigned)__float2int_rz(encode_gain_norm(log2_core(p.min_boost, sm.log2tab), p) * 255.0f) & 0xff;
+    code_hi = (unsigned)__float2int_rz(encode_gain_norm(log2_core(p.max_boost, sm.log2tab), p) * 255.0f) & 0xff;
+  }
 #pragma unroll 1
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
@@ -487,8 +532,7 @@ __global__ void __launch_bounds__(256, 4) k_gainmap_scaled(const GainmapGenParam
         if (s3[c] > 0.0f) gain = div_pos(h3[c], s3[c]);
         if (gain < p.min_boost) gain = p.min_boost;
         if (gain > p.max_boost) gain = p.max_boost;
-        const float gn = encode_gain_norm(log2_core(gain, sm.log2tab), p);
-        p.dst[((size_t)y * p.dst_stride + x) * NCH + c] = (uint8_t)((unsigned)__float2int_rz(gn * 255.0f) & 0xff);
+        p.dst[((size_t)y * p.dst_stride + x) * NCH + c] = (uint8_t)encode_gain_code(gain, p, inv_range_f, thr1, code_lo, code_hi, sm.log2tab);
       } else {         // computeGain :773-782
         const float q = div_pos(h3[c] + 1e-7f, s3[c] + 1e-7f);
         const bool dark = s3[c] < 2.f / 255.0f;
@@ -582,15 +626,6 @@ __global__ void __launch_bounds__(192) k_affine_fast(const AffineParams p, const
 // trunc(clamp(t)).  When t is further than the bound (plus the float roundings of the map itself) from the nearest
 // integer, the exact t truncates to the same byte; otherwise the value takes the exact path.  On natural content a few
 // values in ten thousand do.
-constexpr float kLg2Abs = 8e-7f, kLg2Rel = 3.2e-7f, kAffineRound = 2e-4f;   // measured worst case: 0.35 of this bound
-
-__device__ __forceinline__ float lg2_fast(float x) {
-  float r;
-  asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float lg2_fast_bound(float g) { return kLg2Abs + fabsf(g) * kLg2Rel; }
-
 // log2 with the table in global memory (a dozen evaluations per thread at kernel start)
 __device__ __forceinline__ float log2f_exact_g(float q, const double* __restrict__ tab_g) {
   const unsigned ix = __float_as_uint(q);
