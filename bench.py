@@ -528,7 +528,7 @@ def bench_b200(args, rank, world):
     except OSError:
         pass
     if world == 1:
-        cpu = cpu_baseline(frames)
+        cpu = cpu_baseline(frames, reps=2)   # two frames per host thread back to back, like the reference arm
     else:
         cpu = {"value": None, "unit": "MPix/s", "cores": 0, "kind": "reference", "sample": "timed at N=1 only"}
 
