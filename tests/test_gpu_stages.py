@@ -95,6 +95,33 @@ def test_generate_rgba8888_sdr_and_boost_hints(gpu, checker):
         assert (g1 == g2).all() and T.md_equal(m1, m2), kw
 
 
+def test_generate_fast_path_hints_and_degenerate_ranges(gpu, checker):
+    """The quotient-plane two-pass path (P010 + YUV420) with content-boost hints (they clamp min / max after the
+    extremes were found, which makes the affine range small and many values saturate), with constant images (range
+    forced to 0.1 by the |max - min| < eps rule), with an all-dark SDR image (only the capped class exists), at
+    scales 1 / 4 and both channel counts."""
+    bad = []
+    for kind, scale, multi in itertools.product(["noise", "smooth", "black", "white"], [1, 4], [0, 1]):
+        hdr, k1 = _hdr(kind, "p010", 2, A.CT_PQ)
+        sdr, k2 = _sdr(kind, 0)
+        for kw in ({}, {"min_content_boost": 0.5, "max_content_boost": 6.0}, {"min_content_boost": 1.0, "max_content_boost": 1.25},
+                   {"max_content_boost": 0.9, "min_content_boost": 0.8}, {"target_disp_peak_nits": 1600.0}):
+            cfg = A.default_gm_config(scale_factor=scale, multichannel=multi, **kw)
+            g1, m1 = gpu.generate(sdr, hdr, cfg)
+            g2, m2 = checker.generate(sdr, hdr, cfg)
+            if not ((g1 == g2).all() and T.md_equal(m1, m2)):
+                bad.append((kind, scale, multi, kw, int((g1 != g2).sum())))
+    # dark HDR over bright SDR and the reverse: every gain at one end
+    for hk, sk in (("black", "white"), ("white", "black")):
+        hdr, k1 = _hdr(hk, "p010", 2, A.CT_HLG)
+        sdr, k2 = _sdr(sk, 0)
+        g1, m1 = gpu.generate(sdr, hdr)
+        g2, m2 = checker.generate(sdr, hdr)
+        if not ((g1 == g2).all() and T.md_equal(m1, m2)):
+            bad.append((hk, sk, int((g1 != g2).sum())))
+    assert not bad, bad[:8]
+
+
 def _map_for(gpu_or_chk, kind, multi, scale):
     hdr, k1 = _hdr(kind, "p010", 2, A.CT_HLG)
     sdr, k2 = _sdr(kind, 0)
