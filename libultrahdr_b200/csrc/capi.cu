@@ -522,7 +522,7 @@ UHDR_API uhdr_error_info_t uhdr_decode(uhdr_codec_private_t* dec) {
   h->gainmap_desc.stride[0] = h->info.gm_width;
   h->codec.set_lazy_gainmap(true);  // the map leaves HBM only if uhdr_get_decoded_gainmap_image() is called
   int rc = h->codec.decode(h->stream.data(), h->stream.size(), h->out_ct, h->out_fmt, h->max_boost, &h->decoded_desc,
-                           &h->gainmap_desc, nullptr);
+                           &h->gainmap_desc, nullptr, &h->info);   // uhdr_dec_probe above already located the two images
   h->status = from_rc(rc);
   return h->status;
 }

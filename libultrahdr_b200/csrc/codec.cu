@@ -412,13 +412,20 @@ int JpegRCodec::probe(const uint8_t* data, size_t size, DecodedInfo* info) {
 }
 
 int JpegRCodec::decode(const uint8_t* data, size_t size, int out_ct, int out_fmt, float max_display_boost,
-                       uhdr_raw_image_t* dest, uhdr_raw_image_t* gainmap_out, uhdr_gainmap_metadata_t* md_out) {
+                       uhdr_raw_image_t* dest, uhdr_raw_image_t* gainmap_out, uhdr_gainmap_metadata_t* md_out,
+                       const DecodedInfo* probed) {
   (void)out_fmt;
   PhaseTrace tr;
   ws_.rewind();
   size_t po, pl, go, gl;
-  int rc = split_jpegr(data, size, &po, &pl, &go, &gl);
+  int rc = E_OK;
+  if (probed && probed->base_len && probed->gainmap_len && probed->gainmap_off + probed->gainmap_len <= size) {
+    po = probed->base_off; pl = probed->base_len; go = probed->gainmap_off; gl = probed->gainmap_len;
+  } else {
+    rc = split_jpegr(data, size, &po, &pl, &go, &gl);
+  }
   if (rc) return rc;
+  tr.mark("container split");
   const bool sdr_only = out_ct == UHDR_CT_SRGB;  // :1479-1481, :1520-1523: the base image as RGBA8888, no gain map applied
   DevImage sdr, map;
   JpegHeader ph, gh;

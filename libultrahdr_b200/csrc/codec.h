@@ -66,8 +66,10 @@ class JpegRCodec {
   int probe(const uint8_t* data, size_t size, DecodedInfo* info);
   // JpegR::decodeJPEGR (jpegr.cpp:1469-1531).  dest: host descriptor with planes allocated by the
   // caller (fmt/stride set); gainmap_out optional host descriptor (planes allocated, Y400/RGBA8888).
+  // `probed`: the result of probe() on the same stream (saves the second scan of the container), or null.
   int decode(const uint8_t* data, size_t size, int out_ct, int out_fmt, float max_display_boost,
-             uhdr_raw_image_t* dest, uhdr_raw_image_t* gainmap_out, uhdr_gainmap_metadata_t* md_out);
+             uhdr_raw_image_t* dest, uhdr_raw_image_t* gainmap_out, uhdr_gainmap_metadata_t* md_out,
+             const DecodedInfo* probed = nullptr);
 
   // With gainmap_out->planes[0] == nullptr and lazy_gainmap set, decode() only fills the descriptor's
   // geometry and keeps the map in HBM; fetch_gainmap() copies it out when somebody asks for it
