@@ -547,7 +547,7 @@ def bench_b200(args, rank, world):
                 "d2h_bytes_per_step": int(sum(e2e_out)), "ms_per_step": round(t_e2e / args.steps * 1e3, 3),
                 "h2d_achieved_gbs": round(world * in_bytes / (t_e2e / args.steps) / 1e9, 1),
                 "h2d_achieved_gbs_per_gpu": round(in_bytes / (t_e2e / args.steps) / 1e9, 1), "pcie_probe": pcie,
-                "frac_of_concurrent_h2d_probe": (round(world * in_bytes / (t_e2e / args.steps) / 1e9 / pcie["h2d_gbs_sum"], 3)
+                "frac_of_h2d_probe": (round(world * in_bytes / (t_e2e / args.steps) / 1e9 / pcie["h2d_gbs_sum"], 3)
                                                  if world > 1 and pcie.get("h2d_gbs_sum") else
                                                  (round(in_bytes / (t_e2e / args.steps) / 1e9 / pcie["h2d_gbs"], 3) if pcie.get("h2d_gbs") else None)),
                 "bound": "pcie h2d: 37.3 MB of raw pixels enter per 4K frame, 2.3 MB of JPEG/R leave"},

@@ -943,7 +943,19 @@ cudaError_t launch_affine_q(const AffineParams& p, const GainmapFinalizeParams& 
   if (log2_table_dev(&tab) != E_OK) return cudaErrorUnknown;
   const long long n4 = (long long)p.map_w * p.map_h * p.nch / 4;
   long long ctas = (n4 + 192 * 4 - 1) / (192 * 4);
-  if (ctas > 148 * 10) ctas = 148 * 10;
+  // grid-stride walk: exactly the co-resident CTAs (a partial second wave would cost a whole one)
+  static int resident[2] = {0, 0};
+  int& res = resident[p.nch == 3 ? 1 : 0];
+  if (!res) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const cudaError_t oe = p.nch == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_affine_q<3>, 192, 0)
+                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_affine_q<1>, 192, 0);
+    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+    res = per_sm * (sms > 0 ? sms : 148);
+  }
+  if (ctas > res) ctas = res;
   if (ctas < 1) ctas = 1;
   if (p.nch == 3) k_affine_q<3><<<(unsigned)ctas, 192, 0, s>>>(p, fin, n4, tab, exact_count, kNegZero2);
   else k_affine_q<1><<<(unsigned)ctas, 192, 0, s>>>(p, fin, n4, tab, exact_count, kNegZero2);
