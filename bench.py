@@ -141,17 +141,26 @@ def load_api(path):
     return T.UhdrApi(lib), lib
 
 
-def run_threads(n, fn):
+def run_threads(n, fn, before_start=None):
+    """n host threads run fn(i).  With before_start: the threads are created first and wait at a gate; before_start()
+    runs (synchronise the device / the ranks, read the clock), then the gate opens -- thread creation stays outside
+    the timed region, the work does not."""
     errs = []
+    gate = threading.Barrier(n + 1) if before_start else None
 
     def wrap(i):
         try:
+            if gate:
+                gate.wait()
             fn(i)
         except Exception as e:  # noqa: BLE001
             errs.append(repr(e))
     th = [threading.Thread(target=wrap, args=(i,)) for i in range(n)]
     for t in th:
         t.start()
+    if gate:
+        before_start()
+        gate.wait()
     for t in th:
         t.join()
     if errs:
@@ -335,24 +344,28 @@ def bench_b200(args, rank, world):
     # K steps = K passes over the rank's F frames.  The host threads (one per encoder slot) are started once per
     # timed region and walk their share of every step back to back: a thread join after every step would idle the
     # device for one encode latency per step, which is an artefact of the harness, not of the library.
-    def resident_steps(k):
+    def resident_steps(k, before_start=None):
         def work(s):
             for _ in range(k):
                 for i in range(s, F, slots_n):
                     handles[i].rearm()
                     out_bytes[i] = handles[i].encode()
-        run_threads(slots_n, work)
+        run_threads(slots_n, work, before_start)
 
     resident_steps(args.warmup)
     lib.uhdr_b200_set_kernel_timing(0)
     sampler = ClockSampler(local, nvh)
     sampler.start()
-    barrier()
-    l0 = lib.uhdr_b200_kernel_launches()
-    t0 = time.perf_counter()
-    resident_steps(args.steps)
+    clock = {}
+
+    def open_timed_region():
+        barrier()
+        clock["l0"] = lib.uhdr_b200_kernel_launches()
+        clock["t0"] = time.perf_counter()
+    resident_steps(args.steps, open_timed_region)
     torch.cuda.synchronize()
-    t_res = max_over_ranks(time.perf_counter() - t0)
+    t_res = max_over_ranks(time.perf_counter() - clock["t0"])
+    l0 = clock["l0"]
     launches = lib.uhdr_b200_kernel_launches() - l0
     lib.uhdr_b200_set_kernel_timing(1)
     barrier()
@@ -377,7 +390,7 @@ def bench_b200(args, rank, world):
     e2e_slots = [EncoderSlot(lib) for _ in range(slots_n)]
     e2e_out = [0] * F
 
-    def e2e_steps(k):
+    def e2e_steps(k, before_start=None):
         def work(s):
             sl = e2e_slots[s]
             for _ in range(k):
@@ -385,14 +398,16 @@ def bench_b200(args, rank, world):
                     sl.reset()
                     sl.set_inputs(descs[i][0], descs[i][1])
                     e2e_out[i] = sl.encode()
-        run_threads(slots_n, work)
+        run_threads(slots_n, work, before_start)
 
     e2e_steps(max(1, args.warmup // 2))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps(args.steps)
+
+    def open_e2e_region():
+        barrier()
+        clock["t0"] = time.perf_counter()
+    e2e_steps(args.steps, open_e2e_region)
     torch.cuda.synchronize()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    t_e2e = max_over_ranks(time.perf_counter() - clock["t0"])
     e2e_value = world * F * args.steps * MPIX_4K / t_e2e
 
     # ---------------- decode arm of the metric (config 3): 8K JPEG/R -> RGBA half float ------------
