@@ -615,19 +615,16 @@ UHDR_API int uhdr_b200_jpeg_encode(const uhdr_raw_image_t* img, int quality, con
   int rc = upload_image(c->ws(), *img, &d);
   if (rc) return rc;
   JpegEncodeJob job;
-  const bool dev = gpu_entropy_available();
-  rc = jpeg_forward_dev(c->ws(), d, quality, &job, dev);
+  rc = jpeg_forward_dev(c->ws(), d, quality, &job, /*zigzag=*/true);
   if (rc) return rc;
-  rc = dev ? jpeg_entropy_dev(c->ws(), &job) : jpeg_fetch_coefs(c->ws(), &job);
+  rc = jpeg_entropy_dev(c->ws(), &job);
   if (rc) return rc;
   rc = c->ws().sync();
   if (rc) return rc;
-  if (dev) {
-    rc = jpeg_entropy_fetch(c->ws(), &job);
-    if (rc) return rc;
-    rc = c->ws().sync();
-    if (rc) return rc;
-  }
+  rc = jpeg_entropy_fetch(c->ws(), &job);
+  if (rc) return rc;
+  rc = c->ws().sync();
+  if (rc) return rc;
   std::vector<uint8_t> s;
   const bool gm = img->fmt == UHDR_IMG_FMT_24bppRGB888 || img->fmt == UHDR_IMG_FMT_8bppYCbCr400;
   rc = jpeg_finish_stream(job, icc, icc_size, gm ? jpeg_gainmap_comment() : nullptr, &s);

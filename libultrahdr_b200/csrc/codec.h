@@ -95,6 +95,5 @@ class JpegRCodec {
   DevImage last_map_{};
 };
 
-bool gpu_entropy_available();
 
 }  // namespace uhdr_b200

@@ -499,7 +499,6 @@ static int device_books(const uint32_t** out) {
 
 }  // namespace
 
-bool gpu_entropy_available() { return true; }
 
 int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job) {
   const JpegFrame& fr = job->frame;

@@ -1,9 +1,9 @@
 // Baseline JPEG codec of libuhdr_b200: the B200 counterpart of JpegEncoderHelper /
 // JpegDecoderHelper (lib/src/jpegencoderhelper.cpp, lib/src/jpegdecoderhelper.cpp), which in the
 // reference are thin drivers over libjpeg-turbo.  Block arithmetic (colour conversion, level
-// shift, islow FDCT/IDCT, quantise/dequantise) runs in CUDA kernels (kernels.cu); entropy coding
-// runs either on the device (huffman.cu) or on the host (this file) and the marker layer is host
-// code.  Streams are byte-identical to what libjpeg-turbo emits for the reference's settings
+// shift, islow FDCT/IDCT, quantise/dequantise) runs in CUDA kernels; entropy coding runs on the device
+// (huffman.cu; decoding: huffdec.cu, with a host decoder in jpeg_host.cpp for the streams it declines) and the
+// marker layer is host code.  Streams are byte-identical to what libjpeg-turbo emits for the reference's settings
 // (jpeg_set_defaults + jpeg_set_quality(q, TRUE), JDCT_ISLOW, default Huffman tables, one
 // interleaved scan, no restart markers).
 #pragma once
@@ -50,7 +50,6 @@ struct JpegEncodeJob {
   unsigned* h_scan_bytes = nullptr;  // pinned control words: [3] = bytes, [4] = overflow flag
   size_t scan_capacity = 0;
   bool zigzag = false;            // d_coefs hold zigzag-ordered blocks
-  int16_t* h_coefs[3] = {nullptr, nullptr, nullptr};  // pinned (host Huffman path)
 };
 
 // Enqueue the block stage for `img` (device image): colour conversion (RGB888 only), level
@@ -61,8 +60,6 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
 int jpeg_entropy_dev(Workspace& ws, JpegEncodeJob* job);
 // second phase, once the stream was synchronised and the sizes are on the host
 int jpeg_entropy_fetch(Workspace& ws, JpegEncodeJob* job);
-// Enqueue D2H of coefficients for the host entropy coder.
-int jpeg_fetch_coefs(Workspace& ws, JpegEncodeJob* job);
 // After stream sync: assemble SOI..EOI.  `comment` != nullptr adds the COM marker the reference
 // writes for gain-map images (jpegencoderhelper.cpp:205-211).
 int jpeg_finish_stream(const JpegEncodeJob& job, const void* icc, size_t icc_size,
@@ -76,8 +73,6 @@ int jpeg_finish_stream_into(const JpegEncodeJob& job, const void* icc, size_t ic
 // pointer into the pinned buffer the device wrote it to.  No copy of the segment is made.
 int jpeg_stream_pieces(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment, uint8_t* head,
                        size_t head_cap, size_t* head_len, const uint8_t** scan, size_t* scan_len);
-// host Huffman coder over [block][64] coefficient arrays
-void jpeg_host_entropy(const JpegFrame& f, const int16_t* const coefs[3], std::vector<uint8_t>* scan);
 
 // ---- decoder -----------------------------------------------------------------------------------
 struct JpegMarker { uint8_t id; size_t offset, length; };

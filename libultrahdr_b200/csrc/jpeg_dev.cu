@@ -76,16 +76,6 @@ int jpeg_forward_dev(Workspace& ws, const DevImage& img, int quality, JpegEncode
   return E_OK;
 }
 
-int jpeg_fetch_coefs(Workspace& ws, JpegEncodeJob* job) {
-  const JpegFrame& f = job->frame;
-  for (int c = 0; c < f.ncomp; c++) {
-    job->h_coefs[c] = (int16_t*)ws.halloc(f.blocks(c) * 128);
-    if (!job->h_coefs[c]) return E_MEM;
-    CUDA_TRY(cudaMemcpyAsync(job->h_coefs[c], job->d_coefs[c], f.blocks(c) * 128, cudaMemcpyDeviceToHost, ws.stream()));
-  }
-  return E_OK;
-}
-
 int jpeg_idct_dev(Workspace& ws, const JpegHeader& h, int16_t* const d_coefs[3], uint8_t* d_planes[3], int plane_stride[3]) {
   const JpegFrame& f = h.frame;
   for (int c = 0; c < f.ncomp; c++) {

@@ -208,104 +208,16 @@ static void write_headers(const JpegFrame& f, const void* icc, size_t icc_size, 
   o.u8(0);
 }
 
-// ---- host entropy coder ---------------------------------------------------------------------------
-namespace {
-struct BitPacker {
-  std::vector<uint8_t>& out;
-  uint64_t acc = 0;
-  int fill = 0;  // bits held in acc
-  void put(uint32_t bits, int n) {
-    acc = (acc << n) | (bits & ((1u << n) - 1u));
-    fill += n;
-    while (fill >= 8) {
-      const uint8_t b = (uint8_t)(acc >> (fill - 8));
-      out.push_back(b);
-      if (b == 0xFF) out.push_back(0);
-      fill -= 8;
-    }
-  }
-  void finish() {  // jchuff.c flush_bits: fill the last byte with ones
-    if (fill) put(0x7F, 8 - fill);
-  }
-};
-inline int magnitude_bits(int v) { return v ? 32 - __builtin_clz((unsigned)v) : 0; }
-
-void code_block(BitPacker& bp, const int16_t* blk, int& pred, const Codebook& dc, const Codebook& ac) {
-  int diff = blk[0] - pred;
-  pred = blk[0];
-  int mag = diff < 0 ? -diff : diff, low = diff < 0 ? diff - 1 : diff;
-  int nb = magnitude_bits(mag);
-  bp.put(dc.e[nb] >> 8, dc.e[nb] & 0xff);
-  if (nb) bp.put((uint32_t)low, nb);
-  int run = 0;
-  for (int k = 1; k < 64; k++) {
-    const int v = blk[kZigzag[k]];
-    if (!v) { run++; continue; }
-    for (; run > 15; run -= 16) bp.put(ac.e[0xF0] >> 8, ac.e[0xF0] & 0xff);
-    mag = v < 0 ? -v : v;
-    low = v < 0 ? v - 1 : v;
-    nb = magnitude_bits(mag);
-    const uint32_t e = ac.e[(run << 4) | nb];
-    bp.put(e >> 8, e & 0xff);
-    bp.put((uint32_t)low, nb);
-    run = 0;
-  }
-  if (run) bp.put(ac.e[0] >> 8, ac.e[0] & 0xff);
-}
-}  // namespace
-
-void jpeg_host_entropy(const JpegFrame& f, const int16_t* const coefs[3], std::vector<uint8_t>* scan) {
-  static const Codebook cb[4] = {make_codebook(kStdHuff[0]), make_codebook(kStdHuff[1]),
-                                 make_codebook(kStdHuff[2]), make_codebook(kStdHuff[3])};
-  BitPacker bp{*scan};
-  int pred[3] = {0, 0, 0};
-  int16_t filler[64];
-  for (int my = 0; my < f.mcu_rows; my++)
-    for (int mx = 0; mx < f.mcus_per_row; mx++) {
-      int last_dc = 0;  // jccoefct.c: dummy blocks repeat the DC of the block coded before them
-      for (int c = 0; c < f.ncomp; c++) {
-        const JpegComp& k = f.comp[c];
-        const int mw = f.ncomp == 1 ? 1 : k.h_samp, mh = f.ncomp == 1 ? 1 : k.v_samp;
-        for (int j = 0; j < mh; j++)
-          for (int i = 0; i < mw; i++) {
-            const int bx = mx * mw + i, by = my * mh + j;
-            const int16_t* blk;
-            if (bx < k.wblocks && by < k.hblocks) {
-              blk = coefs[c] + ((size_t)by * k.wblocks + bx) * 64;
-            } else {
-              memset(filler, 0, sizeof filler);
-              filler[0] = (int16_t)last_dc;
-              blk = filler;
-            }
-            last_dc = blk[0];
-            code_block(bp, blk, pred[c], cb[c == 0 ? 0 : 2], cb[c == 0 ? 1 : 3]);
-          }
-      }
-    }
-  bp.finish();
-}
+// (There is no host entropy coder: every stream is coded by huffman.cu on the device.)
 
 int jpeg_finish_stream(const JpegEncodeJob& job, const void* icc, size_t icc_size, const char* comment,
                        std::vector<uint8_t>* out) {
-  const JpegFrame& f = job.frame;
-  const size_t head_cap = jpeg_head_capacity(icc_size, comment);
-  out->clear();
-  out->reserve(head_cap + 2 + (job.h_scan_bytes ? job.h_scan_bytes[3] : f.total_blocks() * 24));
-  out->resize(head_cap);
-  ByteSink head(out->data(), head_cap);
-  write_headers(f, icc, icc_size, comment, head);
-  if (!head.ok()) return fail(E_ERROR, "JPEG header of %zu bytes exceeds its bound of %zu", head.size(), head_cap);
-  out->resize(head.size());
-  if (job.h_scan_bytes) {
-    if (job.h_scan_bytes[4] || !job.h_scan)
-      return fail(E_MEM, "entropy-coded segment exceeds the device scan buffer (%zu bytes)", job.scan_capacity);
-    out->insert(out->end(), job.h_scan, job.h_scan + job.h_scan_bytes[3]);
-  } else {
-    const int16_t* c[3] = {job.h_coefs[0], job.h_coefs[1], job.h_coefs[2]};
-    jpeg_host_entropy(f, c, out);
-  }
-  out->push_back(0xFF);
-  out->push_back(0xD9);
+  if (!job.h_scan_bytes) return fail(E_ERROR, "jpeg_finish_stream called before the device entropy coder ran");
+  out->resize(jpeg_head_capacity(icc_size, comment) + job.h_scan_bytes[3] + 2);
+  size_t n = 0;
+  const int rc = jpeg_finish_stream_into(job, icc, icc_size, comment, out->data(), out->size(), &n);
+  if (rc) return rc;
+  out->resize(n);
   return E_OK;
 }
 
