@@ -210,7 +210,7 @@ UHDR_API uhdr_error_info_t uhdr_enc_set_raw_image(uhdr_codec_private_t* enc, uhd
   DevImage d;
   int rc = upload_image(h->codec.ws(), *img, &d);
   if (rc) return from_rc(rc);
-  if (cudaStreamSynchronize(h->codec.ws().stream()) != cudaSuccess) return err(UHDR_CODEC_ERROR, "upload failed");
+  if (h->codec.ws().sync() != E_OK) return err(UHDR_CODEC_ERROR, "upload failed");
   h->raw[intent] = d;
   h->codec.ws().set_floor();  // inputs stay resident; per-encode scratch is recycled above them
   return ok();

@@ -1,6 +1,7 @@
 #include "runtime.h"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <atomic>
 #include <cstdio>
 #include <new>
@@ -203,6 +204,7 @@ Workspace::~Workspace() {
   }
   for (auto& s : spans_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
+  if (sync_ev_) cudaEventDestroy(sync_ev_);
 }
 int Workspace::init() {
   if (stream_) return E_OK;
@@ -212,8 +214,21 @@ int Workspace::init() {
   CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   return E_OK;
 }
+// A host thread waiting for its stream normally spins (lowest latency).  With many handles per GPU and several GPUs
+// per host that is one busy core per waiting thread; UHDR_B200_BLOCKING_SYNC=1 makes the wait a sleep on an event
+// created with cudaEventBlockingSync (a few tens of microseconds more per wait, no core burnt).
+static bool blocking_sync_wanted() {
+  static const bool on = [] { const char* e = getenv("UHDR_B200_BLOCKING_SYNC"); return e && *e && *e != '0'; }();
+  return on;
+}
 int Workspace::sync() {
-  CUDA_TRY(cudaStreamSynchronize(stream()));
+  if (blocking_sync_wanted()) {
+    if (!sync_ev_) CUDA_TRY(cudaEventCreateWithFlags(&sync_ev_, cudaEventBlockingSync | cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(sync_ev_, stream()));
+    CUDA_TRY(cudaEventSynchronize(sync_ev_));
+  } else {
+    CUDA_TRY(cudaStreamSynchronize(stream()));
+  }
   if (!spans_.empty()) t_collect();
   return E_OK;
 }

@@ -109,6 +109,7 @@ class Workspace {
   Arena dev_{false}, host_{true};
   cudaStream_t stream_ = nullptr;
   cudaStream_t ext_stream_ = nullptr;
+  cudaEvent_t sync_ev_ = nullptr;   // UHDR_B200_BLOCKING_SYNC=1: sync() sleeps on this event instead of spinning
   bool ext_stream_set_ = false;
   const float* luts_ = nullptr;
   int device_ = -1;
