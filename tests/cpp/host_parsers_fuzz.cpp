@@ -63,6 +63,61 @@ static int single(const uint8_t* d, size_t n) {
   return jpeg_host_decode_coefs(d, n, h, coefs) ? 3 : 0;
 }
 
+// the heap-free writers with exact-size heap buffers: ISO 21496-1 block and JPEG/R assembly at every capacity from 0 up
+// to what they need (too small: an error, never a write past the end), and a header with more APPn markers than the
+// fixed marker list keeps
+static int writers(const uint8_t* d, size_t n) {
+  size_t po, pl, go, gl;
+  if (split_jpegr(d, n, &po, &pl, &go, &gl)) return 1;
+  uhdr_gainmap_metadata_t md;
+  memset(&md, 0, sizeof md);
+  for (int i = 0; i < 3; i++) {
+    md.max_content_boost[i] = 3.5f + i; md.min_content_boost[i] = 0.9f; md.gamma[i] = 1.0f + 0.1f * i;
+    md.offset_sdr[i] = md.offset_hdr[i] = 1.0f / 64;
+  }
+  md.hdr_capacity_min = 1.0f; md.hdr_capacity_max = 5.5f; md.use_base_cg = 1;
+  size_t need = 0;
+  {
+    uint8_t big[kIsoMetadataMaxBytes];
+    if (iso_encode_metadata(md, big, sizeof big, &need)) return 2;
+  }
+  int refused = 0;
+  for (size_t cap = 0; cap <= need; cap++) {
+    uint8_t* b = (uint8_t*)malloc(cap ? cap : 1);
+    size_t got = 0;
+    const int rc = iso_encode_metadata(md, b, cap, &got);
+    if (rc) refused++;
+    else if (cap != need || got != need) return 3;
+    free(b);
+  }
+  if (refused != (int)need) return 4;
+  JpegPieces pb, pg;
+  pb.head = d + po; pb.head_len = pl; pb.scan = nullptr; pb.scan_len = 0; pb.whole = true;
+  pg.head = d + go; pg.head_len = gl; pg.scan = nullptr; pg.scan_len = 0; pg.whole = true;
+  std::vector<uint8_t> full(n + 4096);
+  size_t out_n = 0;
+  if (assemble_jpegr(pb, pg, nullptr, 0, md, full.data(), full.size(), &out_n)) return 5;
+  for (size_t cap : {(size_t)0, (size_t)1, (size_t)100, out_n / 2, out_n - 1, out_n}) {
+    uint8_t* b = (uint8_t*)malloc(cap ? cap : 1);
+    size_t got = 0;
+    const int rc = assemble_jpegr(pb, pg, nullptr, 0, md, b, cap, &got);
+    if ((cap < out_n) != (rc != 0)) return 6;
+    if (!rc && memcmp(b, full.data(), out_n)) return 7;
+    free(b);
+  }
+  // 100 APP11 markers in front of a header: the list keeps its first kMax, the walk still finds SOF / SOS
+  std::vector<uint8_t> many(d + po, d + po + 2);
+  for (int i = 0; i < 100; i++) { const uint8_t m[8] = {0xFF, 0xEB, 0x00, 0x06, 'a', 'b', 'c', (uint8_t)i}; many.insert(many.end(), m, m + 8); }
+  many.insert(many.end(), d + po + 2, d + po + pl);
+  uint8_t* mp = (uint8_t*)malloc(many.size());
+  memcpy(mp, many.data(), many.size());
+  JpegHeader h;
+  const int hrc = jpeg_read_header(mp, many.size(), &h);
+  const bool ok = !hrc && h.markers.size() <= (size_t)JpegMarkerList::kMax && h.frame.width > 0;
+  free(mp);
+  return ok ? 0 : 8;
+}
+
 int main(int argc, char** argv) {
   FILE* f = fopen(argv[1], "rb");
   std::vector<uint8_t> good;
@@ -75,6 +130,14 @@ int main(int argc, char** argv) {
     const int rc = single(p, good.size());
     free(p);
     printf("single rc=%d\nharness done\n", rc);
+    return 0;
+  }
+  if (argc > 2 && !strcmp(argv[2], "writers")) {
+    uint8_t* p = (uint8_t*)malloc(good.size());
+    memcpy(p, good.data(), good.size());
+    const int rc = writers(p, good.size());
+    free(p);
+    printf("writers rc=%d\nharness done\n", rc);
     return 0;
   }
   std::mt19937 rs(atoi(argv[2]));

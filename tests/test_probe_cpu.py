@@ -158,6 +158,10 @@ def test_host_parsers_under_sanitizers(oracle_libs, tmp_path):
     r = subprocess.run([exe, str(seed), "7", "6000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "harness done" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-2000:]
+    # the heap-free writers (fixed-capacity sinks) at every capacity, and a header with more APPn markers than the list keeps
+    r = subprocess.run([exe, str(seed), "writers"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "writers rc=0" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+    assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-2000:]
     # regression (round-1 advisor finding): a DHT table that no scan component selects may be malformed
     # (libjpeg derives tables lazily, so such a file is legal); the table builders must never see it.
     # Gray JPEG using tables DC0/AC0 + an extra DC table id 1 whose 255 one-bit codes describe no prefix code.
