@@ -71,7 +71,9 @@ __device__ __forceinline__ double log2_core(float q, const double2* __restrict__
 //   q = RN(a*y);  r = a - b*q (exact in the fma);  q' = RN(q + r*y)
 // q is within one ulp of a/b, so q + r*y differs from a/b by less than 2^-51 ulp before rounding; with a 24-bit
 // divisor a/b stays at least 2^-25 ulp away from every rounding boundary of a double (|A*2^k - B*(2n+1)| >= 1 for
-// integers A < 2^53, B < 2^24), hence q' = RN(a/b): the same double the division returns, bit for bit.
+// integers A < 2^53, B < 2^24), hence q' = RN(a/b): the same double the division returns, bit for bit.  (No underflow:
+// a is exactly 0 or at least 2^-52 * |log2_min| resp. log2(1 + 2^-23) in magnitude.  tests/test_exact_quotient_cpu.py
+// runs the three operations against the hardware division on a few million operand pairs.)
 __device__ __forceinline__ float encode_gain_norm(double log2_gain, const GainmapGenParams& p) {
   const double a = log2_gain - (double)p.log2_min;
   const double b = (double)(p.log2_max - p.log2_min);
