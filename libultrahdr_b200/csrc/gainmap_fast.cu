@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(192) k_affine_q(const AffineParams p, const Ga
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dj));
     rc[j] = __fmaf_rn(r, __fmaf_rn(-dj, r, 1.0f), r);
     const float gmax = fmaxf(fabsf(mn[j]), fabsf(s_mm[3 + c])) + 1.0f;
-    thr[j] = (kLg2Abs + gmax * kLg2Rel) * (255.0f * rc[j] * 1.0001f) + kAffineRound;
+    thr[j] = (kLg2Abs + gmax * kLg2Rel) * (255.0f * fabsf(rc[j]) * 1.0001f) + kAffineRound;   // |rc|: hints can turn the range around
   }
   const V2 mnv[2] = {v2(mn[0], mn[1]), v2(mn[2], mn[3])}, ndv[2] = {v2(nd[0], nd[1]), v2(nd[2], nd[3])};
   const V2 rcv[2] = {v2(rc[0], rc[1]), v2(rc[2], rc[3])};
